@@ -1,0 +1,163 @@
+"""Pin the oracle against the LIVE reference and mint golden fixtures.
+
+Run in the build container only (it imports /root/reference, which does not
+exist on the GPU box):
+
+    python oracle/make_golden.py            # writes tests/golden/*.npz
+
+For each case it (1) builds the reference ``Model`` (build_model.py:7-34) from
+the same config dict, (2) asserts that ``doc2tex_b200.synth.make_state_dict``
+produces exactly the reference's state_dict schema and loads it with
+``strict=True``, (3) runs the reference and the oracle on the same seeded
+images, asserts they agree, and (4) stores the REFERENCE's outputs as small
+fixtures.  tests/test_oracle_golden.py re-checks the oracle against them, and
+the GPU parity tests check the engine against them.
+"""
+from __future__ import annotations
+
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+
+from doc2tex_b200 import synth  # noqa: E402
+from oracle import oracle_model as om  # noqa: E402
+
+from doc2tex.modules.build_model import Model  # noqa: E402  (reference)
+from doc2tex.tools.beam import Beam  # noqa: E402  (reference)
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+LOGIT_STEPS = [0, 1, 2, 10, 75, 150]
+
+
+def ref_model(cfg, sd):
+    m = Model(copy.deepcopy(cfg)).eval()
+    ref_sd = m.state_dict()
+    assert set(ref_sd.keys()) == set(sd.keys()), set(ref_sd.keys()) ^ set(sd.keys())
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(sd[k].shape) and v.dtype == sd[k].dtype, k
+    # fixed buffers must be reproduced exactly by the synth restatement
+    for k in (synth.SEQ + "pos_embed", synth.PRED + "pos_enc.pe"):
+        if k in ref_sd:
+            assert torch.equal(ref_sd[k], sd[k]), k
+    m.load_state_dict(sd, strict=True)
+    return m
+
+
+def ref_beam(m, ctx1, beam_size, max_len):
+    """Reference forward_beam with a fresh Beam (demo semantics)."""
+    head = m.predicter.Prediction
+    head.beam = Beam(ignore_w=0, start_w=1, stop_w=2, max_len=max_len, device="cpu")
+    seq, score = head.forward_beam(ctx1, beam_size)
+    return seq[0].tolist(), float(score)
+
+
+def margins(logits):
+    top2 = torch.topk(logits, 2, dim=-1).values
+    return (top2[..., 0] - top2[..., 1])
+
+
+def tfm_case(name, H, W, B, end_bias, beam_imgs):
+    cfg = synth.make_config("TFM")
+    sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias)
+    img = synth.make_images(B, H, W, seed=2024)
+    m = ref_model(cfg, sd)
+    out = {"end_bias": np.array(np.nan if end_bias is None else end_bias)}
+    with torch.no_grad():
+        ctx_ref, shape, pad = m.forward_encoder(img)
+        taps = {}
+        ctx_or, grid, pad_o = om.encoder_forward(sd, img, taps=taps)
+        assert tuple(shape) == tuple(grid) and tuple(pad) == tuple(pad_o)
+        d = (ctx_ref - ctx_or).abs().max().item()
+        print(f"[{name}] ctx ref-vs-oracle max abs diff {d:.3e}")
+        assert d <= 1e-5
+        out["ctx"] = ctx_ref.numpy()
+        out["grid"] = np.array(grid)
+        out["pad"] = np.array(pad)
+        for k, v in taps.items():  # per-stage summaries to localise an engine mismatch
+            flat = v.flatten()
+            idx = torch.linspace(0, flat.numel() - 1, 64).long()
+            out[f"tap_{k}_shape"] = np.array(v.shape)
+            out[f"tap_{k}_stats"] = np.array([flat.mean().item(), flat.abs().max().item(), flat.std().item()])
+            out[f"tap_{k}_samples"] = flat[idx].numpy()
+
+        text = torch.full((B, 1), 1, dtype=torch.long)
+        ids_ref, logits_ref, _ = m(img, text, is_train=False, is_test=True)
+        head = om.TFMHead(sd, max_seq_len=150)
+        ids_or, logits_or, gen_or = head.greedy(ctx_or, is_test=True)
+        assert torch.equal(ids_ref, ids_or), "greedy ids differ between reference and oracle"
+        d = (logits_ref - logits_or).abs().max().item()
+        print(f"[{name}] greedy steps {ids_ref.shape[1]} logits max abs diff {d:.3e}; "
+              f"min top1-top2 margin {margins(logits_ref).min().item():.3e}")
+        assert d <= 1e-4
+        out["greedy_ids"] = ids_ref.numpy()
+        out["greedy_gen"] = gen_or.numpy()
+        steps = [s for s in LOGIT_STEPS if s < logits_ref.shape[1]]
+        out["greedy_logit_steps"] = np.array(steps)
+        out["greedy_logits"] = logits_ref[:, steps, :].numpy()
+        out["greedy_margin"] = margins(logits_ref).numpy()
+
+        seqs, scores, traces = [], [], []
+        for i in range(beam_imgs):
+            s_ref, sc_ref = ref_beam(m, ctx_ref[i:i + 1], 5, 150)
+            tr = []
+            s_or, sc_or = head.beam(ctx_or[i:i + 1], 5, trace=tr)
+            assert s_ref == s_or, f"beam seq differs for image {i}"
+            assert abs(sc_ref - sc_or) <= 1e-3 * max(1.0, abs(sc_ref)), (sc_ref, sc_or)
+            print(f"[{name}] beam img {i}: len {len(s_ref)} score {sc_ref:.4f} steps {len(tr)}")
+            seqs.append(s_ref); scores.append(sc_ref); traces.append(tr)
+        if beam_imgs:
+            L = max(len(s) for s in seqs)
+            out["beam_seq"] = np.array([s + [-1] * (L - len(s)) for s in seqs])
+            out["beam_len"] = np.array([len(s) for s in seqs])
+            out["beam_score"] = np.array(scores, dtype=np.float64)
+            T = max(len(t) for t in traces)
+            par = np.full((beam_imgs, T, 5), -1, dtype=np.int64)
+            wrd = np.full((beam_imgs, T, 5), -1, dtype=np.int64)
+            sco = np.zeros((beam_imgs, T, 5), dtype=np.float32)
+            for i, t in enumerate(traces):
+                for s, (p, w, sc) in enumerate(t):
+                    par[i, s, :len(p)] = p; wrd[i, s, :len(w)] = w; sco[i, s, :len(sc)] = sc
+            out["beam_parents"], out["beam_words"], out["beam_scores"] = par, wrd, sco
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+
+
+def attn_case(name, H, W, B, end_bias):
+    cfg = synth.make_config("Attnv2")
+    sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias)
+    img = synth.make_images(B, H, W, seed=2024)
+    m = ref_model(cfg, sd)
+    with torch.no_grad():
+        text = torch.zeros(B, 151, dtype=torch.long)
+        ids_ref, probs_ref, _ = m(img, text, is_train=False, is_test=True)
+        ctx_or, _, _ = om.encoder_forward(sd, img)
+        ids_or, probs_or = om.AttnV2Head(sd).greedy(ctx_or, 150, True)
+        assert torch.equal(ids_ref, ids_or)
+        d = (probs_ref - probs_or).abs().max().item()
+        print(f"[{name}] attnv2 logits max abs diff {d:.3e}; nonzero steps "
+              f"{int((probs_ref.abs().sum(-1) > 0).sum(1).max())}")
+        assert d <= 1e-4
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), ids=ids_ref.numpy(),
+                        end_bias=np.array(np.nan if end_bias is None else end_bias),
+                        logit_steps=np.array(LOGIT_STEPS), logits=probs_ref[:, LOGIT_STEPS, :].numpy(),
+                        margin=margins(probs_ref).numpy())
+
+
+if __name__ == "__main__":
+    torch.manual_seed(0)
+    os.makedirs(GOLD, exist_ok=True)
+    print("torch", torch.__version__, "threads", torch.get_num_threads())
+    tfm_case("tfm_64x256_natural", 64, 256, 2, None, 2)
+    tfm_case("tfm_64x256_full", 64, 256, 2, -1e4, 2)       # END suppressed: full 151 steps
+    tfm_case("tfm_64x256_end15", 64, 256, 2, 1.5, 2)       # 3 beams complete, 2 run out of steps
+    tfm_case("tfm_64x256_end20", 64, 256, 2, 2.0, 2)       # all 5 beams complete by step 1
+    tfm_case("tfm_96x384_full", 96, 384, 1, -1e4, 1)
+    attn_case("attnv2_64x256_natural", 64, 256, 2, None)
+    attn_case("attnv2_64x256_full", 64, 256, 2, -1e4)
+    attn_case("attnv2_64x256_end", 64, 256, 2, 3.0)
