@@ -1,0 +1,294 @@
+// Host side of the decode loops (included at the end of engine.cu).
+//
+// One decode step = a fixed kernel sequence that reads the step index from device memory, so the
+// same CUDA graph is replayed for every step; the host only polls a pinned counter every few steps
+// for the early-exit conditions of the reference (tfm.py:138-140, 174).
+
+namespace {
+
+constexpr int TFM_PAD = 0, TFM_GO = 1, TFM_END = 2;  // TFMLabelConverter (tfm_converter.py:8)
+constexpr int POLL_EVERY = 8;
+
+struct TfmBuffers {
+  float *crosskv = nullptr, *selfkv = nullptr;
+  float *x = nullptr, *x2 = nullptr, *q = nullptr, *att = nullptr, *ffn = nullptr, *logits = nullptr;
+  int *tokens = nullptr, *anc = nullptr, *n_live = nullptr, *n_done = nullptr, *finished = nullptr;
+  int *done_seq = nullptr, *done_len = nullptr, *ended = nullptr, *counters = nullptr, *trace = nullptr;
+  float *scores = nullptr, *done_score = nullptr, *trace_score = nullptr, *logits_out = nullptr;
+  long long* ids = nullptr;
+};
+
+template <typename T>
+int pool_get(d2t_engine* e, T** out, size_t n) {
+  cudaError_t st = cudaSuccess;
+  *out = (T*)e->dec_pool.get(n * sizeof(T), &st);
+  if (!*out) return e->fail(D2T_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(st));
+  return 0;
+}
+
+int dec_linear(d2t_engine* e, ConvGemm p, cudaStream_t s) { return run_contraction(e, p, nullptr, D2T_PREC_FP32, s); }
+
+int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long row_stride, const int* anc,
+                      long long anc_parity, int anc_ld, int rows_per_src, const int* step, int n_fixed, int smem_ld,
+                      float* out, int R, cudaStream_t s) {
+  const int heads = e->cfg.dec_heads, D = e->cfg.hidden;
+  const size_t smem = (size_t)heads * smem_ld * sizeof(float);
+  decode_attention_kernel<32><<<R, heads * 32, smem, s>>>(q, D, kv, row_stride, 2 * D, anc, anc_parity, anc_ld,
+                                                          rows_per_src, step, n_fixed, smem_ld, out, D);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  return 0;
+}
+
+// One decoder step for R rows (tfm.py:125-135 / 152-169 with a KV cache):
+// nn.TransformerDecoderLayer defaults = post-norm, ReLU, eps 1e-5.
+int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok, int beam, int T, bool want_logits,
+                     cudaStream_t s) {
+  const d2t_config& c = e->cfg;
+  const int D = c.hidden, F = c.dec_ff, V = c.vocab, L = T + 1;
+  int* step = b.counters;
+  const long long par = beam > 0 ? (long long)R * L : 0;
+  int rc;
+  embed_tokens_kernel<<<(R * D / 4 + 255) / 256, 256, 0, s>>>(b.tokens, L, step, par, e->dev[PRED + "word_embed.weight"],
+                                                            e->dev[PRED + "pos_enc.pe"], b.x, R, D, sqrtf((float)D));
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  for (int l = 0; l < c.dec_layers; ++l) {
+    const std::string p = PRED + "model.layers." + std::to_string(l) + ".";
+    float* selfkv = b.selfkv + (size_t)l * R * T * 2 * D;
+    const float* crosskv = b.crosskv + (size_t)l * B * ntok * 2 * D;
+    // self-attention: in_proj (q -> b.q, k|v -> cache slot t), attention over the prefix, out_proj + residual, norm1
+    {
+      ConvGemm g = linear_params(b.x, e->dev[p + "self_attn.in_proj_weight"], e->dev[p + "self_attn.in_proj_bias"], b.q, R, 3 * D, D);
+      g.ldc = D; g.n_split = D; g.out2 = selfkv; g.ldc2 = T * 2 * D; g.dyn = step; g.dyn_mul2 = 2 * D;
+      if ((rc = dec_linear(e, g, s))) return rc;
+    }
+    if ((rc = enqueue_attention(e, b.q, selfkv, (long long)T * 2 * D, beam > 0 ? b.anc : nullptr, par, L,
+                                beam > 0 ? beam : 1, step, 0, T, b.att, R, s))) return rc;
+    {
+      ConvGemm g = linear_params(b.att, e->dev[p + "self_attn.out_proj.weight"], e->dev[p + "self_attn.out_proj.bias"], b.x2, R, D, D);
+      g.res = b.x; g.ldr = D;
+      if ((rc = dec_linear(e, g, s))) return rc;
+    }
+    if ((rc = layernorm(e, b.x2, e->dev[p + "norm1.weight"], e->dev[p + "norm1.bias"], b.x, R, D, 1e-5f, s))) return rc;
+    // cross-attention over the encoder memory (K/V projected once per image, shared by its beams), norm2
+    {
+      ConvGemm g = linear_params(b.x, e->dev[p + "multihead_attn.in_proj_weight"], e->dev[p + "multihead_attn.in_proj_bias"], b.q, R, D, D);
+      if ((rc = dec_linear(e, g, s))) return rc;
+    }
+    if ((rc = enqueue_attention(e, b.q, crosskv, (long long)ntok * 2 * D, nullptr, 0, 0, beam > 0 ? beam : 1, nullptr,
+                                ntok, ntok, b.att, R, s))) return rc;
+    {
+      ConvGemm g = linear_params(b.att, e->dev[p + "multihead_attn.out_proj.weight"], e->dev[p + "multihead_attn.out_proj.bias"], b.x2, R, D, D);
+      g.res = b.x; g.ldr = D;
+      if ((rc = dec_linear(e, g, s))) return rc;
+    }
+    if ((rc = layernorm(e, b.x2, e->dev[p + "norm2.weight"], e->dev[p + "norm2.bias"], b.x, R, D, 1e-5f, s))) return rc;
+    // feed-forward, norm3
+    {
+      ConvGemm g = linear_params(b.x, e->dev[p + "linear1.weight"], e->dev[p + "linear1.bias"], b.ffn, R, F, D);
+      g.act = ACT_RELU;
+      if ((rc = dec_linear(e, g, s))) return rc;
+    }
+    {
+      ConvGemm g = linear_params(b.ffn, e->dev[p + "linear2.weight"], e->dev[p + "linear2.bias"], b.x2, R, D, F);
+      g.res = b.x; g.ldr = D;
+      if ((rc = dec_linear(e, g, s))) return rc;
+    }
+    if ((rc = layernorm(e, b.x2, e->dev[p + "norm3.weight"], e->dev[p + "norm3.bias"], b.x, R, D, 1e-5f, s))) return rc;
+  }
+  {
+    ConvGemm g = linear_params(b.x, e->dev[PRED + "proj.weight"], e->dev[PRED + "proj.bias"], b.logits, R, V, D);
+    if ((rc = dec_linear(e, g, s))) return rc;
+  }
+  if (beam > 0) {
+    BeamState st{};
+    st.tokens = b.tokens; st.anc = b.anc; st.scores = b.scores; st.n_live = b.n_live; st.n_done = b.n_done;
+    st.finished = b.finished; st.done_seq = b.done_seq; st.done_len = b.done_len; st.done_score = b.done_score;
+    st.counters = b.counters; st.trace = b.trace; st.trace_score = b.trace_score;
+    st.L = L; st.beam = beam; st.B = B; st.V = V; st.end_id = TFM_END; st.max_steps = T;
+    beam_step_kernel<<<B, 256, (size_t)beam * V * sizeof(float), s>>>(b.logits, st);
+  } else {
+    greedy_pick_kernel<<<R, 128, 0, s>>>(b.logits, V, step, b.tokens, L, b.ids, T, want_logits ? b.logits_out : nullptr,
+                                         b.ended, b.counters + 1, b.counters + 2, R, TFM_END);
+  }
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  advance_step_kernel<<<1, 1, 0, s>>>(step);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  return 0;
+}
+
+int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int max_steps, bool stop_early,
+               bool want_logits, TfmBuffers* bufs, int* steps_out, cudaStream_t s) {
+  const d2t_config& c = e->cfg;
+  if (c.head != D2T_HEAD_TFM) return e->fail(D2T_ERR_STATE, "engine was not configured with the TFM head");
+  if (!e->finalized) return e->fail(D2T_ERR_STATE, "decode before d2t_finalize_weights");
+  if (!ctx || B <= 0 || ntok <= 0 || max_steps <= 0) return e->fail(D2T_ERR_INVALID, "bad decode arguments");
+  if (max_steps > c.max_seq_len + 1)
+    return e->fail(D2T_ERR_INVALID, "max_steps %d exceeds max_seq_len+1 = %d", max_steps, c.max_seq_len + 1);
+  if (beam > BEAM_MAX) return e->fail(D2T_ERR_UNSUPPORTED, "beam size %d > %d", beam, BEAM_MAX);
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  const int D = c.hidden, F = c.dec_ff, V = c.vocab, T = max_steps, L = T + 1;
+  const int R = beam > 0 ? B * beam : B;
+  const int nl = c.dec_layers;
+  e->dec_pool.release_all();
+  TfmBuffers& b = *bufs;
+  int rc;
+  if ((rc = pool_get(e, &b.crosskv, (size_t)nl * B * ntok * 2 * D))) return rc;
+  if ((rc = pool_get(e, &b.selfkv, (size_t)nl * R * T * 2 * D))) return rc;
+  if ((rc = pool_get(e, &b.x, (size_t)R * D))) return rc;
+  if ((rc = pool_get(e, &b.x2, (size_t)R * D))) return rc;
+  if ((rc = pool_get(e, &b.q, (size_t)R * D))) return rc;
+  if ((rc = pool_get(e, &b.att, (size_t)R * D))) return rc;
+  if ((rc = pool_get(e, &b.ffn, (size_t)R * F))) return rc;
+  if ((rc = pool_get(e, &b.logits, (size_t)R * V))) return rc;
+  if ((rc = pool_get(e, &b.counters, 4))) return rc;
+  const int nbuf = beam > 0 ? 2 : 1;
+  if ((rc = pool_get(e, &b.tokens, (size_t)nbuf * R * L))) return rc;
+  if (beam > 0) {
+    if ((rc = pool_get(e, &b.anc, (size_t)2 * R * L))) return rc;
+    if ((rc = pool_get(e, &b.scores, (size_t)R))) return rc;
+    if ((rc = pool_get(e, &b.n_live, (size_t)B))) return rc;
+    if ((rc = pool_get(e, &b.n_done, (size_t)B))) return rc;
+    if ((rc = pool_get(e, &b.finished, (size_t)B))) return rc;
+    if ((rc = pool_get(e, &b.done_seq, (size_t)R * L))) return rc;
+    if ((rc = pool_get(e, &b.done_len, (size_t)R))) return rc;
+    if ((rc = pool_get(e, &b.done_score, (size_t)R))) return rc;
+    if ((rc = pool_get(e, &b.trace, (size_t)B * T * beam * 2))) return rc;
+    if ((rc = pool_get(e, &b.trace_score, (size_t)B * T * beam))) return rc;
+    CUDA_TRY(e, cudaMemsetAsync(b.trace, 0xFF, (size_t)B * T * beam * 2 * sizeof(int), s));
+    CUDA_TRY(e, cudaMemsetAsync(b.trace_score, 0, (size_t)B * T * beam * sizeof(float), s));
+  } else {
+    if ((rc = pool_get(e, &b.ended, (size_t)R))) return rc;
+    if ((rc = pool_get(e, &b.ids, (size_t)R * T))) return rc;
+    CUDA_TRY(e, cudaMemsetAsync(b.ids, 0, (size_t)R * T * sizeof(long long), s));
+    if (want_logits) {
+      if ((rc = pool_get(e, &b.logits_out, (size_t)R * T * V))) return rc;
+      CUDA_TRY(e, cudaMemsetAsync(b.logits_out, 0, (size_t)R * T * V * sizeof(float), s));
+    }
+  }
+  init_decode_state_kernel<<<grid_for((long long)nbuf * R * L, 256, e->num_sms), 256, 0, s>>>(
+      b.tokens, (long long)nbuf * R * L, L, R, beam, TFM_GO, b.anc, L, b.scores, b.n_live, b.n_done, b.finished,
+      b.ended, b.counters);
+  set_go_tokens_kernel<<<(R + 255) / 256, 256, 0, s>>>(b.tokens, L, beam > 0 ? (long long)R * L : 0, R, TFM_GO);
+  e->launches += 2;
+  CUDA_TRY(e, cudaGetLastError());
+  // cross-attention K/V of the encoder memory, once per image and layer (the reference re-projects
+  // them at every step: nn.MultiheadAttention inside tfm.py:130 / :165)
+  for (int l = 0; l < nl; ++l) {
+    const std::string p = PRED + "model.layers." + std::to_string(l) + ".multihead_attn.";
+    ConvGemm g = linear_params(ctx, e->dev[p + "in_proj_weight"] + (size_t)D * D, e->dev[p + "in_proj_bias"] + D,
+                               b.crosskv + (size_t)l * B * ntok * 2 * D, B * ntok, 2 * D, D);
+    if ((rc = dec_linear(e, g, s))) return rc;
+  }
+
+  // ---- step graph ----
+  cudaGraphExec_t exec = nullptr;
+  int nodes = 0;
+  if (c.use_graphs) {
+    std::vector<long long> key = {(long long)R, B, ntok, beam, T, want_logits ? 1 : 0};
+    const void* ptrs[] = {b.crosskv, b.selfkv, b.x, b.x2, b.q, b.att, b.ffn, b.logits, b.counters, b.tokens, b.anc,
+                          b.scores, b.n_live, b.n_done, b.finished, b.done_seq, b.done_len, b.done_score, b.trace,
+                          b.trace_score, b.ended, b.ids, b.logits_out};
+    for (const void* q : ptrs) key.push_back((long long)(uintptr_t)q);
+    for (auto& g : e->graphs) if (g.key == key) { exec = g.exec; nodes = g.nodes; }
+    if (!exec) {
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(e, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const int64_t before = e->launches;
+      rc = enqueue_tfm_step(e, b, R, B, ntok, beam, T, want_logits, s);
+      nodes = (int)(e->launches - before);
+      e->launches = before;
+      cudaError_t st = cudaStreamEndCapture(s, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(st));
+      st = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(st));
+      if (e->graphs.size() >= 16) {  // bounded cache
+        cudaGraphExecDestroy(e->graphs.front().exec);
+        e->graphs.erase(e->graphs.begin());
+      }
+      d2t_engine::GraphEntry ge; ge.key = key; ge.exec = exec; ge.nodes = nodes;
+      e->graphs.push_back(ge);
+    }
+  }
+  int executed = 0, done_step = -1;
+  for (int t = 0; t < T; ++t) {
+    if (exec) {
+      CUDA_TRY(e, cudaGraphLaunch(exec, s));
+      e->launches += nodes;
+    } else if ((rc = enqueue_tfm_step(e, b, R, B, ntok, beam, T, want_logits, s))) {
+      return rc;
+    }
+    executed = t + 1;
+    if (stop_early && (executed % POLL_EVERY == 0) && executed < T) {
+      CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(e, cudaStreamSynchronize(s));
+      if (e->h_counters[2] >= 0) break;
+    }
+  }
+  CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(e, cudaStreamSynchronize(s));
+  done_step = e->h_counters[2];
+  *steps_out = (stop_early && done_step >= 0) ? done_step : executed;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int d2t_decode_greedy(d2t_engine* e, const float* ctx, int B, int ntok, int max_steps, int stop_on_all_eos,
+                      int64_t* ids, float* logits, int* steps_out, d2t_stream stream) {
+  if (!e) return D2T_ERR_INVALID;
+  if (!ids || !steps_out) return e->fail(D2T_ERR_INVALID, "ids_dev and steps_out are required");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  WorkStream ws(e, (cudaStream_t)stream);
+  cudaStream_t s = ws.get();
+  TfmBuffers b;
+  int steps = 0;
+  if (int rc = tfm_decode(e, ctx, B, ntok, 0, max_steps, stop_on_all_eos != 0, logits != nullptr, &b, &steps, s)) return rc;
+  CUDA_TRY(e, cudaMemcpyAsync(ids, b.ids, (size_t)B * max_steps * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  if (logits)
+    CUDA_TRY(e, cudaMemcpyAsync(logits, b.logits_out, (size_t)B * max_steps * e->cfg.vocab * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(e, cudaStreamSynchronize(s));
+  *steps_out = steps;
+  return D2T_OK;
+}
+
+int d2t_decode_beam(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int max_steps, int64_t* best_ids,
+                    int32_t* best_len, float* best_score, int32_t* trace, float* trace_score, int* steps_out,
+                    d2t_stream stream) {
+  if (!e) return D2T_ERR_INVALID;
+  if (!best_ids || !best_len || !best_score || !steps_out) return e->fail(D2T_ERR_INVALID, "output pointers are required");
+  if (beam < 1) return e->fail(D2T_ERR_INVALID, "beam must be >= 1");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  WorkStream ws(e, (cudaStream_t)stream);
+  cudaStream_t s = ws.get();
+  TfmBuffers b;
+  int steps = 0;
+  if (int rc = tfm_decode(e, ctx, B, ntok, beam, max_steps, true, false, &b, &steps, s)) return rc;
+  BeamState st{};
+  st.tokens = b.tokens; st.anc = b.anc; st.scores = b.scores; st.n_live = b.n_live; st.n_done = b.n_done;
+  st.finished = b.finished; st.done_seq = b.done_seq; st.done_len = b.done_len; st.done_score = b.done_score;
+  st.counters = b.counters; st.L = max_steps + 1; st.beam = beam; st.B = B; st.V = e->cfg.vocab; st.end_id = TFM_END;
+  st.max_steps = max_steps;
+  // device step counter == number of executed steps == parity of the live token buffer
+  beam_finalize_kernel<<<B, 128, 0, s>>>(st, e->h_counters[0], (long long*)best_ids, max_steps, best_len, best_score);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  if (trace)
+    CUDA_TRY(e, cudaMemcpyAsync(trace, b.trace, (size_t)B * max_steps * beam * 2 * sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (trace_score)
+    CUDA_TRY(e, cudaMemcpyAsync(trace_score, b.trace_score, (size_t)B * max_steps * beam * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(e, cudaStreamSynchronize(s));
+  *steps_out = steps;
+  return D2T_OK;
+}
+
+}  // extern "C"
+
+#include "lstm_host.inl"

@@ -1,0 +1,235 @@
+// Memory-bound encoder kernels: first conv (Cin=1), max-pools, token assembly, LayerNorm,
+// and the flash-style encoder self-attention.  All activations are NHWC / row-major fp32.
+#pragma once
+#include "common.cuh"
+
+namespace d2t {
+
+// conv0_1: Conv2d(1 -> Cout, 3x3, s1, p1, bias=False) + BN(eval) + ReLU  (resnet.py:206-208).
+// K = 9 is not tensor-core work: direct conv, output-bandwidth bound.  x: [B,H,W] (NCHW with C=1),
+// out: NHWC [B,H,W,Cout].  One thread = one pixel x 4 output channels (float4 store, coalesced).
+__global__ void conv0_direct_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cout][9]*/,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    float* __restrict__ out, int B, int H, int W, int Cout) {
+  extern __shared__ float sm[];  // [9][Cout] weights, [Cout] scale, [Cout] shift
+  float* sw = sm;
+  float* ssc = sm + 9 * Cout;
+  float* ssh = ssc + Cout;
+  for (int i = threadIdx.x; i < 9 * Cout; i += blockDim.x) {
+    const int c = i % Cout, t = i / Cout;
+    sw[i] = w[c * 9 + t];
+  }
+  for (int i = threadIdx.x; i < Cout; i += blockDim.x) { ssc[i] = scale[i]; ssh[i] = shift[i]; }
+  __syncthreads();
+  const int cg = Cout / 4;
+  const long long total = (long long)B * H * W * cg;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % cg) * 4;
+    const long long pix = idx / cg;
+    const int ow = (int)(pix % W);
+    const int oh = (int)((pix / W) % H);
+    const int b = (int)(pix / ((long long)W * H));
+    const float* xb = x + (size_t)b * H * W;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh + kh - 1;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int iw = ow + kw - 1;
+        const float v = ((unsigned)ih < (unsigned)H && (unsigned)iw < (unsigned)W) ? __ldg(xb + (size_t)ih * W + iw) : 0.f;
+        const float* wr = sw + (kh * 3 + kw) * Cout + c4;
+        a0 = fmaf(v, wr[0], a0); a1 = fmaf(v, wr[1], a1); a2 = fmaf(v, wr[2], a2); a3 = fmaf(v, wr[3], a3);
+      }
+    }
+    float4 o;
+    o.x = fmaxf(a0 * ssc[c4 + 0] + ssh[c4 + 0], 0.f);
+    o.y = fmaxf(a1 * ssc[c4 + 1] + ssh[c4 + 1], 0.f);
+    o.z = fmaxf(a2 * ssc[c4 + 2] + ssh[c4 + 2], 0.f);
+    o.w = fmaxf(a3 * ssc[c4 + 3] + ssh[c4 + 3], 0.f);
+    *reinterpret_cast<float4*>(out + pix * Cout + c4) = o;
+  }
+}
+
+// MaxPool2d(kernel 2x2, stride (SH,SW), padding (PH,PW)) on NHWC; padding behaves as -inf
+// (resnet.py:97,107,120: maxpool3 is k2 s(2,1) p(0,1)).
+__global__ void maxpool2x2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W,
+                                       int C, int OH, int OW, int SH, int SW, int PH, int PW) {
+  const int c4n = C / 4;
+  const long long total = (long long)B * OH * OW * c4n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(idx % c4n) * 4;
+    long long pix = idx / c4n;
+    const int ow = (int)(pix % OW);
+    const int oh = (int)((pix / OW) % OH);
+    const int b = (int)(pix / ((long long)OW * OH));
+    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+    for (int kh = 0; kh < 2; ++kh) {
+      const int ih = oh * SH - PH + kh;
+      if ((unsigned)ih >= (unsigned)H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 2; ++kw) {
+        const int iw = ow * SW - PW + kw;
+        if ((unsigned)iw >= (unsigned)W) continue;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x + (((size_t)b * H + ih) * W + iw) * C + c4));
+        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      }
+    }
+    *reinterpret_cast<float4*>(out + pix * C + c4) = m;
+  }
+}
+
+// x[b,0,:] = cls + pos[0];  x[b,1+p,:] = tok[b,p,:] + pos[1+p]   (vit_encoder.py:255-260; pos is the
+// PREFIX slice of the max-grid table, quirk Q3).
+__global__ void assemble_tokens_kernel(const float* __restrict__ tok, const float* __restrict__ cls,
+                                       const float* __restrict__ pos, float* __restrict__ x, int B, int N, int D) {
+  const int d4n = D / 4;
+  const long long total = (long long)B * (N + 1) * d4n;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % d4n) * 4;
+    const long long r = idx / d4n;
+    const int t = (int)(r % (N + 1));
+    const int b = (int)(r / (N + 1));
+    const float4 a = (t == 0) ? *reinterpret_cast<const float4*>(cls + d)
+                              : *reinterpret_cast<const float4*>(tok + ((size_t)b * N + (t - 1)) * D + d);
+    const float4 pe = *reinterpret_cast<const float4*>(pos + (size_t)t * D + d);
+    *reinterpret_cast<float4*>(x + r * D + d) = make_float4(a.x + pe.x, a.y + pe.y, a.z + pe.z, a.w + pe.w);
+  }
+}
+
+// LayerNorm over the last dim, one warp per row, values kept in registers (D = 128 * NV4).
+// Two-pass mean / biased variance in fp32, y = (x - mean) / sqrt(var + eps) * w + b (torch semantics).
+template <int NV4>
+__global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                 float* __restrict__ y, int rows, float eps) {
+  constexpr int D = 128 * NV4;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* xr = x + (size_t)warp * D;
+  float4 v[NV4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) * (1.0f / D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const float a = v[i].x - mean, c = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+    q += (a * a + c * c) + (d * d + e * e);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / D) + eps);
+  float* yr = y + (size_t)warp * D;
+#pragma unroll
+  for (int i = 0; i < NV4; ++i) {
+    const int o = (i * 32 + lane) * 4;
+    const float4 ww = *reinterpret_cast<const float4*>(w + o);
+    const float4 bb = *reinterpret_cast<const float4*>(b + o);
+    float4 r;
+    r.x = (v[i].x - mean) * rstd * ww.x + bb.x;
+    r.y = (v[i].y - mean) * rstd * ww.y + bb.y;
+    r.z = (v[i].z - mean) * rstd * ww.z + bb.z;
+    r.w = (v[i].w - mean) * rstd * ww.w + bb.w;
+    *reinterpret_cast<float4*>(yr + o) = r;
+  }
+}
+
+// Encoder self-attention, flash style: softmax(q k^T * scale) v for one (image, head), no mask
+// (vision_transformer.py:61-81; zero-padded patch tokens attend and are attended, quirk Q4).
+// qkv: [B*N, 3*D] rows = tokens, q | k | v column blocks, head h at columns h*HD.  out: [B*N, D].
+// One thread owns one query (q and the output accumulator live in registers), keys/values stream
+// through shared memory in tiles and are read as warp broadcasts; S and P never leave the chip.
+template <int HD, int KT>
+__global__ void __launch_bounds__(128)
+encoder_attention_kernel(const float* __restrict__ qkv, float* __restrict__ out, int N, int D, float scale) {
+  __shared__ __align__(16) float Ks[KT][HD];
+  __shared__ __align__(16) float Vs[KT][HD];
+  const int heads = D / HD;
+  const int b = blockIdx.y / heads, h = blockIdx.y % heads;
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool qok = qi < N;
+  const size_t ld = 3 * (size_t)D;
+  const float* base = qkv + (size_t)b * N * ld;
+  float q[HD], acc[HD];
+#pragma unroll
+  for (int d = 0; d < HD; d += 4) {
+    const float4 v = qok ? *reinterpret_cast<const float4*>(base + (size_t)qi * ld + h * HD + d) : make_float4(0, 0, 0, 0);
+    q[d] = v.x; q[d + 1] = v.y; q[d + 2] = v.z; q[d + 3] = v.w;
+    acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
+  }
+  float mx = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < N; k0 += KT) {
+    const int kn = min(KT, N - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kn * (HD / 4); i += blockDim.x) {
+      const int r = i / (HD / 4), c = (i % (HD / 4)) * 4;
+      const float* src = base + (size_t)(k0 + r) * ld + h * HD + c;
+      *reinterpret_cast<float4*>(&Ks[r][c]) = *reinterpret_cast<const float4*>(src + D);
+      *reinterpret_cast<float4*>(&Vs[r][c]) = *reinterpret_cast<const float4*>(src + 2 * D);
+    }
+    __syncthreads();
+    for (int j0 = 0; j0 < kn; j0 += 8) {
+      float s[8];
+      float cm = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = j0 + jj;
+        float d0 = 0.f;
+        if (j < kn) {
+#pragma unroll
+          for (int d = 0; d < HD; ++d) d0 = fmaf(q[d], Ks[j][d], d0);
+          d0 *= scale;
+        } else {
+          d0 = -INFINITY;
+        }
+        s[jj] = d0;
+        cm = fmaxf(cm, d0);
+      }
+      const float nm = fmaxf(mx, cm);
+      const float corr = expf(mx - nm);  // exp(-inf) = 0 on the first chunk
+      l *= corr;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) acc[d] *= corr;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        const int j = j0 + jj;
+        if (j < kn) {
+          const float pj = expf(s[jj] - nm);
+          l += pj;
+#pragma unroll
+          for (int d = 0; d < HD; ++d) acc[d] = fmaf(pj, Vs[j][d], acc[d]);
+        }
+      }
+      mx = nm;
+    }
+  }
+  if (qok) {
+    const float inv = 1.0f / l;
+    float* o = out + ((size_t)b * N + qi) * D + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 4)
+      *reinterpret_cast<float4*>(o + d) = make_float4(acc[d] * inv, acc[d + 1] * inv, acc[d + 2] * inv, acc[d + 3] * inv);
+  }
+}
+
+// NHWC [B,H,W,C] -> NCHW [B,C,H,W] (debug taps only).
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int H, int W, int C) {
+  const long long total = (long long)B * H * W * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int w = (int)(idx % W);
+    const int h = (int)((idx / W) % H);
+    const int c = (int)((idx / ((long long)W * H)) % C);
+    const int b = (int)(idx / ((long long)W * H * C));
+    y[idx] = x[(((size_t)b * H + h) * W + w) * C + c];
+  }
+}
+
+}  // namespace d2t

@@ -1,0 +1,754 @@
+// doc2tex_b200 engine: host orchestration + C ABI (include/doc2tex_b200.h).
+//
+// One engine per (process, device).  Weights arrive by their reference state_dict keys
+// (SURVEY.md Appendix C), are folded / repacked once, and every API call enqueues hand-written
+// sm_100a kernels on the caller's stream.  There is no CPU fallback anywhere in this file.
+#include "../../include/doc2tex_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+#include "decoder_kernels.cuh"
+#include "encoder_kernels.cuh"
+#include "gemm_simt.cuh"
+#include "lstm_kernels.cuh"
+#include "gemm_tc.cuh"
+
+using namespace d2t;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct HostTensor {
+  std::vector<float> f;
+  std::vector<int64_t> shape;
+};
+
+struct ConvW {
+  float* w = nullptr;      // [Cout][KH][KW][Cin]
+  float* scale = nullptr;  // folded BN scale (or nullptr)
+  float* shift = nullptr;  // folded BN shift / bias
+  int cout = 0, cin = 0, kh = 0, kw = 0;
+  TcWeight tc;             // operand planes for the tcgen05 path (empty in fp32 mode)
+};
+
+struct Fmap {  // NHWC activation
+  float* p = nullptr;
+  int B = 0, H = 0, W = 0, C = 0;
+  size_t numel() const { return (size_t)B * H * W * C; }
+};
+
+// Caching slot allocator: cudaMalloc only the first time a size class is needed (warm-up), then reuse.
+struct SlotPool {
+  struct Slot { void* p; size_t cap; bool used; };
+  std::vector<Slot> slots;
+  size_t total = 0;
+  void* get(size_t bytes, cudaError_t* err) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    int best = -1;
+    for (int i = 0; i < (int)slots.size(); ++i)
+      if (!slots[i].used && slots[i].cap >= bytes && (best < 0 || slots[i].cap < slots[best].cap)) best = i;
+    if (best >= 0 && slots[best].cap <= bytes * 2 + (1 << 20)) { slots[best].used = true; return slots[best].p; }
+    void* p = nullptr;
+    *err = cudaMalloc(&p, bytes);
+    if (*err != cudaSuccess) return nullptr;
+    slots.push_back({p, bytes, true});
+    total += bytes;
+    return p;
+  }
+  void release(void* p) {
+    for (auto& s : slots) if (s.p == p) { s.used = false; return; }
+  }
+  void release_all() { for (auto& s : slots) s.used = false; }
+  void destroy() { for (auto& s : slots) cudaFree(s.p); slots.clear(); total = 0; }
+};
+
+struct Tap { Fmap a; bool tokens; };
+
+}  // namespace
+
+struct d2t_engine {
+  d2t_config cfg{};
+  int device = 0;
+  int num_sms = 148;
+  std::string err;
+  bool finalized = false;
+  int64_t launches = 0;
+
+  std::unordered_map<std::string, HostTensor> host;
+  std::vector<void*> owned;  // device weight allocations
+  std::map<std::string, ConvW> conv;
+  std::map<std::string, float*> dev;  // linear weights, biases, LN params, embeddings (by reference key)
+
+  SlotPool enc_pool, dec_pool;
+  bool keep_taps = false;
+  std::map<std::string, Tap> taps;
+
+  // decode graph cache
+  struct GraphEntry { std::vector<long long> key; cudaGraphExec_t exec = nullptr; int nodes = 0; };
+  std::vector<GraphEntry> graphs;
+  int* h_counters = nullptr;  // pinned [4]
+  cudaStream_t work = nullptr;   // engine-owned stream for the decode loop (the legacy default stream cannot be captured)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+
+  int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    err = buf;
+    return code;
+  }
+};
+
+int finalize_attn_extras(d2t_engine* e);
+
+#define CUDA_TRY(e, call)                                                                          \
+  do {                                                                                             \
+    cudaError_t _s = (call);                                                                       \
+    if (_s != cudaSuccess) return (e)->fail(D2T_ERR_CUDA, "%s failed: %s (%s:%d)", #call,          \
+                                            cudaGetErrorString(_s), __FILE__, __LINE__);          \
+  } while (0)
+
+// Decode loops run on the engine's own stream, ordered after the caller's stream on entry and
+// joined back on exit (RAII), so that a step can be captured into a CUDA graph even when the caller
+// is on the legacy default stream.
+struct WorkStream {
+  d2t_engine* e; cudaStream_t caller;
+  WorkStream(d2t_engine* e_, cudaStream_t c) : e(e_), caller(c) {
+    cudaEventRecord(e->ev_in, caller);
+    cudaStreamWaitEvent(e->work, e->ev_in, 0);
+  }
+  ~WorkStream() {
+    cudaEventRecord(e->ev_out, e->work);
+    cudaStreamWaitEvent(caller, e->ev_out, 0);
+  }
+  cudaStream_t get() const { return e->work; }
+};
+
+namespace {
+
+const std::string SEQ = "seqmodeler.SequenceModeling.";
+const std::string NET = SEQ + "patch_embed.backbone.ConvNet.";
+const std::string PRED = "predicter.Prediction.";
+
+int upload(d2t_engine* e, const float* src, size_t n, float** out) {
+  float* p = nullptr;
+  CUDA_TRY(e, cudaMalloc(&p, n * sizeof(float)));
+  e->owned.push_back(p);
+  CUDA_TRY(e, cudaMemcpy(p, src, n * sizeof(float), cudaMemcpyHostToDevice));
+  *out = p;
+  return 0;
+}
+
+const HostTensor* find(d2t_engine* e, const std::string& key) {
+  auto it = e->host.find(key);
+  return it == e->host.end() ? nullptr : &it->second;
+}
+
+int need(d2t_engine* e, const std::string& key, const HostTensor** t, std::vector<int64_t> shape = {}) {
+  *t = find(e, key);
+  if (!*t) return e->fail(D2T_ERR_MISSING, "state_dict tensor '%s' was not loaded", key.c_str());
+  if (!shape.empty() && (*t)->shape != shape) {
+    std::string got, want;
+    for (auto v : (*t)->shape) got += std::to_string(v) + ",";
+    for (auto v : shape) want += std::to_string(v) + ",";
+    return e->fail(D2T_ERR_INVALID, "tensor '%s' has shape (%s) expected (%s)", key.c_str(), got.c_str(), want.c_str());
+  }
+  return 0;
+}
+
+int upload_key(d2t_engine* e, const std::string& key, std::vector<int64_t> shape = {}) {
+  const HostTensor* t;
+  if (int rc = need(e, key, &t, shape)) return rc;
+  float* p;
+  if (int rc = upload(e, t->f.data(), t->f.size(), &p)) return rc;
+  e->dev[key] = p;
+  return 0;
+}
+
+// Conv2d(bias=False) + BatchNorm2d(eval): y = conv(x) * alpha + beta with alpha = gamma / sqrt(var + eps),
+// beta = bias - mean * alpha (what torch's CPU inference kernel evaluates; resnet.py:32-40, quirk Q1).
+int make_conv(d2t_engine* e, const std::string& cname, const std::string& bname, int cout, int cin, int kh, int kw) {
+  const HostTensor *w, *g, *b, *m, *v;
+  if (int rc = need(e, NET + cname + ".weight", &w, {cout, cin, kh, kw})) return rc;
+  if (int rc = need(e, NET + bname + ".weight", &g, {cout})) return rc;
+  if (int rc = need(e, NET + bname + ".bias", &b, {cout})) return rc;
+  if (int rc = need(e, NET + bname + ".running_mean", &m, {cout})) return rc;
+  if (int rc = need(e, NET + bname + ".running_var", &v, {cout})) return rc;
+  std::vector<float> packed((size_t)cout * kh * kw * cin), alpha(cout), beta(cout);
+  for (int o = 0; o < cout; ++o) {
+    for (int i = 0; i < cin; ++i)
+      for (int y = 0; y < kh; ++y)
+        for (int x = 0; x < kw; ++x)
+          packed[(((size_t)o * kh + y) * kw + x) * cin + i] = w->f[(((size_t)o * cin + i) * kh + y) * kw + x];
+    const float invstd = 1.0f / sqrtf(v->f[o] + 1e-5f);
+    alpha[o] = g->f[o] * invstd;
+    beta[o] = b->f[o] - m->f[o] * alpha[o];
+  }
+  ConvW c;
+  c.cout = cout; c.cin = cin; c.kh = kh; c.kw = kw;
+  if (int rc = upload(e, packed.data(), packed.size(), &c.w)) return rc;
+  if (int rc = upload(e, alpha.data(), cout, &c.scale)) return rc;
+  if (int rc = upload(e, beta.data(), cout, &c.shift)) return rc;
+  e->conv[cname] = c;
+  return 0;
+}
+
+int make_layer(d2t_engine* e, const std::string& name, int cin, int planes, int blocks) {
+  for (int b = 0; b < blocks; ++b) {
+    const int ci = b == 0 ? cin : planes;
+    const std::string p = name + "." + std::to_string(b);
+    if (int rc = make_conv(e, p + ".conv1", p + ".bn1", planes, ci, 3, 3)) return rc;
+    if (int rc = make_conv(e, p + ".conv2", p + ".bn2", planes, planes, 3, 3)) return rc;
+    if (b == 0 && ci != planes)
+      if (int rc = make_conv(e, p + ".downsample.0", p + ".downsample.1", planes, ci, 1, 1)) return rc;
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch helpers
+// ---------------------------------------------------------------------------------------------
+inline int grid_for(long long total, int block, int num_sms) {
+  long long g = (total + block - 1) / block;
+  const long long cap = (long long)num_sms * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+int run_contraction(d2t_engine* e, const ConvGemm& p, const TcWeight* tcw, int precision, cudaStream_t s) {
+  if (p.K % 16 != 0 || p.C % 16 != 0)
+    return e->fail(D2T_ERR_UNSUPPORTED, "contraction needs K and C multiples of 16 (K=%d C=%d)", p.K, p.C);
+  if (precision != D2T_PREC_FP32 && tcw != nullptr && tcw->ready && tc_supported(p)) {
+    cudaError_t st = launch_conv_gemm_tc(p, *tcw, precision, s, e->num_sms);
+    if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tcgen05 contraction launch failed: %s", cudaGetErrorString(st));
+    e->launches += 1;
+    return 0;
+  }
+  cudaError_t st = launch_conv_gemm_simt(p, s, e->num_sms);
+  if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "contraction launch failed: %s", cudaGetErrorString(st));
+  e->launches += 1;
+  return 0;
+}
+
+ConvGemm linear_params(const float* x, const float* w, const float* bias, float* out, int M, int N, int K) {
+  ConvGemm p{};
+  p.x = x; p.w = w; p.scale = nullptr; p.shift = bias; p.res = nullptr; p.out = out; p.out2 = nullptr;
+  p.dyn = nullptr; p.dyn_mul2 = 0; p.ldc = N; p.ldc2 = 0; p.ldr = N; p.n_split = N;
+  p.B = M; p.H = 1; p.W = 1; p.C = K; p.KH = 1; p.KW = 1; p.SH = 1; p.SW = 1; p.PH = 0; p.PW = 0; p.OH = 1; p.OW = 1;
+  p.M = M; p.N = N; p.K = K; p.act = ACT_NONE;
+  return p;
+}
+
+int alloc_act(d2t_engine* e, SlotPool& pool, Fmap* a, int B, int H, int W, int C) {
+  cudaError_t st = cudaSuccess;
+  a->B = B; a->H = H; a->W = W; a->C = C;
+  a->p = (float*)pool.get(a->numel() * sizeof(float), &st);
+  if (!a->p) return e->fail(D2T_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", a->numel() * 4, cudaGetErrorString(st));
+  return 0;
+}
+
+void free_act(d2t_engine* e, SlotPool& pool, Fmap& a) {
+  if (!e->keep_taps && a.p) pool.release(a.p);
+  a.p = nullptr;
+}
+
+int conv_layer(d2t_engine* e, const std::string& name, const Fmap& x, Fmap* y, int sh, int sw, int ph, int pw,
+               const Fmap* res, int act, cudaStream_t s, int oh_override = -1, int ow_override = -1) {
+  auto it = e->conv.find(name);
+  if (it == e->conv.end()) return e->fail(D2T_ERR_STATE, "conv '%s' not finalized", name.c_str());
+  const ConvW& c = it->second;
+  const int OH = oh_override > 0 ? oh_override : (x.H + 2 * ph - c.kh) / sh + 1;
+  const int OW = ow_override > 0 ? ow_override : (x.W + 2 * pw - c.kw) / sw + 1;
+  if (int rc = alloc_act(e, e->enc_pool, y, x.B, OH, OW, c.cout)) return rc;
+  ConvGemm p{};
+  p.x = x.p; p.w = c.w; p.scale = c.scale; p.shift = c.shift; p.res = res ? res->p : nullptr;
+  p.out = y->p; p.out2 = nullptr; p.dyn = nullptr; p.dyn_mul2 = 0;
+  p.ldc = c.cout; p.ldc2 = 0; p.ldr = c.cout; p.n_split = c.cout;
+  p.B = x.B; p.H = x.H; p.W = x.W; p.C = x.C; p.KH = c.kh; p.KW = c.kw; p.SH = sh; p.SW = sw; p.PH = ph; p.PW = pw;
+  p.OH = OH; p.OW = OW; p.M = x.B * OH * OW; p.N = c.cout; p.K = c.kh * c.kw * c.cin; p.act = act;
+  return run_contraction(e, p, &c.tc, e->cfg.precision, s);
+}
+
+int pool_layer(d2t_engine* e, const Fmap& x, Fmap* y, int sh, int sw, int ph, int pw, cudaStream_t s) {
+  const int OH = (x.H + 2 * ph - 2) / sh + 1, OW = (x.W + 2 * pw - 2) / sw + 1;
+  if (int rc = alloc_act(e, e->enc_pool, y, x.B, OH, OW, x.C)) return rc;
+  const long long total = (long long)y->numel() / 4;
+  maxpool2x2_nhwc_kernel<<<grid_for(total, 256, e->num_sms), 256, 0, s>>>(x.p, y->p, x.B, x.H, x.W, x.C, OH, OW, sh, sw, ph, pw);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  return 0;
+}
+
+void tap(d2t_engine* e, const std::string& name, const Fmap& a, bool tokens = false) {
+  if (e->keep_taps) e->taps[name] = Tap{a, tokens};
+}
+
+int basic_block(d2t_engine* e, const std::string& name, Fmap& x, cudaStream_t s) {
+  // BasicBlock.forward (resnet.py:32-48): conv-bn-relu, conv-bn, (+1x1 conv-bn downsample), add, relu
+  Fmap t, ds, o;
+  if (int rc = conv_layer(e, name + ".conv1", x, &t, 1, 1, 1, 1, nullptr, ACT_RELU, s)) return rc;
+  const Fmap* res = &x;
+  if (e->conv.count(name + ".downsample.0")) {
+    if (int rc = conv_layer(e, name + ".downsample.0", x, &ds, 1, 1, 0, 0, nullptr, ACT_NONE, s)) return rc;
+    res = &ds;
+  }
+  if (int rc = conv_layer(e, name + ".conv2", t, &o, 1, 1, 1, 1, res, ACT_RELU, s)) return rc;
+  free_act(e, e->enc_pool, t);
+  if (ds.p) free_act(e, e->enc_pool, ds);
+  free_act(e, e->enc_pool, x);
+  x = o;
+  return 0;
+}
+
+int layernorm(d2t_engine* e, const float* x, const float* w, const float* b, float* y, int rows, int D, float eps,
+              cudaStream_t s) {
+  const int threads = 256, wpb = threads / 32;
+  const int grid = (rows + wpb - 1) / wpb;
+  switch (D / 128) {
+    case 1: layernorm_kernel<1><<<grid, threads, 0, s>>>(x, w, b, y, rows, eps); break;
+    case 2: layernorm_kernel<2><<<grid, threads, 0, s>>>(x, w, b, y, rows, eps); break;
+    case 4: layernorm_kernel<4><<<grid, threads, 0, s>>>(x, w, b, y, rows, eps); break;
+    case 8: layernorm_kernel<8><<<grid, threads, 0, s>>>(x, w, b, y, rows, eps); break;
+    default: return e->fail(D2T_ERR_UNSUPPORTED, "LayerNorm width %d unsupported (need 128/256/512/1024)", D);
+  }
+  if (D % 128) return e->fail(D2T_ERR_UNSUPPORTED, "LayerNorm width %d unsupported", D);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  return 0;
+}
+
+int linear(d2t_engine* e, const float* x, const std::string& wkey, const std::string& bkey, float* out, int M, int N,
+           int K, int act, const float* res, cudaStream_t s, int w_row_off = 0) {
+  auto wi = e->dev.find(wkey);
+  if (wi == e->dev.end()) return e->fail(D2T_ERR_STATE, "weight '%s' not finalized", wkey.c_str());
+  const float* bias = nullptr;
+  if (!bkey.empty()) {
+    auto bi = e->dev.find(bkey);
+    if (bi == e->dev.end()) return e->fail(D2T_ERR_STATE, "bias '%s' not finalized", bkey.c_str());
+    bias = bi->second + w_row_off;
+  }
+  ConvGemm p = linear_params(x, wi->second + (size_t)w_row_off * K, bias, out, M, N, K);
+  p.act = act; p.res = res; p.ldr = N;
+  return run_contraction(e, p, nullptr, D2T_PREC_FP32, s);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* d2t_version(void) { return "doc2tex_b200 0.1 (sm_100a)"; }
+
+const char* d2t_last_error(const d2t_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int64_t d2t_launch_count(const d2t_engine* e) { return e ? e->launches : 0; }
+
+int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
+  if (!cfg || !out) { g_create_error = "null argument"; return D2T_ERR_INVALID; }
+  if (cfg->struct_size != (int32_t)sizeof(d2t_config)) {
+    g_create_error = "d2t_config.struct_size mismatch (ABI)";
+    return D2T_ERR_INVALID;
+  }
+  int ndev = 0;
+  cudaError_t st = cudaGetDeviceCount(&ndev);
+  if (st != cudaSuccess || ndev == 0) {
+    g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(st) + " (this engine has no CPU fallback)";
+    return D2T_ERR_CUDA;
+  }
+  if (device < 0 || device >= ndev) { g_create_error = "device index out of range"; return D2T_ERR_INVALID; }
+  cudaDeviceProp prop;
+  st = cudaGetDeviceProperties(&prop, device);
+  if (st != cudaSuccess) { g_create_error = cudaGetErrorString(st); return D2T_ERR_CUDA; }
+  if (prop.major != 10) {
+    g_create_error = "doc2tex_b200 is built for sm_100a (B200) only; found compute capability " +
+                     std::to_string(prop.major) + "." + std::to_string(prop.minor);
+    return D2T_ERR_UNSUPPORTED;
+  }
+  if (cfg->in_channels != 1) { g_create_error = "only input_channel == 1 (grayscale) is supported"; return D2T_ERR_UNSUPPORTED; }
+  if (cfg->hidden % 128 || cfg->hidden / cfg->heads != 32) {
+    g_create_error = "hidden must be a multiple of 128 with head_dim 32";
+    return D2T_ERR_UNSUPPORTED;
+  }
+  if (cfg->head == D2T_HEAD_TFM && (cfg->dec_heads <= 0 || cfg->hidden / cfg->dec_heads != 32)) {
+    g_create_error = "TFM head needs d_model/nhead == 32";
+    return D2T_ERR_UNSUPPORTED;
+  }
+  auto* e = new d2t_engine();
+  e->cfg = *cfg;
+  e->device = device;
+  e->num_sms = prop.multiProcessorCount;
+  cudaSetDevice(device);
+  if (cudaMallocHost(&e->h_counters, 4 * sizeof(int)) != cudaSuccess) {
+    g_create_error = "cudaMallocHost failed";
+    delete e;
+    return D2T_ERR_CUDA;
+  }
+  if (cudaStreamCreateWithFlags(&e->work, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+    g_create_error = "stream/event creation failed";
+    delete e;
+    return D2T_ERR_CUDA;
+  }
+  // decode attention may need > 48 KB of dynamic shared memory for long encoder memories
+  cudaFuncSetAttribute(decode_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+  cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  *out = e;
+  return D2T_OK;
+}
+
+int d2t_destroy(d2t_engine* e) {
+  if (!e) return D2T_OK;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (void* p : e->owned) cudaFree(p);
+  e->enc_pool.destroy();
+  e->dec_pool.destroy();
+  if (e->h_counters) cudaFreeHost(e->h_counters);
+  if (e->work) cudaStreamDestroy(e->work);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
+  delete e;
+  return D2T_OK;
+}
+
+int d2t_load_tensor(d2t_engine* e, const char* key, const void* data, const int64_t* shape, int ndim, int dtype) {
+  if (!e || !key || !data || ndim < 0 || ndim > 8) return e ? e->fail(D2T_ERR_INVALID, "bad load_tensor arguments") : D2T_ERR_INVALID;
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) { t.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+  t.f.resize(n);
+  if (dtype == D2T_F32) {
+    memcpy(t.f.data(), data, n * sizeof(float));
+  } else if (dtype == D2T_I64) {
+    const int64_t* s = (const int64_t*)data;
+    for (size_t i = 0; i < n; ++i) t.f[i] = (float)s[i];
+  } else {
+    return e->fail(D2T_ERR_INVALID, "unsupported dtype %d for '%s'", dtype, key);
+  }
+  e->host[key] = std::move(t);
+  e->finalized = false;
+  return D2T_OK;
+}
+
+int d2t_finalize_weights(d2t_engine* e) {
+  if (!e) return D2T_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  for (void* p : e->owned) cudaFree(p);
+  e->owned.clear(); e->conv.clear(); e->dev.clear();
+  for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+  const d2t_config& c = e->cfg;
+  const int C = c.stem_channels, D = c.hidden;
+  const int c16 = C / 16, c8 = C / 8, c4 = C / 4, c2 = C / 2;
+  int rc;
+  // --- ResNet stem (resnet.py:51-156) ---
+  if ((rc = make_conv(e, "conv0_1", "bn0_1", c16, c.in_channels, 3, 3))) return rc;
+  if ((rc = make_conv(e, "conv0_2", "bn0_2", c8, c16, 3, 3))) return rc;
+  if ((rc = make_layer(e, "layer1", c8, c4, 1))) return rc;
+  if ((rc = make_conv(e, "conv1", "bn1", c4, c4, 3, 3))) return rc;
+  if ((rc = make_layer(e, "layer2", c4, c2, 2))) return rc;
+  if ((rc = make_conv(e, "conv2", "bn2", c2, c2, 3, 3))) return rc;
+  if ((rc = make_layer(e, "layer3", c2, C, 5))) return rc;
+  if ((rc = make_conv(e, "conv3", "bn3", C, C, 3, 3))) return rc;
+  if ((rc = make_layer(e, "layer4", C, C, 3))) return rc;
+  if ((rc = make_conv(e, "conv4_1", "bn4_1", C, C, 2, 2))) return rc;
+  if ((rc = make_conv(e, "conv4_2", "bn4_2", C, C, 2, 2))) return rc;
+  // --- patch embed (patchembed.py:111-113): Conv2d(C -> D, k2, s2, bias) ---
+  {
+    const HostTensor *w, *b;
+    if ((rc = need(e, SEQ + "patch_embed.proj.weight", &w, {D, C, 2, 2}))) return rc;
+    if ((rc = need(e, SEQ + "patch_embed.proj.bias", &b, {D}))) return rc;
+    std::vector<float> packed((size_t)D * 4 * C);
+    for (int o = 0; o < D; ++o)
+      for (int i = 0; i < C; ++i)
+        for (int y = 0; y < 2; ++y)
+          for (int x = 0; x < 2; ++x)
+            packed[(((size_t)o * 2 + y) * 2 + x) * C + i] = w->f[(((size_t)o * C + i) * 2 + y) * 2 + x];
+    ConvW cw; cw.cout = D; cw.cin = C; cw.kh = 2; cw.kw = 2;
+    if ((rc = upload(e, packed.data(), packed.size(), &cw.w))) return rc;
+    if ((rc = upload(e, b->f.data(), D, &cw.shift))) return rc;
+    e->conv["patch_embed.proj"] = cw;
+  }
+  // --- ViT (vit_encoder.py:229-268, vision_transformer.py:119-122) ---
+  if ((rc = upload_key(e, SEQ + "cls_token", {1, 1, D}))) return rc;
+  if ((rc = upload_key(e, SEQ + "pos_embed", {1, c.max_tokens, D}))) return rc;
+  for (int i = 0; i < c.depth; ++i) {
+    const std::string p = SEQ + "blocks." + std::to_string(i) + ".";
+    const char* vec256[] = {"norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias", "attn.proj.bias", "mlp.fc2.bias"};
+    for (const char* k : vec256) if ((rc = upload_key(e, p + k, {D}))) return rc;
+    if ((rc = upload_key(e, p + "attn.qkv.weight", {3 * D, D}))) return rc;
+    if ((rc = upload_key(e, p + "attn.qkv.bias", {3 * D}))) return rc;
+    if ((rc = upload_key(e, p + "attn.proj.weight", {D, D}))) return rc;
+    if ((rc = upload_key(e, p + "mlp.fc1.weight", {4 * D, D}))) return rc;
+    if ((rc = upload_key(e, p + "mlp.fc1.bias", {4 * D}))) return rc;
+    if ((rc = upload_key(e, p + "mlp.fc2.weight", {D, 4 * D}))) return rc;
+  }
+  if ((rc = upload_key(e, SEQ + "norm.weight", {D}))) return rc;
+  if ((rc = upload_key(e, SEQ + "norm.bias", {D}))) return rc;
+  // --- prediction head ---
+  if (c.head == D2T_HEAD_TFM) {
+    const int V = c.vocab, F = c.dec_ff;
+    if ((rc = upload_key(e, PRED + "word_embed.weight", {V, D}))) return rc;
+    {
+      const HostTensor* pe;
+      if ((rc = need(e, PRED + "pos_enc.pe", &pe))) return rc;
+      if (pe->shape.size() != 2 || pe->shape[1] != D || pe->shape[0] < c.max_seq_len + 2)
+        return e->fail(D2T_ERR_INVALID, "pos_enc.pe must be (>=max_seq_len+2, %d)", D);
+      if ((rc = upload_key(e, PRED + "pos_enc.pe"))) return rc;
+    }
+    for (int l = 0; l < c.dec_layers; ++l) {
+      const std::string p = PRED + "model.layers." + std::to_string(l) + ".";
+      for (const char* a : {"self_attn.", "multihead_attn."}) {
+        if ((rc = upload_key(e, p + a + "in_proj_weight", {3 * D, D}))) return rc;
+        if ((rc = upload_key(e, p + a + "in_proj_bias", {3 * D}))) return rc;
+        if ((rc = upload_key(e, p + a + "out_proj.weight", {D, D}))) return rc;
+        if ((rc = upload_key(e, p + a + "out_proj.bias", {D}))) return rc;
+      }
+      if ((rc = upload_key(e, p + "linear1.weight", {F, D}))) return rc;
+      if ((rc = upload_key(e, p + "linear1.bias", {F}))) return rc;
+      if ((rc = upload_key(e, p + "linear2.weight", {D, F}))) return rc;
+      if ((rc = upload_key(e, p + "linear2.bias", {D}))) return rc;
+      for (const char* n : {"norm1", "norm2", "norm3"}) {
+        if ((rc = upload_key(e, p + n + ".weight", {D}))) return rc;
+        if ((rc = upload_key(e, p + n + ".bias", {D}))) return rc;
+      }
+    }
+    if ((rc = upload_key(e, PRED + "proj.weight", {V, D}))) return rc;
+    if ((rc = upload_key(e, PRED + "proj.bias", {V}))) return rc;
+  } else if (c.head == D2T_HEAD_ATTNV2) {
+    const int V = c.vocab, Hs = c.attn_hidden, Kd = c.attn_kernel_dim, taps = 2 * c.attn_kernel_size + 1;
+    const std::string a = PRED + "attention_cell.attn.";
+    if ((rc = upload_key(e, PRED + "embedding.weight", {V, D}))) return rc;
+    if ((rc = upload_key(e, a + "loc_conv.weight", {Kd, 1, taps}))) return rc;
+    if ((rc = upload_key(e, a + "loc_conv.bias", {Kd}))) return rc;
+    if ((rc = upload_key(e, a + "loc_proj.weight", {Hs, Kd}))) return rc;
+    if ((rc = upload_key(e, a + "loc_proj.bias", {Hs}))) return rc;
+    if ((rc = upload_key(e, a + "query_proj.weight", {Hs, Hs}))) return rc;
+    if ((rc = upload_key(e, a + "query_proj.bias", {Hs}))) return rc;
+    if ((rc = upload_key(e, a + "key_proj.weight", {Hs, D}))) return rc;
+    if ((rc = upload_key(e, a + "key_proj.bias", {Hs}))) return rc;
+    if ((rc = upload_key(e, a + "score.weight", {1, Hs}))) return rc;
+    if ((rc = upload_key(e, a + "score.bias", {1}))) return rc;
+    const std::string r = PRED + "attention_cell.rnn.";
+    // LSTMCell input = [context ; embedding] (attention1D.py:236-239): gates = W_ih x + b_ih + W_hh h + b_hh.
+    // Packed once as one [4H, D+D+H] matrix over [context ; embedding ; h] with the two biases kept separate.
+    {
+      const HostTensor *wih, *whh, *bih, *bhh;
+      if ((rc = need(e, r + "weight_ih", &wih, {4 * Hs, 2 * D}))) return rc;
+      if ((rc = need(e, r + "weight_hh", &whh, {4 * Hs, Hs}))) return rc;
+      if ((rc = need(e, r + "bias_ih", &bih, {4 * Hs}))) return rc;
+      if ((rc = need(e, r + "bias_hh", &bhh, {4 * Hs}))) return rc;
+      const int Kc = 2 * D + Hs;
+      std::vector<float> cat((size_t)4 * Hs * Kc);
+      for (int g = 0; g < 4 * Hs; ++g) {
+        memcpy(&cat[(size_t)g * Kc], &wih->f[(size_t)g * 2 * D], 2 * D * sizeof(float));
+        memcpy(&cat[(size_t)g * Kc + 2 * D], &whh->f[(size_t)g * Hs], Hs * sizeof(float));
+      }
+      float* p;
+      if ((rc = upload(e, cat.data(), cat.size(), &p))) return rc;
+      e->dev["lstm.w_cat"] = p;
+      if ((rc = upload_key(e, r + "bias_ih"))) return rc;
+      if ((rc = upload_key(e, r + "bias_hh"))) return rc;
+    }
+    if ((rc = upload_key(e, PRED + "attention_cell.generator.weight", {V, Hs}))) return rc;
+    if ((rc = upload_key(e, PRED + "attention_cell.generator.bias", {V}))) return rc;
+    for (const char* n : {"proj_init_h", "proj_init_c"}) {
+      if ((rc = upload_key(e, PRED + n + ".weight", {Hs, D}))) return rc;
+      if ((rc = upload_key(e, PRED + n + ".bias", {Hs}))) return rc;
+    }
+    if ((rc = finalize_attn_extras(e))) return rc;
+  }
+  // operand planes for the tensor-core contraction path
+  if (c.precision != D2T_PREC_FP32) {
+    for (auto& kv : e->conv) {
+      if (kv.first == "conv0_1") continue;
+      cudaError_t st = tc_prepare_weight(kv.second.w, kv.second.cout, kv.second.kh * kv.second.kw * kv.second.cin,
+                                         c.precision, &kv.second.tc, &e->owned);
+      if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tc_prepare_weight(%s): %s", kv.first.c_str(), cudaGetErrorString(st));
+    }
+  }
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  e->finalized = true;
+  return D2T_OK;
+}
+
+int d2t_encoder_geometry(const d2t_engine* e, int H, int W, int* gh, int* gw, int* pad_w, int* pad_h, int* ntok) {
+  if (!e) return D2T_ERR_INVALID;
+  if (H < 32 || W < 32 || H % 32 || W % 32) return const_cast<d2t_engine*>(e)->fail(D2T_ERR_INVALID, "H and W must be multiples of 32 (got %dx%d)", H, W);
+  const int fh = H / 16 - 1, fw = W / 4 + 1;  // quirk Q2
+  const int g_h = (fh + 1) / 2, g_w = (fw + 1) / 2;
+  if (gh) *gh = g_h;
+  if (gw) *gw = g_w;
+  if (pad_h) *pad_h = fh % 2;
+  if (pad_w) *pad_w = fw % 2;
+  if (ntok) *ntok = 1 + g_h * g_w;
+  return D2T_OK;
+}
+
+int d2t_set_debug(d2t_engine* e, int keep_taps) {
+  if (!e) return D2T_ERR_INVALID;
+  e->keep_taps = keep_taps != 0;
+  return D2T_OK;
+}
+
+int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx, d2t_stream stream) {
+  if (!e) return D2T_ERR_INVALID;
+  if (!e->finalized) return e->fail(D2T_ERR_STATE, "d2t_encode before d2t_finalize_weights");
+  if (!img || !ctx || B <= 0) return e->fail(D2T_ERR_INVALID, "bad encode arguments");
+  int gh, gw, ntok;
+  if (int rc = d2t_encoder_geometry(e, H, W, &gh, &gw, nullptr, nullptr, &ntok)) return rc;
+  if (ntok > e->cfg.max_tokens)
+    return e->fail(D2T_ERR_INVALID, "image %dx%d needs %d tokens but pos_embed has %d rows (max_dimension)", H, W, ntok, e->cfg.max_tokens);
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  e->enc_pool.release_all();
+  e->taps.clear();
+  const d2t_config& c = e->cfg;
+  const int D = c.hidden;
+  int rc;
+
+  // ---- ResNet stem, NHWC (resnet.py:205-245) ----
+  Fmap x, y;
+  {
+    const ConvW& c0 = e->conv["conv0_1"];
+    if ((rc = alloc_act(e, e->enc_pool, &x, B, H, W, c0.cout))) return rc;
+    const long long total = (long long)B * H * W * (c0.cout / 4);
+    const size_t smem = (size_t)11 * c0.cout * sizeof(float);
+    conv0_direct_kernel<<<grid_for(total, 256, e->num_sms), 256, smem, s>>>(img, c0.w, c0.scale, c0.shift, x.p, B, H, W, c0.cout);
+    e->launches += 1;
+    CUDA_TRY(e, cudaGetLastError());
+    tap(e, "conv0_1", x);
+  }
+  if ((rc = conv_layer(e, "conv0_2", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s))) return rc;
+  free_act(e, e->enc_pool, x); tap(e, "conv0_2", y);
+  if ((rc = pool_layer(e, y, &x, 2, 2, 0, 0, s))) return rc;
+  free_act(e, e->enc_pool, y);
+  if ((rc = basic_block(e, "layer1.0", x, s))) return rc;
+  tap(e, "layer1", x);
+  if ((rc = conv_layer(e, "conv1", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s))) return rc;
+  free_act(e, e->enc_pool, x); tap(e, "conv1", y);
+  if ((rc = pool_layer(e, y, &x, 2, 2, 0, 0, s))) return rc;
+  free_act(e, e->enc_pool, y);
+  for (int b = 0; b < 2; ++b) if ((rc = basic_block(e, "layer2." + std::to_string(b), x, s))) return rc;
+  tap(e, "layer2", x);
+  if ((rc = conv_layer(e, "conv2", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s))) return rc;
+  free_act(e, e->enc_pool, x); tap(e, "conv2", y);
+  if ((rc = pool_layer(e, y, &x, 2, 1, 0, 1, s))) return rc;  // maxpool3: k2 s(2,1) p(0,1), -inf padding
+  free_act(e, e->enc_pool, y); tap(e, "pool3", x);
+  for (int b = 0; b < 5; ++b) if ((rc = basic_block(e, "layer3." + std::to_string(b), x, s))) return rc;
+  tap(e, "layer3", x);
+  if ((rc = conv_layer(e, "conv3", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s))) return rc;
+  free_act(e, e->enc_pool, x); tap(e, "conv3", y);
+  x = y; y = Fmap{};
+  for (int b = 0; b < 3; ++b) if ((rc = basic_block(e, "layer4." + std::to_string(b), x, s))) return rc;
+  tap(e, "layer4", x);
+  if ((rc = conv_layer(e, "conv4_1", x, &y, 2, 1, 0, 1, nullptr, ACT_RELU, s))) return rc;
+  free_act(e, e->enc_pool, x); tap(e, "conv4_1", y);
+  if ((rc = conv_layer(e, "conv4_2", y, &x, 1, 1, 0, 0, nullptr, ACT_RELU, s))) return rc;
+  free_act(e, e->enc_pool, y); tap(e, "conv4_2", x);
+  if (x.H != H / 16 - 1 || x.W != W / 4 + 1) return e->fail(D2T_ERR_INVALID, "internal: stem geometry %dx%d", x.H, x.W);
+
+  // ---- HybridEmbed: zero-pad right/bottom to even, Conv2d(k2,s2)+bias, flatten (patchembed.py:121-135) ----
+  Fmap tok;
+  if ((rc = conv_layer(e, "patch_embed.proj", x, &tok, 2, 2, 0, 0, nullptr, ACT_NONE, s, gh, gw))) return rc;
+  free_act(e, e->enc_pool, x);
+  {
+    Fmap t = tok; t.B = B; t.H = 1; t.W = gh * gw; tap(e, "patch_embed", t, true);
+  }
+  const int N = gh * gw, T = N + 1, rows = B * T;
+  Fmap xs, hs, qkv, att, x2, ff;
+  if ((rc = alloc_act(e, e->enc_pool, &xs, B, 1, T, D))) return rc;
+  if ((rc = alloc_act(e, e->enc_pool, &hs, B, 1, T, D))) return rc;
+  if ((rc = alloc_act(e, e->enc_pool, &qkv, B, 1, T, 3 * D))) return rc;
+  if ((rc = alloc_act(e, e->enc_pool, &att, B, 1, T, D))) return rc;
+  if ((rc = alloc_act(e, e->enc_pool, &ff, B, 1, T, 4 * D))) return rc;
+  assemble_tokens_kernel<<<grid_for((long long)rows * D / 4, 256, e->num_sms), 256, 0, s>>>(
+      tok.p, e->dev[SEQ + "cls_token"], e->dev[SEQ + "pos_embed"], xs.p, B, N, D);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  free_act(e, e->enc_pool, tok);
+  const float scale = 1.0f / sqrtf((float)(D / c.heads));
+  for (int i = 0; i < c.depth; ++i) {
+    const std::string p = SEQ + "blocks." + std::to_string(i) + ".";
+    if ((rc = alloc_act(e, e->enc_pool, &x2, B, 1, T, D))) return rc;
+    if ((rc = layernorm(e, xs.p, e->dev[p + "norm1.weight"], e->dev[p + "norm1.bias"], hs.p, rows, D, 1e-6f, s))) return rc;
+    if ((rc = linear(e, hs.p, p + "attn.qkv.weight", p + "attn.qkv.bias", qkv.p, rows, 3 * D, D, ACT_NONE, nullptr, s))) return rc;
+    {
+      dim3 grid((T + 127) / 128, B * c.heads);
+      encoder_attention_kernel<32, 64><<<grid, 128, 0, s>>>(qkv.p, att.p, T, D, scale);
+      e->launches += 1;
+      CUDA_TRY(e, cudaGetLastError());
+    }
+    if ((rc = linear(e, att.p, p + "attn.proj.weight", p + "attn.proj.bias", x2.p, rows, D, D, ACT_NONE, xs.p, s))) return rc;
+    if ((rc = layernorm(e, x2.p, e->dev[p + "norm2.weight"], e->dev[p + "norm2.bias"], hs.p, rows, D, 1e-6f, s))) return rc;
+    if ((rc = linear(e, hs.p, p + "mlp.fc1.weight", p + "mlp.fc1.bias", ff.p, rows, 4 * D, D, ACT_GELU, nullptr, s))) return rc;
+    free_act(e, e->enc_pool, xs);
+    if ((rc = alloc_act(e, e->enc_pool, &xs, B, 1, T, D))) return rc;
+    if ((rc = linear(e, ff.p, p + "mlp.fc2.weight", p + "mlp.fc2.bias", xs.p, rows, D, 4 * D, ACT_NONE, x2.p, s))) return rc;
+    free_act(e, e->enc_pool, x2);
+    tap(e, "block" + std::to_string(i), xs, true);
+  }
+  if ((rc = layernorm(e, xs.p, e->dev[SEQ + "norm.weight"], e->dev[SEQ + "norm.bias"], ctx, rows, D, 1e-6f, s))) return rc;
+  return D2T_OK;
+}
+
+int d2t_debug_tap(d2t_engine* e, const char* name, float* out, int64_t* numel, int64_t* shape4, d2t_stream stream) {
+  if (!e || !name) return D2T_ERR_INVALID;
+  auto it = e->taps.find(name);
+  if (it == e->taps.end()) return e->fail(D2T_ERR_INVALID, "no tap '%s' (enable d2t_set_debug before encode)", name);
+  const Fmap& a = it->second.a;
+  if (numel) *numel = (int64_t)a.numel();
+  if (shape4) {
+    if (it->second.tokens) { shape4[0] = a.B; shape4[1] = a.W; shape4[2] = a.C; shape4[3] = 0; }
+    else { shape4[0] = a.B; shape4[1] = a.C; shape4[2] = a.H; shape4[3] = a.W; }
+  }
+  if (!out) return D2T_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (it->second.tokens) {
+    CUDA_TRY(e, cudaMemcpyAsync(out, a.p, a.numel() * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    nhwc_to_nchw_kernel<<<grid_for((long long)a.numel(), 256, e->num_sms), 256, 0, s>>>(a.p, out, a.B, a.H, a.W, a.C);
+    CUDA_TRY(e, cudaGetLastError());
+  }
+  return D2T_OK;
+}
+
+int d2t_debug_gemm(d2t_engine* e, const float* a, const float* w, const float* scale, const float* shift, float* c,
+                   int M, int N, int K, int act, int precision, d2t_stream stream) {
+  if (!e) return D2T_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  ConvGemm p = linear_params(a, w, shift, c, M, N, K);
+  p.scale = scale; p.act = act;
+  if (precision == D2T_PREC_FP32) return run_contraction(e, p, nullptr, precision, (cudaStream_t)stream);
+  TcWeight tw;
+  std::vector<void*> tmp;
+  cudaError_t st = tc_prepare_weight(w, N, K, precision, &tw, &tmp);
+  if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tc_prepare_weight: %s", cudaGetErrorString(st));
+  if (!tw.ready || !tc_supported(p)) {
+    for (void* q : tmp) cudaFree(q);
+    return e->fail(D2T_ERR_UNSUPPORTED, "tcgen05 path does not support M=%d N=%d K=%d", M, N, K);
+  }
+  int rc = run_contraction(e, p, &tw, precision, (cudaStream_t)stream);
+  cudaStreamSynchronize((cudaStream_t)stream);
+  for (void* q : tmp) cudaFree(q);
+  return rc;
+}
+
+}  // extern "C"
+
+#include "decode_host.inl"

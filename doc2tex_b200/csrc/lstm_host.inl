@@ -1,0 +1,200 @@
+// Host side of the Attnv2 (LSTM + coverage attention) greedy decode (included at the end of decode_host.inl).
+
+namespace {
+
+constexpr int ATTN_GO = 0, ATTN_END = 1;  // AttnLabelConverter (attn_converter.py:8)
+
+struct AttnBuffers {
+  float *keyproj = nullptr, *qp = nullptr, *xcat = nullptr, *gates = nullptr, *h = nullptr, *c = nullptr;
+  float *alpha_cum = nullptr, *logits = nullptr, *logits_out = nullptr;
+  int *tokens = nullptr, *ended = nullptr, *counters = nullptr;
+  long long* ids = nullptr;
+};
+
+int enqueue_attn_step(d2t_engine* e, const AttnBuffers& b, const float* ctx, int B, int ntok, int T, bool want_logits,
+                      cudaStream_t s) {
+  const d2t_config& c = e->cfg;
+  const int D = c.hidden, Hs = c.attn_hidden, V = c.vocab, L = T + 1, Kc = 2 * D + Hs;
+  const int taps = 2 * c.attn_kernel_size + 1, S = ntok - 1;
+  const std::string a = PRED + "attention_cell.attn.";
+  int* step = b.counters;
+  int rc;
+  lstm_embed_kernel<<<(B * D / 4 + 255) / 256, 256, 0, s>>>(b.tokens, L, step, e->dev[PRED + "embedding.weight"], b.xcat, Kc, D, B, D);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  {  // query_proj(h_prev): h lives in xcat[:, 2D:2D+Hs]
+    ConvGemm g = linear_params(b.h, e->dev[a + "query_proj.weight"], e->dev[a + "query_proj.bias"], b.qp, B, Hs, Hs);
+    if ((rc = dec_linear(e, g, s))) return rc;
+  }
+  lstm_attention_step_kernel<256><<<B, 256, (size_t)2 * S * sizeof(float), s>>>(
+      b.keyproj, ctx, ntok, b.qp, e->dev["attn.locM"], e->dev["attn.locc"], taps, e->dev[a + "score.weight"],
+      e->dev[a + "score.bias"], b.alpha_cum, b.xcat, Kc);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  {  // LSTMCell gates over [context ; embedding ; h]
+    ConvGemm g = linear_params(b.xcat, e->dev["lstm.w_cat"], e->dev["lstm.b_sum"], b.gates, B, 4 * Hs, Kc);
+    if ((rc = dec_linear(e, g, s))) return rc;
+  }
+  lstm_pointwise_kernel<<<(B * Hs + 255) / 256, 256, 0, s>>>(b.gates, b.c, b.h, b.xcat, Kc, 2 * D, B, Hs);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  {
+    ConvGemm g = linear_params(b.h, e->dev[PRED + "attention_cell.generator.weight"], e->dev[PRED + "attention_cell.generator.bias"], b.logits, B, V, Hs);
+    if ((rc = dec_linear(e, g, s))) return rc;
+  }
+  lstm_pick_kernel<<<B, 128, 0, s>>>(b.logits, V, step, b.tokens, L, b.ids, T, want_logits ? b.logits_out : nullptr,
+                                     b.ended, b.counters + 1, b.counters + 2, B, ATTN_END, T - 1);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  advance_step_kernel<<<1, 1, 0, s>>>(step);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// Folds loc_proj(conv1d(.)) into one [Hs][taps] matrix + bias (both are linear, attention1D.py:146-148), and
+// sums the two LSTM biases.  Called from d2t_finalize_weights.
+int finalize_attn_extras(d2t_engine* e) {
+  const d2t_config& c = e->cfg;
+  const int Hs = c.attn_hidden, Kd = c.attn_kernel_dim, taps = 2 * c.attn_kernel_size + 1;
+  const std::string a = PRED + "attention_cell.attn.";
+  const HostTensor *wc, *bc, *wp, *bp, *bih, *bhh;
+  int rc;
+  if ((rc = need(e, a + "loc_conv.weight", &wc))) return rc;
+  if ((rc = need(e, a + "loc_conv.bias", &bc))) return rc;
+  if ((rc = need(e, a + "loc_proj.weight", &wp))) return rc;
+  if ((rc = need(e, a + "loc_proj.bias", &bp))) return rc;
+  if ((rc = need(e, PRED + "attention_cell.rnn.bias_ih", &bih))) return rc;
+  if ((rc = need(e, PRED + "attention_cell.rnn.bias_hh", &bhh))) return rc;
+  std::vector<float> M((size_t)Hs * taps), cv(Hs), bs(4 * Hs);
+  for (int h = 0; h < Hs; ++h) {
+    for (int j = 0; j < taps; ++j) {
+      double acc = 0.0;
+      for (int k = 0; k < Kd; ++k) acc += (double)wp->f[(size_t)h * Kd + k] * (double)wc->f[(size_t)k * taps + j];
+      M[(size_t)h * taps + j] = (float)acc;
+    }
+    double acc = bp->f[h];
+    for (int k = 0; k < Kd; ++k) acc += (double)wp->f[(size_t)h * Kd + k] * (double)bc->f[k];
+    cv[h] = (float)acc;
+  }
+  for (int i = 0; i < 4 * Hs; ++i) bs[i] = bih->f[i] + bhh->f[i];
+  float* p;
+  if ((rc = upload(e, M.data(), M.size(), &p))) return rc;
+  e->dev["attn.locM"] = p;
+  if ((rc = upload(e, cv.data(), cv.size(), &p))) return rc;
+  e->dev["attn.locc"] = p;
+  if ((rc = upload(e, bs.data(), bs.size(), &p))) return rc;
+  e->dev["lstm.b_sum"] = p;
+  return 0;
+}
+
+extern "C" int d2t_decode_attn_greedy(d2t_engine* e, const float* ctx, int B, int ntok, int max_steps,
+                                      int stop_on_all_eos, int64_t* ids, float* logits, int* steps_out,
+                                      d2t_stream stream) {
+  if (!e) return D2T_ERR_INVALID;
+  const d2t_config& c = e->cfg;
+  if (c.head != D2T_HEAD_ATTNV2) return e->fail(D2T_ERR_STATE, "engine was not configured with the Attnv2 head");
+  if (!e->finalized) return e->fail(D2T_ERR_STATE, "decode before d2t_finalize_weights");
+  if (!ctx || !ids || !steps_out || B <= 0 || ntok < 2 || max_steps <= 0) return e->fail(D2T_ERR_INVALID, "bad decode arguments");
+  if (c.attn_hidden != 256 || c.hidden != 256) return e->fail(D2T_ERR_UNSUPPORTED, "Attnv2 head needs hidden_size == input_size == 256");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  WorkStream ws(e, (cudaStream_t)stream);
+  cudaStream_t s = ws.get();
+  const int D = c.hidden, Hs = c.attn_hidden, V = c.vocab, T = max_steps, L = T + 1, Kc = 2 * D + Hs, S = ntok - 1;
+  const bool want_logits = logits != nullptr;
+  e->dec_pool.release_all();
+  AttnBuffers b;
+  int rc;
+  if ((rc = pool_get(e, &b.keyproj, (size_t)B * ntok * Hs))) return rc;
+  if ((rc = pool_get(e, &b.qp, (size_t)B * Hs))) return rc;
+  if ((rc = pool_get(e, &b.xcat, (size_t)B * Kc))) return rc;
+  if ((rc = pool_get(e, &b.gates, (size_t)B * 4 * Hs))) return rc;
+  if ((rc = pool_get(e, &b.h, (size_t)B * Hs))) return rc;
+  if ((rc = pool_get(e, &b.c, (size_t)B * Hs))) return rc;
+  if ((rc = pool_get(e, &b.alpha_cum, (size_t)B * S))) return rc;
+  if ((rc = pool_get(e, &b.logits, (size_t)B * V))) return rc;
+  if ((rc = pool_get(e, &b.tokens, (size_t)B * L))) return rc;
+  if ((rc = pool_get(e, &b.ended, (size_t)B))) return rc;
+  if ((rc = pool_get(e, &b.counters, 4))) return rc;
+  if ((rc = pool_get(e, &b.ids, (size_t)B * T))) return rc;
+  CUDA_TRY(e, cudaMemsetAsync(b.ids, 0, (size_t)B * T * sizeof(long long), s));
+  CUDA_TRY(e, cudaMemsetAsync(b.alpha_cum, 0, (size_t)B * S * sizeof(float), s));
+  if (want_logits) {
+    if ((rc = pool_get(e, &b.logits_out, (size_t)B * T * V))) return rc;
+    CUDA_TRY(e, cudaMemsetAsync(b.logits_out, 0, (size_t)B * T * V * sizeof(float), s));
+  }
+  init_decode_state_kernel<<<grid_for((long long)B * L, 256, e->num_sms), 256, 0, s>>>(
+      b.tokens, (long long)B * L, L, B, 0, ATTN_GO, nullptr, L, nullptr, nullptr, nullptr, nullptr, b.ended, b.counters);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  const std::string a = PRED + "attention_cell.attn.";
+  {  // key_proj(H) hoisted out of the loop (computed for every ctx row; the cls row is simply unused)
+    ConvGemm g = linear_params(ctx, e->dev[a + "key_proj.weight"], e->dev[a + "key_proj.bias"], b.keyproj, B * ntok, Hs, D);
+    if ((rc = dec_linear(e, g, s))) return rc;
+  }
+  for (int which = 0; which < 2; ++which) {  // h0 / c0 = proj_init_{h,c}(ctx[:, 0]) (seq2seq_v2.py:196-199)
+    const std::string n = which == 0 ? "proj_init_h" : "proj_init_c";
+    ConvGemm g = linear_params(ctx, e->dev[PRED + n + ".weight"], e->dev[PRED + n + ".bias"], which == 0 ? b.h : b.c, B, Hs, D);
+    g.W = ntok; g.SW = ntok;  // row m reads pixel (b, 0, 0) of a [B,1,ntok,D] tensor = the cls token
+    if ((rc = dec_linear(e, g, s))) return rc;
+  }
+  CUDA_TRY(e, cudaMemcpy2DAsync(b.xcat + 2 * D, (size_t)Kc * sizeof(float), b.h, (size_t)Hs * sizeof(float),
+                                (size_t)Hs * sizeof(float), B, cudaMemcpyDeviceToDevice, s));
+
+  cudaGraphExec_t exec = nullptr;
+  int nodes = 0;
+  if (c.use_graphs) {
+    std::vector<long long> key = {-2, B, ntok, T, want_logits ? 1 : 0, (long long)(uintptr_t)ctx};
+    const void* ptrs[] = {b.keyproj, b.qp, b.xcat, b.gates, b.h, b.c, b.alpha_cum, b.logits, b.logits_out, b.tokens,
+                          b.ended, b.counters, b.ids};
+    for (const void* q : ptrs) key.push_back((long long)(uintptr_t)q);
+    for (auto& g : e->graphs) if (g.key == key) { exec = g.exec; nodes = g.nodes; }
+    if (!exec) {
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(e, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+      const int64_t before = e->launches;
+      rc = enqueue_attn_step(e, b, ctx, B, ntok, T, want_logits, s);
+      nodes = (int)(e->launches - before);
+      e->launches = before;
+      cudaError_t st = cudaStreamEndCapture(s, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(st));
+      st = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(st));
+      if (e->graphs.size() >= 16) { cudaGraphExecDestroy(e->graphs.front().exec); e->graphs.erase(e->graphs.begin()); }
+      d2t_engine::GraphEntry ge; ge.key = key; ge.exec = exec; ge.nodes = nodes;
+      e->graphs.push_back(ge);
+    }
+  }
+  int executed = 0;
+  for (int t = 0; t < T; ++t) {
+    if (exec) { CUDA_TRY(e, cudaGraphLaunch(exec, s)); e->launches += nodes; }
+    else if ((rc = enqueue_attn_step(e, b, ctx, B, ntok, T, want_logits, s))) return rc;
+    executed = t + 1;
+    if (stop_on_all_eos && (executed % POLL_EVERY == 0) && executed < T) {
+      CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(e, cudaStreamSynchronize(s));
+      if (e->h_counters[2] >= 0) break;
+    }
+  }
+  CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(e, cudaStreamSynchronize(s));
+  const int done_step = e->h_counters[2];
+  const int steps = (stop_on_all_eos && done_step >= 0) ? done_step : executed;
+  // rows past the reference's break stay zero, like its untouched `probs` buffer (seq2seq_v2.py:219-225, 291)
+  if (steps < T) {
+    CUDA_TRY(e, cudaMemset2DAsync(b.ids + steps, (size_t)T * sizeof(long long), 0, (size_t)(T - steps) * sizeof(long long), B, s));
+    if (want_logits)
+      CUDA_TRY(e, cudaMemset2DAsync(b.logits_out + (size_t)steps * V, (size_t)T * V * sizeof(float), 0,
+                                    (size_t)(T - steps) * V * sizeof(float), B, s));
+  }
+  CUDA_TRY(e, cudaMemcpyAsync(ids, b.ids, (size_t)B * T * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
+  if (want_logits)
+    CUDA_TRY(e, cudaMemcpyAsync(logits, b.logits_out, (size_t)B * T * V * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CUDA_TRY(e, cudaStreamSynchronize(s));
+  *steps_out = steps;
+  return D2T_OK;
+}

@@ -1,0 +1,164 @@
+/*
+ * doc2tex_b200 — C ABI of the B200-native recognizer engine.
+ *
+ * This is the drop-in boundary for the hot path of duylebkHCM/doc2tex: the batched
+ * recognizer forward and its autoregressive decode.  Every entry point replaces a
+ * Python/PyTorch call site of the reference (file:line relative to the reference
+ * repository).  Only plain pointers, sizes and a CUDA stream handle cross the
+ * boundary; the caller (PyTorch on the host side) owns all input/output buffers,
+ * the engine owns weights, KV caches, workspaces and CUDA graphs.
+ *
+ * All functions return 0 on success and a non-zero d2t_status otherwise;
+ * d2t_last_error() gives the message.  No C++ exception crosses the boundary.
+ * One engine per (process, device); calls on one engine are not re-entrant.
+ * All pointers named *_dev are device pointers on the engine's device; work is
+ * enqueued on the caller's stream and is asynchronous w.r.t. the host unless noted.
+ */
+#ifndef DOC2TEX_B200_H_
+#define DOC2TEX_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct d2t_engine d2t_engine;
+typedef void* d2t_stream; /* cudaStream_t */
+
+enum d2t_status {
+  D2T_OK = 0,
+  D2T_ERR_INVALID = 1,   /* bad argument / shape / config */
+  D2T_ERR_MISSING = 2,   /* a state_dict tensor the config requires was never loaded */
+  D2T_ERR_CUDA = 3,      /* CUDA runtime / driver error */
+  D2T_ERR_STATE = 4,     /* call order (e.g. encode before finalize) */
+  D2T_ERR_UNSUPPORTED = 5
+};
+
+enum d2t_head { D2T_HEAD_NONE = 0, D2T_HEAD_TFM = 1, D2T_HEAD_ATTNV2 = 2 };
+
+/* Arithmetic of the dense contractions (conv stem, patch-embed, linear layers). */
+enum d2t_precision {
+  D2T_PREC_FP32 = 0,    /* fp32 FFMA (CUDA cores): the parity anchor */
+  D2T_PREC_TF32X3 = 1,  /* tcgen05 kind::tf32, error-compensated 3-pass split (~2^-21) */
+  D2T_PREC_BF16X3 = 2,  /* tcgen05 kind::f16 on bf16 hi/lo planes, 3 passes (~2^-16) */
+  D2T_PREC_BF16 = 3     /* tcgen05 kind::f16, single bf16 pass, fp32 accumulate */
+};
+
+enum d2t_dtype { D2T_F32 = 0, D2T_I64 = 1 };
+
+/*
+ * Mirrors the YAML keys Model(opt) reads on this path
+ * (build_model.py:7-34, vit_encoder.py:271-317, tfm.py:36-47, seq2seq.py:11-28).
+ */
+typedef struct d2t_config {
+  int32_t struct_size;      /* sizeof(d2t_config), ABI check */
+  int32_t in_channels;      /* SequenceModeling.params.backbone.input_channel (1) */
+  int32_t stem_channels;    /* ...backbone.output_channel (512) */
+  int32_t hidden;           /* ...hidden_size (256) */
+  int32_t depth;            /* ...depth (6) */
+  int32_t heads;            /* ...num_heads (8) */
+  int32_t max_tokens;       /* rows of pos_embed = 1 + max grid (vit_encoder.py:234-237) */
+  int32_t head;             /* d2t_head; Prediction.name */
+  int32_t vocab;            /* num_class (build_pred.py:16-26) */
+  int32_t dec_layers;       /* TFM: num_decoder_layers */
+  int32_t dec_heads;        /* TFM: nhead */
+  int32_t dec_ff;           /* TFM: dim_feedforward */
+  int32_t max_seq_len;      /* TFM: max_seq_len / Attn: batch_max_length */
+  int32_t attn_hidden;      /* Attnv2: hidden_size */
+  int32_t attn_kernel_dim;  /* Attnv2: kernel_dim */
+  int32_t attn_kernel_size; /* Attnv2: kernel_size (Conv1d taps = 2k+1) */
+  int32_t precision;        /* d2t_precision */
+  int32_t use_graphs;       /* capture the decode step in a CUDA graph */
+} d2t_config;
+
+/* Replaces Model.__init__ (build_model.py:7-34). */
+int d2t_create(const d2t_config* cfg, int device, d2t_engine** out);
+int d2t_destroy(d2t_engine* e);
+const char* d2t_last_error(const d2t_engine* e); /* e may be NULL: last create error */
+const char* d2t_version(void);
+
+/*
+ * Replaces Model.load_state_dict / utils.model_utils.load_checkpoint
+ * (model_utils.py:136-237): hand every state_dict entry to the engine by its
+ * reference key, then finalize once.  `data` is a HOST
+ * pointer, contiguous, row-major; the engine copies it.
+ */
+int d2t_load_tensor(d2t_engine* e, const char* key, const void* data,
+                    const int64_t* shape, int ndim, int dtype);
+/* Folds eval-mode BatchNorm into per-channel scale/shift, repacks conv weights to
+ * [Cout][KH][KW][Cin] (K-major, NHWC activations) and uploads. */
+int d2t_finalize_weights(d2t_engine* e);
+
+/*
+ * Replaces Model.forward_encoder (build_model.py:36-43 -> build_seq.py:59-66 ->
+ * vit_encoder.py:249-268 -> patchembed.py:115-141 -> resnet.py:205-245).
+ * img_dev: (B,1,H,W) fp32 NCHW, H and W multiples of 32.
+ * ctx_dev: (B, ntok, hidden) fp32 out, ntok = 1 + gh*gw (see d2t_encoder_geometry).
+ */
+int d2t_encode(d2t_engine* e, const float* img_dev, int B, int H, int W,
+               float* ctx_dev, d2t_stream stream);
+/* (gh, gw) = output_shape, (pad_w, pad_h) = feat_pad of forward_encoder. */
+int d2t_encoder_geometry(const d2t_engine* e, int H, int W, int* gh, int* gw,
+                         int* pad_w, int* pad_h, int* ntok);
+
+/*
+ * Replaces TransformerPrediction.forward_greedy, eval branch (tfm.py:119-143), with a
+ * KV cache instead of the reference's full-prefix recompute.
+ * ctx_dev (B, ntok, hidden).  ids_dev (B, max_steps) int64: token chosen at each step.
+ * logits_dev (B, max_steps, vocab) fp32 or NULL.  Runs until every row has emitted END
+ * (when stop_on_all_eos, i.e. is_test=True) or max_steps; *steps_out (host) receives the
+ * number of steps the reference would have executed.  Synchronises the stream.
+ */
+int d2t_decode_greedy(d2t_engine* e, const float* ctx_dev, int B, int ntok,
+                      int max_steps, int stop_on_all_eos, int64_t* ids_dev,
+                      float* logits_dev, int* steps_out, d2t_stream stream);
+
+/*
+ * Replaces TransformerPrediction.forward_beam + tools/beam.py (tfm.py:145-186,
+ * beam.py:38-140), batched over B images (the reference is batch-1 only; each image gets
+ * a fresh beam).  best_ids_dev (B, max_steps) int64 padded with PAD(0);
+ * best_len_dev (B) int32; best_score_dev (B) fp32.
+ * trace_dev: optional (B, max_steps, beam, 2) int32 = (parent, word) of the top-k
+ * candidates per step in top-k order, -1 where unused; trace_score_dev optional
+ * (B, max_steps, beam) fp32.  Synchronises the stream.
+ */
+int d2t_decode_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, int beam,
+                    int max_steps, int64_t* best_ids_dev, int32_t* best_len_dev,
+                    float* best_score_dev, int32_t* trace_dev, float* trace_score_dev,
+                    int* steps_out, d2t_stream stream);
+
+/*
+ * Replaces AttentionV2.forward_greedy, eval branch (seq2seq_v2.py:176-293).
+ * ids_dev (B, max_steps) int64 (0 = [GO] after early exit, like the reference's
+ * probs.max(2) over untouched zero rows); logits_dev (B, max_steps, vocab) or NULL.
+ */
+int d2t_decode_attn_greedy(d2t_engine* e, const float* ctx_dev, int B, int ntok,
+                           int max_steps, int stop_on_all_eos, int64_t* ids_dev,
+                           float* logits_dev, int* steps_out, d2t_stream stream);
+
+/*
+ * Test / profiling hooks (not part of the reference surface).
+ */
+/* keep_taps != 0: d2t_encode keeps every intermediate activation alive for d2t_debug_tap. */
+int d2t_set_debug(d2t_engine* e, int keep_taps);
+/* Copies an intermediate activation of the LAST d2t_encode call to out_dev as NCHW/BND
+ * fp32 so it can be compared with the oracle taps.  names: "conv0_1","conv0_2","layer1",
+ * "conv1","layer2","conv2","pool3","layer3","conv3","layer4","conv4_1","conv4_2",
+ * "patch_embed","block0".."blockN".  *numel receives the element count (query with
+ * out_dev == NULL). */
+int d2t_debug_tap(d2t_engine* e, const char* name, float* out_dev, int64_t* numel,
+                  int64_t* shape4, d2t_stream stream);
+/* C[M,N] = act(A[M,K] * W[N,K]^T * scale[n] + shift[n]) through the configured GEMM
+ * path (unit parity test of the contraction kernels, including the tcgen05 ones). */
+int d2t_debug_gemm(d2t_engine* e, const float* a_dev, const float* w_dev,
+                   const float* scale_dev, const float* shift_dev, float* c_dev,
+                   int M, int N, int K, int act, int precision, d2t_stream stream);
+/* Number of kernel launches issued by this engine since creation (bench bookkeeping;
+ * launches replayed from a CUDA graph are counted per replay). */
+int64_t d2t_launch_count(const d2t_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DOC2TEX_B200_H_ */
