@@ -26,7 +26,7 @@ int pool_get(d2t_engine* e, T** out, size_t n) {
   return 0;
 }
 
-int dec_linear(d2t_engine* e, ConvGemm p, cudaStream_t s) { return run_contraction(e, p, nullptr, D2T_PREC_FP32, s); }
+int dec_linear(d2t_engine* e, ConvGemm p, cudaStream_t s) { return run_contraction(e, p, nullptr, e->cfg.precision, s); }
 
 int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long row_stride, const int* anc,
                       long long anc_parity, int anc_ld, int rows_per_src, const int* step, int n_fixed, int smem_ld,

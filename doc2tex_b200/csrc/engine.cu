@@ -40,7 +40,6 @@ struct ConvW {
   float* scale = nullptr;  // folded BN scale (or nullptr)
   float* shift = nullptr;  // folded BN shift / bias
   int cout = 0, cin = 0, kh = 0, kw = 0;
-  TcWeight tc;             // operand planes for the tcgen05 path (empty in fp32 mode)
 };
 
 struct Fmap {  // NHWC activation
@@ -90,6 +89,7 @@ struct d2t_engine {
   std::vector<void*> owned;  // device weight allocations
   std::map<std::string, ConvW> conv;
   std::map<std::string, float*> dev;  // linear weights, biases, LN params, embeddings (by reference key)
+  std::map<const float*, TcWeight> tcw;  // tensor-core operand planes + TMA maps, keyed by the fp32 weight matrix
 
   SlotPool enc_pool, dec_pool;
   bool keep_taps = false;
@@ -228,7 +228,11 @@ inline int grid_for(long long total, int block, int num_sms) {
 int run_contraction(d2t_engine* e, const ConvGemm& p, const TcWeight* tcw, int precision, cudaStream_t s) {
   if (p.K % 16 != 0 || p.C % 16 != 0)
     return e->fail(D2T_ERR_UNSUPPORTED, "contraction needs K and C multiples of 16 (K=%d C=%d)", p.K, p.C);
-  if (precision != D2T_PREC_FP32 && tcw != nullptr && tcw->ready && tc_supported(p)) {
+  if (precision != D2T_PREC_FP32 && tcw == nullptr) {
+    auto it = e->tcw.find(p.w);
+    if (it != e->tcw.end()) tcw = &it->second;
+  }
+  if (precision != D2T_PREC_FP32 && tcw != nullptr && tcw->ready && tcw->N == p.N && tcw->K == p.K && tc_supported(p)) {
     cudaError_t st = launch_conv_gemm_tc(p, *tcw, precision, s, e->num_sms);
     if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tcgen05 contraction launch failed: %s", cudaGetErrorString(st));
     e->launches += 1;
@@ -276,7 +280,7 @@ int conv_layer(d2t_engine* e, const std::string& name, const Fmap& x, Fmap* y, i
   p.ldc = c.cout; p.ldc2 = 0; p.ldr = c.cout; p.n_split = c.cout;
   p.B = x.B; p.H = x.H; p.W = x.W; p.C = x.C; p.KH = c.kh; p.KW = c.kw; p.SH = sh; p.SW = sw; p.PH = ph; p.PW = pw;
   p.OH = OH; p.OW = OW; p.M = x.B * OH * OW; p.N = c.cout; p.K = c.kh * c.kw * c.cin; p.act = act;
-  return run_contraction(e, p, &c.tc, e->cfg.precision, s);
+  return run_contraction(e, p, nullptr, e->cfg.precision, s);
 }
 
 int pool_layer(d2t_engine* e, const Fmap& x, Fmap* y, int sh, int sw, int ph, int pw, cudaStream_t s) {
@@ -339,7 +343,7 @@ int linear(d2t_engine* e, const float* x, const std::string& wkey, const std::st
   }
   ConvGemm p = linear_params(x, wi->second + (size_t)w_row_off * K, bias, out, M, N, K);
   p.act = act; p.res = res; p.ldr = N;
-  return run_contraction(e, p, nullptr, D2T_PREC_FP32, s);
+  return run_contraction(e, p, nullptr, e->cfg.precision, s);
 }
 
 }  // namespace
@@ -449,7 +453,7 @@ int d2t_finalize_weights(d2t_engine* e) {
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaDeviceSynchronize());
   for (void* p : e->owned) cudaFree(p);
-  e->owned.clear(); e->conv.clear(); e->dev.clear();
+  e->owned.clear(); e->conv.clear(); e->dev.clear(); e->tcw.clear();
   for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   e->graphs.clear();
   const d2t_config& c = e->cfg;
@@ -573,13 +577,40 @@ int d2t_finalize_weights(d2t_engine* e) {
     }
     if ((rc = finalize_attn_extras(e))) return rc;
   }
-  // operand planes for the tensor-core contraction path
+  // operand planes + TMA maps for the tensor-core contraction path: every conv (but the Cin=1 stem conv) and
+  // every Linear, including the row blocks of the packed in_proj matrices that are used on their own
   if (c.precision != D2T_PREC_FP32) {
+    auto prep = [&](const float* w, int N, int K) -> int {
+      if (!w || e->tcw.count(w)) return 0;
+      TcWeight tw;
+      cudaError_t st = tc_prepare_weight(w, N, K, c.precision, &tw, &e->owned);
+      if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tc_prepare_weight(N=%d,K=%d): %s", N, K, cudaGetErrorString(st));
+      e->tcw[w] = tw;
+      return 0;
+    };
     for (auto& kv : e->conv) {
       if (kv.first == "conv0_1") continue;
-      cudaError_t st = tc_prepare_weight(kv.second.w, kv.second.cout, kv.second.kh * kv.second.kw * kv.second.cin,
-                                         c.precision, &kv.second.tc, &e->owned);
-      if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tc_prepare_weight(%s): %s", kv.first.c_str(), cudaGetErrorString(st));
+      if ((rc = prep(kv.second.w, kv.second.cout, kv.second.kh * kv.second.kw * kv.second.cin))) return rc;
+    }
+    for (int i = 0; i < c.depth; ++i) {
+      const std::string p = SEQ + "blocks." + std::to_string(i) + ".";
+      if ((rc = prep(e->dev[p + "attn.qkv.weight"], 3 * D, D))) return rc;
+      if ((rc = prep(e->dev[p + "attn.proj.weight"], D, D))) return rc;
+      if ((rc = prep(e->dev[p + "mlp.fc1.weight"], 4 * D, D))) return rc;
+      if ((rc = prep(e->dev[p + "mlp.fc2.weight"], D, 4 * D))) return rc;
+    }
+    if (c.head == D2T_HEAD_TFM) {
+      for (int l = 0; l < c.dec_layers; ++l) {
+        const std::string p = PRED + "model.layers." + std::to_string(l) + ".";
+        if ((rc = prep(e->dev[p + "self_attn.in_proj_weight"], 3 * D, D))) return rc;
+        if ((rc = prep(e->dev[p + "self_attn.out_proj.weight"], D, D))) return rc;
+        if ((rc = prep(e->dev[p + "multihead_attn.in_proj_weight"], D, D))) return rc;                      // q rows
+        if ((rc = prep(e->dev[p + "multihead_attn.in_proj_weight"] + (size_t)D * D, 2 * D, D))) return rc;  // k|v rows
+        if ((rc = prep(e->dev[p + "multihead_attn.out_proj.weight"], D, D))) return rc;
+        if ((rc = prep(e->dev[p + "linear1.weight"], c.dec_ff, D))) return rc;
+        if ((rc = prep(e->dev[p + "linear2.weight"], D, c.dec_ff))) return rc;
+      }
+      if ((rc = prep(e->dev[PRED + "proj.weight"], c.vocab, D))) return rc;
     }
   }
   CUDA_TRY(e, cudaDeviceSynchronize());
@@ -739,6 +770,7 @@ int d2t_debug_gemm(d2t_engine* e, const float* a, const float* w, const float* s
   std::vector<void*> tmp;
   cudaError_t st = tc_prepare_weight(w, N, K, precision, &tw, &tmp);
   if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tc_prepare_weight: %s", cudaGetErrorString(st));
+  cudaDeviceSynchronize();
   if (!tw.ready || !tc_supported(p)) {
     for (void* q : tmp) cudaFree(q);
     return e->fail(D2T_ERR_UNSUPPORTED, "tcgen05 path does not support M=%d N=%d K=%d", M, N, K);

@@ -1,16 +1,549 @@
-// tcgen05 / TMEM / TMA implicit-GEMM contraction path (placeholder until the kernel lands).
+// tcgen05 / TMEM / TMA implicit-GEMM contraction for sm_100a.
+//
+//   out[m, n] = act((sum_k A[m,k] W[n,k]) * scale[n] + shift[n] + res[m,n])
+//
+// A is gathered on the fly from the fp32 NHWC activation tensor (implicit GEMM over (kh, kw, cin)),
+// W is the pre-packed K-major weight matrix.  One persistent CTA per SM, warp-specialised:
+//
+//   warps 0-3   epilogue      tcgen05.ld accumulator rows -> folded BN / bias / residual / activation -> HBM
+//   warps 4-11  A producers   LDG (coalesced 128 B runs of the NHWC row) -> split / convert -> swizzled STS
+//   warp  12    W producer    TMA (cp.async.bulk.tensor, 128B swizzle) of the weight tile, one per operand plane
+//   warp  13    MMA issuer    one thread issues tcgen05.mma (M=128, N=BLOCK_N, fp32 accumulators in TMEM)
+//
+// Pipelines: a STAGES-deep smem ring (full/empty mbarriers) between producers and the MMA thread, and a
+// two-deep TMEM accumulator ring (tmem_full/tmem_empty) between the MMA thread and the epilogue, so the
+// epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Precisions (d2t_precision):
+//   BF16     one pass:   bf16(A) . bf16(W)                                   kind::f16
+//   BF16X3   3 passes:   A_hi.W_hi + A_lo.W_hi + A_hi.W_lo, hi/lo bf16       kind::f16   (~2^-16 relative)
+//   TF32X3   3 passes:   same split with tf32 hi/lo kept in fp32 containers  kind::tf32  (~2^-21 relative)
+// The split of A happens in registers inside the producer warps, W planes are split once at load time.
 #pragma once
+#include <cuda.h>
 #include <vector>
 #include "common.cuh"
 
 namespace d2t {
 
-struct TcWeight {
-  bool ready = false;
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ uint32_t mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n}\n"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <bool TF32>
+__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (TF32) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  } else {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte-swizzled operand tile: rows of 128 B, 8-row atoms of 1024 B (SBO), version 1 (sm_100).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);        // start address, bits [0,14)
+  d |= (uint64_t)1 << 16;                         // leading byte offset (unused for swizzled K-major), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;               // stride byte offset = 1024 B, bits [32,46)
+  d |= (uint64_t)1 << 46;                         // descriptor version, bits [46,48)
+  d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B, bits [61,64)
+  return d;
+}
+// Instruction descriptor: fp32 accumulate, A/B K-major, formats BF16 (1) or TF32 (2), M=128.
+__host__ __device__ constexpr uint32_t make_idesc(int fmt, int n) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------
+// Kernel configuration
+// ------------------------------------------------------------------------------------------------
+constexpr int TC_BM = 128;
+constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;
+constexpr int TC_THREADS = (TC_EPI_WARPS + TC_PROD_WARPS + 2) * 32;  // 448
+constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;                  // 256
+constexpr int TC_ROWS_PER_THREAD = TC_BM * 8 / TC_PROD_THREADS;      // 4 (8 x 16-byte chunks per 128-byte row)
+
+template <bool TF32, int PASSES, int BN>
+struct TcCfg {
+  static constexpr int PLANES = PASSES == 1 ? 1 : 2;
+  static constexpr int KB_ELEMS = TF32 ? 32 : 64;   // elements per 128-byte operand row
+  static constexpr int CH_ELEMS = TF32 ? 4 : 8;     // elements per 16-byte chunk
+  static constexpr int A_BYTES = TC_BM * 128;       // per plane
+  static constexpr int B_BYTES = BN * 128;          // per plane
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  static constexpr int SMEM_BUDGET = 200 * 1024;
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two (BN in {64,128,256})
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(STAGES >= 2, "need at least a double buffer");
 };
 
-inline bool tc_supported(const ConvGemm&) { return false; }
-inline cudaError_t tc_prepare_weight(const float*, int, int, int, TcWeight*, std::vector<void*>*) { return cudaSuccess; }
-inline cudaError_t launch_conv_gemm_tc(const ConvGemm&, const TcWeight&, int, cudaStream_t, int) { return cudaErrorNotSupported; }
+struct TcWeight {
+  bool ready = false;
+  int precision = 0, N = 0, K = 0;
+  void* hi = nullptr;
+  void* lo = nullptr;
+  CUtensorMap map_hi[3], map_lo[3];  // TMA boxes of 64 / 128 / 256 weight rows
+};
+
+template <bool TF32, int PASSES, int BN>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi,
+                    const __grid_constant__ CUtensorMap map_lo, int tiles_m, int tiles_n) {
+  using Cfg = TcCfg<TF32, PASSES, BN>;
+  constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - tc::smem_u32(smem_raw));
+  // stage s: [A plane 0][A plane 1][B plane 0][B plane 1]
+  const uint32_t bars = smem_base + STAGES * Cfg::STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = tiles_m * tiles_n;
+  const int nkb = (p.K + Cfg::KB_ELEMS - 1) / Cfg::KB_ELEMS;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(full_bar(s), TC_PROD_THREADS + 1);   // 256 A-producer arrivals + the TMA thread's expect_tx arrive
+      tc::mbar_init(empty_bar(s), 1);                     // one tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(tfull_bar(a), 1);                     // one tcgen05.commit
+      tc::mbar_init(tempty_bar(a), TC_EPI_WARPS * 32);    // every epilogue thread
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == TC_EPI_WARPS + TC_PROD_WARPS + 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == TC_EPI_WARPS + TC_PROD_WARPS && lane == 0) {
+    tc::tma_prefetch_desc(&map_hi);
+    if (PLANES == 2) tc::tma_prefetch_desc(&map_lo);
+  }
+  tc::tcgen05_before_sync();
+  __syncthreads();
+  tc::tcgen05_after_sync();
+  const uint32_t tmem_base = *tmem_slot_gen;
+
+  if (warp < TC_EPI_WARPS) {
+    // =========================== epilogue ===========================
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+      const int acc = it & 1;
+      tc::mbar_wait(tfull_bar(acc), (it >> 1) & 1);
+      tc::tcgen05_after_sync();
+      const int m = tm * TC_BM + warp * 32 + lane;
+      const bool m_ok = m < p.M;
+      float* orow1 = p.out + (size_t)m * p.ldc;
+      float* orow2 = nullptr;   // columns >= n_split (KV-cache slot of the current decode step)
+      if (p.out2) orow2 = p.out2 + (p.dyn ? (long long)(*p.dyn) * p.dyn_mul2 : 0) + (size_t)m * p.ldc2 - p.n_split;
+      const float* rrow = p.res ? p.res + (size_t)m * p.ldr : nullptr;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + j * 32), r);
+        tc::tmem_ld_wait();
+        const int n0 = tn * BN + j * 32;
+        float* orow = (orow2 != nullptr && n0 >= p.n_split) ? orow2 : orow1;
+        if (m_ok && n0 < p.N) {
+          if (n0 + 32 <= p.N) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int n = n0 + q * 4;
+              float4 v = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                                     __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+              if (p.scale) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
+                v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
+              }
+              if (p.shift) {
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
+                v.x += sh.x; v.y += sh.y; v.z += sh.z; v.w += sh.w;
+              }
+              if (rrow) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + n));
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+              }
+              v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
+              v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
+              *reinterpret_cast<float4*>(orow + n) = v;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const int n = n0 + q;
+              if (n < p.N) {
+                float v = __uint_as_float(r[q]);
+                if (p.scale) v *= __ldg(p.scale + n);
+                if (p.shift) v += __ldg(p.shift + n);
+                if (rrow) v += __ldg(rrow + n);
+                orow[n] = apply_act(v, p.act);
+              }
+            }
+          }
+        }
+      }
+      tc::tcgen05_before_sync();
+      tc::mbar_arrive(tempty_bar(acc));
+    }
+  } else if (warp < TC_EPI_WARPS + TC_PROD_WARPS) {
+    // =========================== A producers (implicit-GEMM gather) ===========================
+    const int pt = threadIdx.x - TC_EPI_WARPS * 32;       // 0..255
+    const int chunk = pt & 7;                             // 16-byte chunk within the 128-byte operand row
+    const int rg = pt >> 3;                               // rows rg + 32*i
+    constexpr int RPT = TC_ROWS_PER_THREAD;
+    constexpr int LD4 = TF32 ? 1 : 2;                     // float4 loads per (row, chunk)
+    int kit = 0;                                          // running k-block counter across tiles (ring position)
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / tiles_n;
+      const float* base[RPT];
+      int ih0[RPT], iw0[RPT];
+      bool ok[RPT];
+#pragma unroll
+      for (int i = 0; i < RPT; ++i) {
+        const int m = tm * TC_BM + rg + 32 * i;
+        ok[i] = m < p.M;
+        const int mm = ok[i] ? m : 0;
+        const int ow = mm % p.OW;
+        const int t = mm / p.OW;
+        const int oh = t % p.OH;
+        const int b = t / p.OH;
+        ih0[i] = oh * p.SH - p.PH;
+        iw0[i] = ow * p.SW - p.PW;
+        base[i] = p.x + (size_t)b * p.H * p.W * p.C;
+      }
+      float4 v[2][RPT][LD4];
+      auto load = [&](int kb, float4 (&dst)[RPT][LD4]) {
+        const int k = kb * Cfg::KB_ELEMS + chunk * Cfg::CH_ELEMS;
+        const bool kok = k < p.K;
+        const int tap = kok ? k / p.C : 0;
+        const int ci = k - tap * p.C;
+        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int ih = ih0[i] + kh, iw = iw0[i] + kw;
+          const bool valid = kok && ok[i] && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+          const float4* src = reinterpret_cast<const float4*>(base[i] + ((size_t)ih * p.W + iw) * p.C + ci);
+#pragma unroll
+          for (int q = 0; q < LD4; ++q) dst[i][q] = valid ? __ldg(src + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto store = [&](int s, const float4 (&src)[RPT][LD4]) {
+        uint8_t* a_hi = smem_gen + (size_t)s * Cfg::STAGE_BYTES;
+        uint8_t* a_lo = a_hi + Cfg::A_BYTES;
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+          const int r = rg + 32 * i;
+          const uint32_t off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+          if constexpr (TF32) {
+            const float4 x = src[i][0];
+            float4 h;
+            h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+            h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+            h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+            h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+            *reinterpret_cast<float4*>(a_hi + off) = h;
+            if constexpr (PLANES == 2)
+              *reinterpret_cast<float4*>(a_lo + off) = make_float4(x.x - h.x, x.y - h.y, x.z - h.z, x.w - h.w);
+          } else {
+            const float f[8] = {src[i][0].x, src[i][0].y, src[i][0].z, src[i][0].w,
+                                src[i][1].x, src[i][1].y, src[i][1].z, src[i][1].w};
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * q]), h1 = __float2bfloat16_rn(f[2 * q + 1]);
+              hw[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+              if constexpr (PLANES == 2) {
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * q] - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * q + 1] - __bfloat162float(h1));
+                lw[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+              }
+            }
+            *reinterpret_cast<uint4*>(a_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            if constexpr (PLANES == 2) *reinterpret_cast<uint4*>(a_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
+        }
+      };
+      load(0, v[0]);
+      for (int kb = 0; kb < nkb; kb += 2) {
+        // unrolled by two so that the register double buffer is statically indexed
+        if (kb + 1 < nkb) load(kb + 1, v[1]);
+        {
+          const int s = kit % STAGES;
+          tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
+          store(s, v[0]);
+          tc::fence_proxy_async();
+          tc::mbar_arrive(full_bar(s));
+          ++kit;
+        }
+        if (kb + 1 < nkb) {
+          if (kb + 2 < nkb) load(kb + 2, v[0]);
+          const int s = kit % STAGES;
+          tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
+          store(s, v[1]);
+          tc::fence_proxy_async();
+          tc::mbar_arrive(full_bar(s));
+          ++kit;
+        }
+      }
+    }
+  } else if (warp == TC_EPI_WARPS + TC_PROD_WARPS) {
+    // =========================== W producer (TMA) ===========================
+    if (lane == 0) {
+      int kit = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+        for (int kb = 0; kb < nkb; ++kb, ++kit) {
+          const int s = kit % STAGES;
+          tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(full_bar(s), PLANES * Cfg::B_BYTES);
+          const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES;
+          tc::tma_load_2d(b_hi, &map_hi, full_bar(s), kb * Cfg::KB_ELEMS, tn * BN);
+          if (PLANES == 2) tc::tma_load_2d(b_hi + Cfg::B_BYTES, &map_lo, full_bar(s), kb * Cfg::KB_ELEMS, tn * BN);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(TF32 ? 2 : 1, BN);
+      int kit = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        tc::mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+        tc::tcgen05_after_sync();
+        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++kit) {
+          const int s = kit % STAGES;
+          tc::mbar_wait(full_bar(s), (kit / STAGES) & 1);
+          tc::tcgen05_after_sync();
+          const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
+          const uint32_t b_hi = a_hi + PLANES * Cfg::A_BYTES;
+          const uint64_t da_hi = tc::make_smem_desc(a_hi), db_hi = tc::make_smem_desc(b_hi);
+          const uint64_t da_lo = tc::make_smem_desc(a_hi + Cfg::A_BYTES), db_lo = tc::make_smem_desc(b_hi + Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)  // 4 x (UMMA_K * elem) = 4 x 32 B = one 128-byte row
+            tc::umma<TF32>(d, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb | k) != 0);
+          if constexpr (PASSES == 3) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma<TF32>(d, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tc::umma<TF32>(d, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+          }
+          tc::umma_commit(empty_bar(s));   // frees the smem stage once the MMAs above have read it
+        }
+        tc::umma_commit(tfull_bar(acc));    // accumulator complete -> epilogue
+      }
+    }
+    __syncwarp();
+  }
+  tc::tcgen05_before_sync();
+  __syncthreads();
+  if (warp == TC_EPI_WARPS + TC_PROD_WARPS + 1) {
+    tc::tcgen05_after_sync();
+    tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------------
+__global__ void tc_split_weight_kernel(const float* __restrict__ w, void* __restrict__ hi, void* __restrict__ lo,
+                                       long long n, int tf32) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float x = w[i];
+    if (tf32) {
+      const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+      reinterpret_cast<float*>(hi)[i] = h;
+      if (lo) reinterpret_cast<float*>(lo)[i] = x - h;
+    } else {
+      const __nv_bfloat16 h = __float2bfloat16_rn(x);
+      reinterpret_cast<__nv_bfloat16*>(hi)[i] = h;
+      if (lo) reinterpret_cast<__nv_bfloat16*>(lo)[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled tc_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// Wide tiles (best operand reuse) when they still fill the machine, else narrower tiles for more CTAs.
+inline int tc_pick_bn(int M, int N, int num_sms) {
+  const int tiles_m = (M + TC_BM - 1) / TC_BM;
+  int bn = N % 256 == 0 ? 256 : (N <= 64 ? 64 : 128);
+  while (bn > 64 && tiles_m * ((N + bn - 1) / bn) < num_sms) bn >>= 1;
+  return bn;
+}
+
+inline bool tc_supported(const ConvGemm& p) {
+  // fp32 NHWC activations with 16-byte chunks inside one filter tap; KV-cache split outputs stay on the FFMA kernel
+  return p.C % 8 == 0 && p.K % 8 == 0 && p.ldc % 4 == 0 && (p.res == nullptr || p.ldr % 4 == 0) && p.N % 4 == 0 &&
+         (p.out2 == nullptr || (p.n_split % 32 == 0 && p.ldc2 % 4 == 0 && p.dyn_mul2 % 4 == 0));
+}
+
+inline cudaError_t tc_prepare_weight(const float* w_dev, int N, int K, int precision, TcWeight* out,
+                                     std::vector<void*>* owned) {
+  out->ready = false;
+  if (precision == 0) return cudaSuccess;
+  PFN_encodeTiled enc = tc_encode_fn();
+  if (!enc) return cudaErrorNotSupported;
+  if (K % 8 != 0) return cudaSuccess;  // unsupported shape: caller falls back to the FFMA kernel
+  const bool tf32 = precision == 1;
+  const bool two = precision != 3;
+  const size_t esz = tf32 ? 4 : 2;
+  const long long n = (long long)N * K;
+  cudaError_t st;
+  if ((st = cudaMalloc(&out->hi, n * esz)) != cudaSuccess) return st;
+  owned->push_back(out->hi);
+  out->lo = nullptr;
+  if (two) {
+    if ((st = cudaMalloc(&out->lo, n * esz)) != cudaSuccess) return st;
+    owned->push_back(out->lo);
+  }
+  tc_split_weight_kernel<<<(int)((n + 255) / 256 > 4096 ? 4096 : (n + 255) / 256), 256>>>(w_dev, out->hi, out->lo, n, tf32 ? 1 : 0);
+  if ((st = cudaGetLastError()) != cudaSuccess) return st;
+  out->precision = precision; out->N = N; out->K = K;
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+  const cuuint64_t gstr[1] = {(cuuint64_t)K * esz};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  for (int i = 0; i < 3; ++i) {
+    const cuuint32_t box[2] = {(cuuint32_t)(tf32 ? 32 : 64), (cuuint32_t)(64 << i)};
+    CUresult r = enc(&out->map_hi[i], dt, 2, out->hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    out->map_lo[i] = out->map_hi[i];
+    if (two) {
+      r = enc(&out->map_lo[i], dt, 2, out->lo, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+  }
+  out->ready = true;
+  return cudaSuccess;
+}
+
+template <bool TF32, int PASSES, int BN>
+inline cudaError_t tc_launch_one(const ConvGemm& p, const TcWeight& w, cudaStream_t s, int num_sms) {
+  using Cfg = TcCfg<TF32, PASSES, BN>;
+  static bool attr_set = false;
+  auto kern = conv_gemm_tc_kernel<TF32, PASSES, BN>;
+  if (!attr_set) {
+    cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (st != cudaSuccess) return st;
+    attr_set = true;
+  }
+  const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = (p.N + BN - 1) / BN;
+  const int grid = tiles_m * tiles_n < num_sms ? tiles_m * tiles_n : num_sms;
+  constexpr int mi = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(p, w.map_hi[mi], w.map_lo[mi], tiles_m, tiles_n);
+  return cudaGetLastError();
+}
+
+template <bool TF32, int PASSES>
+inline cudaError_t tc_launch_bn(const ConvGemm& p, const TcWeight& w, cudaStream_t s, int num_sms) {
+  switch (tc_pick_bn(p.M, p.N, num_sms)) {
+    case 256: return tc_launch_one<TF32, PASSES, 256>(p, w, s, num_sms);
+    case 128: return tc_launch_one<TF32, PASSES, 128>(p, w, s, num_sms);
+    case 64: return tc_launch_one<TF32, PASSES, 64>(p, w, s, num_sms);
+  }
+  return cudaErrorInvalidValue;
+}
+
+inline cudaError_t launch_conv_gemm_tc(const ConvGemm& p, const TcWeight& w, int precision, cudaStream_t s, int num_sms) {
+  if (!w.ready || w.precision != precision) return cudaErrorInvalidValue;
+  switch (precision) {
+    case 1: return tc_launch_bn<true, 3>(p, w, s, num_sms);
+    case 2: return tc_launch_bn<false, 3>(p, w, s, num_sms);
+    case 3: return tc_launch_bn<false, 1>(p, w, s, num_sms);
+  }
+  return cudaErrorInvalidValue;
+}
 
 }  // namespace d2t

@@ -1,0 +1,85 @@
+"""tcgen05 contraction kernel: unit parity against a float64 torch reference, and whole-encoder parity per precision."""
+import pytest
+import torch
+
+from doc2tex_b200 import synth
+from tests.util import rel_err, state_dict_for
+
+pytestmark = pytest.mark.gpu
+
+# relative error (max-abs / max-abs) a contraction may show per precision mode; K up to 4608.
+# Measured on B200: bf16 2e-3; bf16x3 4e-6 (K<=576) .. 1.5e-5 (K=4608); tf32x3 1e-6 (K=64) .. 3e-5 (K=4608).
+# The growth with K is the tensor core's fp32 accumulator (truncating adds, one per UMMA_K step), which is
+# why tf32x3 (twice the accumulation steps of bf16x3) is not more accurate than bf16x3 at large K.
+GEMM_TOL = {"bf16": 2e-2, "bf16x3": 1e-4, "tf32x3": 1e-4}
+# whole encoder (31 stacked contractions + ViT) vs the fp32 oracle
+CTX_TOL = {"bf16": 6e-2, "bf16x3": 1e-3, "tf32x3": 1e-4}
+
+
+def _engine(precision):
+    from doc2tex_b200.engine import Engine
+    cfg, sd = state_dict_for("TFM", None)
+    e = Engine(cfg, "cuda:0", precision=precision)
+    return e, cfg, sd
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3", "tf32x3"])
+def test_tc_gemm_matches_float64(built_lib, precision):
+    e, _, _ = _engine("fp32")
+    g = torch.Generator().manual_seed(1)
+    shapes = [(128, 64, 64), (300, 256, 256), (1000, 512, 4608), (257, 128, 576), (4096, 64, 288), (130, 504, 256),
+              (20000, 256, 2048)]
+    for (M, N, K) in shapes:
+        a = torch.randn(M, K, generator=g)
+        w = torch.randn(N, K, generator=g) / K ** 0.5
+        sc = torch.rand(N, generator=g) + 0.5
+        sh = torch.randn(N, generator=g)
+        ref = torch.relu((a.double() @ w.double().t()) * sc.double() + sh.double()).float()
+        out = e.gemm(a.cuda(), w.cuda(), sc.cuda(), sh.cuda(), act=1, precision=precision).cpu()
+        err = rel_err(out, ref)
+        print(f"{precision} M={M} N={N} K={K}: rel err {err:.3e}")
+        assert err < GEMM_TOL[precision], (precision, M, N, K, err)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "bf16x3", "tf32x3"])
+def test_tc_encoder_matches_oracle(built_lib, precision):
+    from oracle import oracle_model as om
+    e, cfg, sd = _engine(precision)
+    e.load_state_dict(sd)
+    img = synth.make_images(2, 64, 256, seed=2024)
+    e.set_debug(True)
+    ctx, _, _ = e.encode(img.cuda())
+    taps = {}
+    ctx_ref, _, _ = om.encoder_forward(sd, img, taps=taps)
+    for name, ref in taps.items():
+        print(f"{precision} stage {name}: rel err {rel_err(e.tap(name).cpu(), ref):.3e}")
+    err = rel_err(ctx.cpu(), ctx_ref)
+    print(f"{precision} ctx rel err {err:.3e}")
+    assert err < CTX_TOL[precision]
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "tf32x3"])
+def test_tc_fp32_parity_modes_decode_token_exact(built_lib, precision):
+    """The error-compensated tensor-core modes must reproduce the reference's tokens (fp32 parity gate)."""
+    from doc2tex_b200.engine import Engine
+    from tests.util import REL_TOL_FP32, end_bias_of, load_golden
+    for case in ("tfm_64x256_full", "tfm_64x256_end15"):
+        g = load_golden(case)
+        cfg, sd = state_dict_for("TFM", end_bias_of(g))
+        e = Engine(cfg, "cuda:0", precision=precision)
+        e.load_state_dict(sd)
+        img = synth.make_images(2, 64, 256, seed=2024)
+        ctx, _, _ = e.encode(img.cuda())
+        assert rel_err(ctx.cpu(), torch.from_numpy(g["ctx"])) < REL_TOL_FP32
+        ids, logits, steps = e.decode_greedy(ctx, is_test=True)
+        ref_ids = torch.from_numpy(g["greedy_gen"])
+        assert steps == ref_ids.shape[1]
+        assert torch.equal(ids[:, :steps].cpu(), ref_ids)
+        ref_logits = torch.from_numpy(g["greedy_logits"])
+        for j, s in enumerate(g["greedy_logit_steps"].tolist()):
+            assert rel_err(logits[:, s].cpu(), ref_logits[:, j]) < REL_TOL_FP32, s
+        bids, blen, bscore, _, _, _ = e.decode_beam(ctx, 5)
+        for i in range(2):
+            n = int(g["beam_len"][i])
+            assert int(blen[i]) == n and bids[i, :n].cpu().tolist() == g["beam_seq"][i, :n].tolist()
+        e.close()

@@ -1,0 +1,124 @@
+"""CPU: host-side logic — converters, synthetic weights, config translation, Model surface, sharding + gather (gloo)."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+import torch
+
+from doc2tex_b200 import synth
+from doc2tex_b200.modules.converter import AttnLabelConverter, TFMLabelConverter, create_converter
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_converter_ids_and_roundtrip(tmp_path):
+    vocab = synth.make_vocab(10)
+    t = TFMLabelConverter(vocab, "cpu")
+    a = AttnLabelConverter(vocab, "cpu")
+    assert (t.PAD(), t.START(), t.END(), t.UNK()) == (0, 1, 2, 3)       # tfm_converter.py:8
+    assert (a.START(), a.END(), a.UNK()) == (0, 1, 2)                   # attn_converter.py:8
+    ids, lens = t.encode([vocab[:3], ["nope"] + vocab[:1]], batch_max_length=6)
+    assert ids.shape == (2, 8) and lens.tolist() == [4, 3]
+    assert ids[0].tolist() == [1, 4, 5, 6, 2, 0, 0, 0] and ids[1, 1].item() == 3
+    assert t.decode(ids[:, 1:5])[0] == f"{vocab[0]} {vocab[1]} {vocab[2]} [s]"
+    assert t.detokenize(ids[:, 1:])[0] == vocab[:3]
+    ids_a, _ = a.encode([vocab[:2]], batch_max_length=4)
+    assert ids_a[0].tolist() == [0, 3, 4, 1, 0, 0]
+    # over-long labels are truncated to batch_max_length tokens + [s]
+    ids_l, lens_l = t.encode([vocab * 2], batch_max_length=5)
+    assert ids_l.shape == (1, 7) and ids_l[0, -1].item() == 2 and lens_l.item() == 21
+    p = tmp_path / "vocab.txt"
+    p.write_text("\n".join(vocab) + "\n")
+    cfg = {"vocab": str(p), "Prediction": {"name": "TFM"}}
+    c = create_converter(cfg, "cpu")
+    assert isinstance(c, TFMLabelConverter) and cfg["character"] == vocab
+    cfg["Prediction"]["name"] = "Attnv2"
+    assert isinstance(create_converter(cfg, "cpu"), AttnLabelConverter)
+
+
+def test_synth_state_dict_is_deterministic_and_shaped():
+    cfg = synth.make_config("TFM")
+    a = synth.make_state_dict(cfg, seed=7)
+    b = synth.make_state_dict(cfg, seed=7)
+    assert len(a) == 346 and all(torch.equal(a[k], b[k]) for k in a)
+    assert a[synth.SEQ + "pos_embed"].shape == (1, 679, 256)
+    assert a[synth.PRED + "proj.weight"].shape == (504, 256)
+    assert synth.make_state_dict(cfg, seed=7, suppress_end=True)[synth.PRED + "proj.bias"][2].item() == -1e4
+    x = synth.make_images(3, 64, 256, seed=5)
+    assert x.shape == (3, 1, 64, 256) and x.max() <= 1 and x.min() >= -1
+    assert torch.equal(x[1:], synth.make_images(2, 64, 256, seed=6))    # a shard equals the rows of the full batch
+    assert synth.grid_hw(64, 256) == (2, 33) and synth.grid_hw(192, 896) == (6, 113)
+
+
+def test_config_translation_and_rejections():
+    from doc2tex_b200.engine import EngineError, config_from_opt
+    c = config_from_opt(synth.make_config("TFM"), "bf16x3")
+    assert (c.hidden, c.depth, c.heads, c.max_tokens, c.head, c.vocab, c.dec_layers, c.dec_ff, c.precision) == \
+           (256, 6, 8, 679, 1, 504, 4, 1024, 2)
+    c = config_from_opt(synth.make_config("Attnv2"))
+    assert (c.head, c.vocab, c.attn_hidden, c.attn_kernel_dim, c.attn_kernel_size, c.max_seq_len) == (2, 503, 256, 128, 2, 150)
+    bad = synth.make_config("TFM")
+    bad["SequenceModeling"]["params"]["fix_embed"] = False
+    with pytest.raises(EngineError):
+        config_from_opt(bad)
+    bad = synth.make_config("TFM")
+    bad["Prediction"]["name"] = "CTC"
+    with pytest.raises(EngineError):
+        config_from_opt(bad)
+
+
+def test_model_surface_without_gpu_fails_loudly():
+    from doc2tex_b200.engine import EngineError
+    from doc2tex_b200.modules.build_model import Model
+    cfg = synth.make_config("TFM")
+    m = Model(cfg)
+    sd = synth.make_state_dict(cfg, seed=3)
+    assert set(m.state_dict().keys()) == set(sd.keys())                # reference schema
+    m.load_state_dict(sd, strict=True)
+    assert cfg["Prediction"]["params"]["num_classes"] == 504            # build_pred.py:16-26 side effect kept
+    with pytest.raises(EngineError):
+        m.train()
+    if not torch.cuda.is_available():
+        with pytest.raises(EngineError):
+            m.forward_encoder(torch.zeros(1, 1, 64, 256))               # no silent CPU fallback
+
+
+def test_shard_range_partitions():
+    from doc2tex_b200.dist import shard_range
+    for n, w in [(256, 8), (10, 4), (3, 8), (1, 1)]:
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+        assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_gather_results_gloo_world2(tmp_path):
+    """N>1 host path on CPU: two gloo ranks with ragged shards, one all-gather, batch order restored."""
+    script = tmp_path / "w.py"
+    script.write_text(textwrap.dedent(f"""
+        import os, sys
+        sys.path.insert(0, {ROOT!r})
+        import torch, torch.distributed as dist
+        from doc2tex_b200.dist import shard_range, gather_results
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+        n, T = 5, 7
+        full = torch.arange(n * T, dtype=torch.int64).reshape(n, T)
+        lens = torch.arange(n, dtype=torch.int32) + 1
+        sc = -torch.arange(n, dtype=torch.float32) - 0.25
+        lo, hi = shard_range(n, r, w)
+        ids, l, s = gather_results(full[lo:hi].clone(), lens[lo:hi].clone(), sc[lo:hi].clone(), n_total=n)
+        assert torch.equal(ids, full) and torch.equal(l, lens) and torch.equal(s, sc), (ids, l, s)
+        ids2, _, _ = gather_results(full[lo:hi].clone())
+        assert torch.equal(ids2, full)
+        dist.destroy_process_group()
+        print("rank", r, "ok")
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2

@@ -1,0 +1,86 @@
+"""CPU: the oracle restatement (oracle/oracle_model.py) against the golden vectors minted from the LIVE
+reference by oracle/make_golden.py.  This is what pins the oracle (the reference has no tests)."""
+import numpy as np
+import pytest
+import torch
+
+from doc2tex_b200 import synth
+from oracle import oracle_model as om
+from tests.util import end_bias_of, load_golden, state_dict_for
+
+
+@pytest.fixture(scope="module")
+def threads():
+    torch.set_num_threads(min(8, torch.get_num_threads()))
+
+
+def _ctx(case, H=64, W=256, B=2):
+    g = load_golden(case)
+    cfg, sd = state_dict_for("TFM", end_bias_of(g))
+    img = synth.make_images(B, H, W, seed=2024)
+    ctx, grid, pad = om.encoder_forward(sd, img)
+    return g, sd, ctx, grid, pad
+
+
+def test_encoder_matches_reference_golden(threads):
+    g, sd, ctx, grid, pad = _ctx("tfm_64x256_natural")
+    assert tuple(grid) == tuple(g["grid"]) == (2, 33) and tuple(pad) == tuple(g["pad"]) == (1, 1)
+    ref = torch.from_numpy(g["ctx"])
+    assert (ctx - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+def test_encoder_other_size_matches_reference_golden(threads):
+    g, sd, ctx, grid, pad = _ctx("tfm_96x384_full", 96, 384, 1)
+    assert tuple(grid) == tuple(g["grid"]) and ctx.shape[1] == 148
+    ref = torch.from_numpy(g["ctx"])
+    assert (ctx - ref).abs().max().item() <= 2e-5 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("case", ["tfm_64x256_full", "tfm_64x256_end15", "tfm_64x256_end20"])
+def test_tfm_greedy_matches_reference_golden(threads, case):
+    g, sd, ctx, _, _ = _ctx(case)
+    ids, logits, gen = om.TFMHead(sd, max_seq_len=150).greedy(ctx, is_test=True)
+    assert torch.equal(ids, torch.from_numpy(g["greedy_ids"]))          # the reference's preds_index
+    assert torch.equal(gen, torch.from_numpy(g["greedy_gen"]))          # the generated tokens
+    ref = torch.from_numpy(g["greedy_logits"])
+    for j, s in enumerate(g["greedy_logit_steps"].tolist()):
+        assert (logits[:, s] - ref[:, j]).abs().max().item() <= 1e-4
+
+
+@pytest.mark.parametrize("case,img", [("tfm_64x256_end15", 0), ("tfm_64x256_end20", 1)])
+def test_tfm_beam_matches_reference_golden(threads, case, img):
+    g, sd, ctx, _, _ = _ctx(case)
+    tr = []
+    seq, score = om.TFMHead(sd, max_seq_len=150).beam(ctx[img:img + 1], 5, trace=tr)
+    n = int(g["beam_len"][img])
+    assert seq == g["beam_seq"][img, :n].tolist()
+    assert abs(score - float(g["beam_score"][img])) <= 1e-3
+    for t, (p, w, s) in enumerate(tr[:8]):
+        k = len(p)
+        assert p == g["beam_parents"][img, t, :k].tolist() and w == g["beam_words"][img, t, :k].tolist()
+
+
+@pytest.mark.parametrize("case", ["attnv2_64x256_full", "attnv2_64x256_end"])
+def test_attnv2_greedy_matches_reference_golden(threads, case):
+    g = load_golden(case)
+    cfg, sd = state_dict_for("Attnv2", end_bias_of(g))
+    img = synth.make_images(2, 64, 256, seed=2024)
+    ctx, _, _ = om.encoder_forward(sd, img)
+    ids, probs = om.AttnV2Head(sd).greedy(ctx, 150, True)
+    assert torch.equal(ids, torch.from_numpy(g["ids"]))
+    ref = torch.from_numpy(g["logits"])
+    for j, s in enumerate(g["logit_steps"].tolist()):
+        assert (probs[:, s] - ref[:, j]).abs().max().item() <= 1e-4
+
+
+def test_oracle_edge_cases():
+    """Quirks the engine must share: causal mask values, prefix pos-embed slice, -inf pooling pad, tie rule."""
+    m = om.TFMHead.causal_mask(4)
+    assert m[2, 1] == 0 and m[1, 2] == float("-inf") and m[3, 3] == 0
+    x = torch.zeros(1, 1, 2, 3)
+    x[0, 0, :, 0] = -5.0
+    y = torch.nn.functional.max_pool2d(x, 2, (2, 1), (0, 1))
+    assert y.shape == (1, 1, 1, 4) and y[0, 0, 0, 0] == -5.0          # padding is -inf, not 0 (quirk Q1)
+    assert int(torch.argmax(torch.tensor([1.0, 3.0, 3.0]))) == 1       # lowest index wins
+    pe = synth.sincos_pos_embed(256, 6, 113)
+    assert pe.shape == (1, 679, 256) and float(pe[0, 0].abs().max()) == 0.0

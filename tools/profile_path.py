@@ -1,0 +1,41 @@
+"""Small driver for ncu: one encode + a short decode of the bench workload (no CUDA graph so every launch is listed).
+
+    python tools/profile_path.py --batch 256 --steps 4 --mode greedy --precision bf16x3
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from doc2tex_b200 import synth  # noqa: E402
+from doc2tex_b200.engine import Engine  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--batch", type=int, default=256)
+ap.add_argument("--steps", type=int, default=4)
+ap.add_argument("--mode", default="greedy")
+ap.add_argument("--beam", type=int, default=5)
+ap.add_argument("--precision", default="bf16x3")
+ap.add_argument("--height", type=int, default=64)
+ap.add_argument("--width", type=int, default=256)
+ap.add_argument("--warm", type=int, default=1)
+ap.add_argument("--graphs", action="store_true")
+a = ap.parse_args()
+
+cfg = synth.make_config("TFM")
+sd = synth.make_state_dict(cfg, seed=1111, suppress_end=True)
+eng = Engine(cfg, "cuda:0", precision=a.precision, use_graphs=a.graphs)
+eng.load_state_dict(sd)
+img = synth.make_images(a.batch, a.height, a.width, seed=2024).cuda()
+for i in range(a.warm + 1):
+    l0 = eng.launch_count()
+    ctx, _, _ = eng.encode(img)
+    l1 = eng.launch_count()
+    if a.mode == "greedy":
+        eng.decode_greedy(ctx, a.steps, is_test=True, return_logits=False)
+    else:
+        eng.decode_beam(ctx, a.beam, a.steps)
+    torch.cuda.synchronize()
+    print(f"pass {i}: encode launches {l1 - l0}, decode launches {eng.launch_count() - l1}")
