@@ -26,7 +26,37 @@ struct ConvGemm {
   int B, H, W, C, KH, KW, SH, SW, PH, PW, OH, OW;
   int M, N, K;
   int act;
+  // tensor-core extras (ignored by the FFMA kernel)
+  __nv_bfloat16* out_hi;   // optional bf16 hi/lo planes of `out` (A operand of the next tensor-core GEMM)
+  __nv_bfloat16* out_lo;
+  const void* a_map_hi;    // optional host pointers to CUtensorMap of pre-split A planes [M, K] (TMA-fed A operand)
+  const void* a_map_lo;
+  long long* dbg;          // optional: CTA 0 writes phase timestamps (globaltimer ns) for latency debugging
 };
+
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start
+// while its predecessor in the stream is still running; it must execute pdl_wait() before touching anything the
+// predecessor wrote.  pdl_trigger() lets the successor's CTAs be scheduled early (its prologue then overlaps our
+// execution).  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool& pdl_enabled() {
+  static thread_local bool on = false;
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
 
 __device__ __forceinline__ float gelu_erf(float x) {
   // nn.GELU() default = exact erf form (vision_transformer.py:15)

@@ -16,6 +16,10 @@ struct TfmBuffers {
   int *done_seq = nullptr, *done_len = nullptr, *ended = nullptr, *counters = nullptr, *trace = nullptr;
   float *scores = nullptr, *done_score = nullptr, *trace_score = nullptr, *logits_out = nullptr;
   long long* ids = nullptr;
+  // bf16 hi/lo operand planes of the decoder activations + their TMA maps (tensor-core precisions only)
+  bool planes = false;
+  __nv_bfloat16 *x_hi = nullptr, *x_lo = nullptr, *att_hi = nullptr, *att_lo = nullptr, *ffn_hi = nullptr, *ffn_lo = nullptr;
+  CUtensorMap map_x_hi, map_x_lo, map_att_hi, map_att_lo, map_ffn_hi, map_ffn_lo;
 };
 
 template <typename T>
@@ -29,30 +33,39 @@ int pool_get(d2t_engine* e, T** out, size_t n) {
 int dec_linear(d2t_engine* e, ConvGemm p, cudaStream_t s) { return run_contraction(e, p, nullptr, e->cfg.precision, s); }
 
 int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long row_stride, const int* anc,
-                      long long anc_parity, int anc_ld, int rows_per_src, const int* step, int n_fixed, int smem_ld,
-                      float* out, int R, cudaStream_t s) {
+                      long long anc_parity, int anc_ld, int rows_per_src, const int* step, int n_fixed,
+                      float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int R, cudaStream_t s) {
   const int heads = e->cfg.dec_heads, D = e->cfg.hidden;
-  const size_t smem = (size_t)heads * smem_ld * sizeof(float);
-  decode_attention_kernel<32><<<R, heads * 32, smem, s>>>(q, D, kv, row_stride, 2 * D, anc, anc_parity, anc_ld,
-                                                          rows_per_src, step, n_fixed, smem_ld, out, D);
+  if (heads > 8) return e->fail(D2T_ERR_UNSUPPORTED, "decode attention supports at most 8 heads per row block");
+  CUDA_TRY(e, launch_kernel(decode_attention_kernel<32>, dim3(R), dim3(heads * 32), 0, s, q, D, kv, row_stride, 2 * D, anc,
+                            anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
   e->launches += 1;
-  CUDA_TRY(e, cudaGetLastError());
   return 0;
 }
 
 // One decoder step for R rows (tfm.py:125-135 / 152-169 with a KV cache):
 // nn.TransformerDecoderLayer defaults = post-norm, ReLU, eps 1e-5.
+struct PdlScope {   // kernels enqueued inside the scope are chained with programmatic dependent launch
+  bool prev;
+  explicit PdlScope(bool on) : prev(pdl_enabled()) { pdl_enabled() = on; }
+  ~PdlScope() { pdl_enabled() = prev; }
+};
+
 int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok, int beam, int T, bool want_logits,
                      cudaStream_t s) {
+  PdlScope pdl(e->use_pdl);
   const d2t_config& c = e->cfg;
   const int D = c.hidden, F = c.dec_ff, V = c.vocab, L = T + 1;
   int* step = b.counters;
   const long long par = beam > 0 ? (long long)R * L : 0;
   int rc;
-  embed_tokens_kernel<<<(R * D / 4 + 255) / 256, 256, 0, s>>>(b.tokens, L, step, par, e->dev[PRED + "word_embed.weight"],
-                                                            e->dev[PRED + "pos_enc.pe"], b.x, R, D, sqrtf((float)D));
+  auto from_x = [&](ConvGemm& g) { if (b.planes) { g.a_map_hi = &b.map_x_hi; g.a_map_lo = b.x_lo ? &b.map_x_lo : nullptr; } };
+  auto from_att = [&](ConvGemm& g) { if (b.planes) { g.a_map_hi = &b.map_att_hi; g.a_map_lo = b.att_lo ? &b.map_att_lo : nullptr; } };
+  auto from_ffn = [&](ConvGemm& g) { if (b.planes) { g.a_map_hi = &b.map_ffn_hi; g.a_map_lo = b.ffn_lo ? &b.map_ffn_lo : nullptr; } };
+  CUDA_TRY(e, launch_kernel(embed_tokens_kernel, dim3((R * D / 4 + 255) / 256), dim3(256), 0, s, b.tokens, L, step, par,
+                            e->dev[PRED + "word_embed.weight"], e->dev[PRED + "pos_enc.pe"], b.x, R, D, sqrtf((float)D),
+                            b.x_hi, b.x_lo));
   e->launches += 1;
-  CUDA_TRY(e, cudaGetLastError());
   for (int l = 0; l < c.dec_layers; ++l) {
     const std::string p = PRED + "model.layers." + std::to_string(l) + ".";
     float* selfkv = b.selfkv + (size_t)l * R * T * 2 * D;
@@ -61,44 +74,48 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
     {
       ConvGemm g = linear_params(b.x, e->dev[p + "self_attn.in_proj_weight"], e->dev[p + "self_attn.in_proj_bias"], b.q, R, 3 * D, D);
       g.ldc = D; g.n_split = D; g.out2 = selfkv; g.ldc2 = T * 2 * D; g.dyn = step; g.dyn_mul2 = 2 * D;
+      from_x(g);
       if ((rc = dec_linear(e, g, s))) return rc;
     }
     if ((rc = enqueue_attention(e, b.q, selfkv, (long long)T * 2 * D, beam > 0 ? b.anc : nullptr, par, L,
-                                beam > 0 ? beam : 1, step, 0, T, b.att, R, s))) return rc;
+                                beam > 0 ? beam : 1, step, 0, b.att, b.att_hi, b.att_lo, R, s))) return rc;
     {
       ConvGemm g = linear_params(b.att, e->dev[p + "self_attn.out_proj.weight"], e->dev[p + "self_attn.out_proj.bias"], b.x2, R, D, D);
-      g.res = b.x; g.ldr = D;
+      g.res = b.x; g.ldr = D; from_att(g);
       if ((rc = dec_linear(e, g, s))) return rc;
     }
-    if ((rc = layernorm(e, b.x2, e->dev[p + "norm1.weight"], e->dev[p + "norm1.bias"], b.x, R, D, 1e-5f, s))) return rc;
+    if ((rc = layernorm(e, b.x2, e->dev[p + "norm1.weight"], e->dev[p + "norm1.bias"], b.x, R, D, 1e-5f, s, b.x_hi, b.x_lo))) return rc;
     // cross-attention over the encoder memory (K/V projected once per image, shared by its beams), norm2
     {
       ConvGemm g = linear_params(b.x, e->dev[p + "multihead_attn.in_proj_weight"], e->dev[p + "multihead_attn.in_proj_bias"], b.q, R, D, D);
+      from_x(g);
       if ((rc = dec_linear(e, g, s))) return rc;
     }
     if ((rc = enqueue_attention(e, b.q, crosskv, (long long)ntok * 2 * D, nullptr, 0, 0, beam > 0 ? beam : 1, nullptr,
-                                ntok, ntok, b.att, R, s))) return rc;
+                                ntok, b.att, b.att_hi, b.att_lo, R, s))) return rc;
     {
       ConvGemm g = linear_params(b.att, e->dev[p + "multihead_attn.out_proj.weight"], e->dev[p + "multihead_attn.out_proj.bias"], b.x2, R, D, D);
-      g.res = b.x; g.ldr = D;
+      g.res = b.x; g.ldr = D; from_att(g);
       if ((rc = dec_linear(e, g, s))) return rc;
     }
-    if ((rc = layernorm(e, b.x2, e->dev[p + "norm2.weight"], e->dev[p + "norm2.bias"], b.x, R, D, 1e-5f, s))) return rc;
+    if ((rc = layernorm(e, b.x2, e->dev[p + "norm2.weight"], e->dev[p + "norm2.bias"], b.x, R, D, 1e-5f, s, b.x_hi, b.x_lo))) return rc;
     // feed-forward, norm3
     {
       ConvGemm g = linear_params(b.x, e->dev[p + "linear1.weight"], e->dev[p + "linear1.bias"], b.ffn, R, F, D);
-      g.act = ACT_RELU;
+      g.act = ACT_RELU; from_x(g);
+      g.out_hi = b.ffn_hi; g.out_lo = b.ffn_lo;
       if ((rc = dec_linear(e, g, s))) return rc;
     }
     {
       ConvGemm g = linear_params(b.ffn, e->dev[p + "linear2.weight"], e->dev[p + "linear2.bias"], b.x2, R, D, F);
-      g.res = b.x; g.ldr = D;
+      g.res = b.x; g.ldr = D; from_ffn(g);
       if ((rc = dec_linear(e, g, s))) return rc;
     }
-    if ((rc = layernorm(e, b.x2, e->dev[p + "norm3.weight"], e->dev[p + "norm3.bias"], b.x, R, D, 1e-5f, s))) return rc;
+    if ((rc = layernorm(e, b.x2, e->dev[p + "norm3.weight"], e->dev[p + "norm3.bias"], b.x, R, D, 1e-5f, s, b.x_hi, b.x_lo))) return rc;
   }
   {
     ConvGemm g = linear_params(b.x, e->dev[PRED + "proj.weight"], e->dev[PRED + "proj.bias"], b.logits, R, V, D);
+    from_x(g);
     if ((rc = dec_linear(e, g, s))) return rc;
   }
   if (beam > 0) {
@@ -107,16 +124,14 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
     st.finished = b.finished; st.done_seq = b.done_seq; st.done_len = b.done_len; st.done_score = b.done_score;
     st.counters = b.counters; st.trace = b.trace; st.trace_score = b.trace_score;
     st.L = L; st.beam = beam; st.B = B; st.V = V; st.end_id = TFM_END; st.max_steps = T;
-    beam_step_kernel<<<B, 256, (size_t)beam * V * sizeof(float), s>>>(b.logits, st);
+    CUDA_TRY(e, launch_kernel(beam_step_kernel, dim3(B), dim3(256), (size_t)beam * V * sizeof(float), s, b.logits, st));
   } else {
-    greedy_pick_kernel<<<R, 128, 0, s>>>(b.logits, V, step, b.tokens, L, b.ids, T, want_logits ? b.logits_out : nullptr,
-                                         b.ended, b.counters + 1, b.counters + 2, R, TFM_END);
+    CUDA_TRY(e, launch_kernel(greedy_pick_kernel, dim3(R), dim3(128), 0, s, b.logits, V, step, b.tokens, L, b.ids, T,
+                              want_logits ? b.logits_out : nullptr, b.ended, b.counters + 1, b.counters + 2, R, TFM_END));
   }
   e->launches += 1;
-  CUDA_TRY(e, cudaGetLastError());
-  advance_step_kernel<<<1, 1, 0, s>>>(step);
+  CUDA_TRY(e, launch_kernel(advance_step_kernel, dim3(1), dim3(1), 0, s, step));
   e->launches += 1;
-  CUDA_TRY(e, cudaGetLastError());
   return 0;
 }
 
@@ -145,6 +160,25 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
   if ((rc = pool_get(e, &b.ffn, (size_t)R * F))) return rc;
   if ((rc = pool_get(e, &b.logits, (size_t)R * V))) return rc;
   if ((rc = pool_get(e, &b.counters, 4))) return rc;
+  b.planes = c.precision == D2T_PREC_BF16X3 || c.precision == D2T_PREC_BF16;
+  if (b.planes) {
+    const bool lo = c.precision == D2T_PREC_BF16X3;
+    if ((rc = pool_get(e, &b.x_hi, (size_t)R * D))) return rc;
+    if ((rc = pool_get(e, &b.att_hi, (size_t)R * D))) return rc;
+    if ((rc = pool_get(e, &b.ffn_hi, (size_t)R * F))) return rc;
+    if (lo) {
+      if ((rc = pool_get(e, &b.x_lo, (size_t)R * D))) return rc;
+      if ((rc = pool_get(e, &b.att_lo, (size_t)R * D))) return rc;
+      if ((rc = pool_get(e, &b.ffn_lo, (size_t)R * F))) return rc;
+    }
+    cudaError_t st = tc_make_act_map(b.x_hi, R, D, &b.map_x_hi);
+    if (st == cudaSuccess) st = tc_make_act_map(b.att_hi, R, D, &b.map_att_hi);
+    if (st == cudaSuccess) st = tc_make_act_map(b.ffn_hi, R, F, &b.map_ffn_hi);
+    if (st == cudaSuccess && lo) st = tc_make_act_map(b.x_lo, R, D, &b.map_x_lo);
+    if (st == cudaSuccess && lo) st = tc_make_act_map(b.att_lo, R, D, &b.map_att_lo);
+    if (st == cudaSuccess && lo) st = tc_make_act_map(b.ffn_lo, R, F, &b.map_ffn_lo);
+    if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "activation tensor map: %s", cudaGetErrorString(st));
+  }
   const int nbuf = beam > 0 ? 2 : 1;
   if ((rc = pool_get(e, &b.tokens, (size_t)nbuf * R * L))) return rc;
   if (beam > 0) {
@@ -191,7 +225,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     std::vector<long long> key = {(long long)R, B, ntok, beam, T, want_logits ? 1 : 0};
     const void* ptrs[] = {b.crosskv, b.selfkv, b.x, b.x2, b.q, b.att, b.ffn, b.logits, b.counters, b.tokens, b.anc,
                           b.scores, b.n_live, b.n_done, b.finished, b.done_seq, b.done_len, b.done_score, b.trace,
-                          b.trace_score, b.ended, b.ids, b.logits_out};
+                          b.trace_score, b.ended, b.ids, b.logits_out, b.x_hi, b.x_lo, b.att_hi, b.att_lo, b.ffn_hi, b.ffn_lo};
     for (const void* q : ptrs) key.push_back((long long)(uintptr_t)q);
     for (auto& g : e->graphs) if (g.key == key) { exec = g.exec; nodes = g.nodes; }
     if (!exec) {

@@ -11,11 +11,20 @@
 
 namespace d2t {
 
+// bf16 hi/lo operand planes of an fp32 value (error-compensated tensor-core modes): x ~= hi + lo.
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
 // x[r,:] = E[tok[r][t]] * sqrt(D) + pe[t]    (tfm.py:92-93, position_encoding.py:24-28)
 __global__ void embed_tokens_kernel(const int* __restrict__ tokens, int tok_ld, const int* __restrict__ step,
                                     long long parity_stride,  // tokens buffer = tokens + (t&1)*parity_stride (0: single buffer)
                                     const float* __restrict__ emb, const float* __restrict__ pe, float* __restrict__ x,
-                                    int R, int D, float mult) {
+                                    int R, int D, float mult, __nv_bfloat16* __restrict__ x_hi,
+                                    __nv_bfloat16* __restrict__ x_lo) {
+  pdl_trigger();
+  pdl_wait();
   const int t = *step;
   const int* tk = tokens + (parity_stride ? (long long)(t & 1) * parity_stride : 0);
   const int d4n = D / 4;
@@ -25,8 +34,18 @@ __global__ void embed_tokens_kernel(const int* __restrict__ tokens, int tok_ld, 
   const int tok = tk[(size_t)r * tok_ld + t];
   const float4 e = *reinterpret_cast<const float4*>(emb + (size_t)tok * D + d);
   const float4 p = *reinterpret_cast<const float4*>(pe + (size_t)t * D + d);
-  *reinterpret_cast<float4*>(x + (size_t)r * D + d) =
-      make_float4(e.x * mult + p.x, e.y * mult + p.y, e.z * mult + p.z, e.w * mult + p.w);
+  const float4 o = make_float4(e.x * mult + p.x, e.y * mult + p.y, e.z * mult + p.z, e.w * mult + p.w);
+  *reinterpret_cast<float4*>(x + (size_t)r * D + d) = o;
+  if (x_hi) {
+    const float f[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(f[u], hi, lo);
+      x_hi[(size_t)r * D + d + u] = hi;
+      if (x_lo) x_lo[(size_t)r * D + d + u] = lo;
+    }
+  }
 }
 
 // Single-query attention for one decoder row and all heads: block = heads warps, warp h = head h.
@@ -35,72 +54,83 @@ __global__ void embed_tokens_kernel(const int* __restrict__ tokens, int tok_ld, 
 //   self-attention, greedy:  src = r                      n_keys = *step + 1
 //   self-attention, beam:    src = img*beam + anc[r][j]   n_keys = *step + 1   (ancestry indirection)
 //   cross-attention:         src = r / rows_per_src       n_keys = n_fixed      (memory shared by the beams)
-// HBM-bound: each key/value row is read once per (row, head) as full 128-byte lines.
+// HBM-bound single pass: every lane owns the keys j = lane (mod 32) and streams its key AND value head slices
+// as two full 128-byte lines per key (all loads of a key independent -> deep memory-level parallelism), keeping an
+// online-softmax state (running max, sum, 32-wide accumulator); the 32 lane states are merged once at the end
+// through shared memory.  Optional bf16 hi/lo planes of the output feed the tensor-core out-projection.
 template <int HD>
-__global__ void decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kv,
-                                        long long row_stride, int pos_stride, const int* __restrict__ anc,
-                                        long long anc_parity_stride, int anc_ld, int rows_per_src,
-                                        const int* __restrict__ step, int n_fixed, int smem_ld,
-                                        float* __restrict__ out, int D) {
-  extern __shared__ float s_scores[];  // [heads][smem_ld], smem_ld >= max number of keys
+__global__ void __launch_bounds__(256)
+decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kv,
+                        long long row_stride, int pos_stride, const int* __restrict__ anc,
+                        long long anc_parity_stride, int anc_ld, int rows_per_src,
+                        const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
+                        __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  pdl_trigger();
+  pdl_wait();
+  static_assert(HD == 32, "one lane per output channel in the merge");
+  __shared__ float s_acc[8][32][HD + 1];
   const int r = blockIdx.x;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = step ? *step : 0;
   const int n_keys = n_fixed > 0 ? n_fixed : t + 1;
-  float* sc = s_scores + (size_t)h * smem_ld;
   const int* anc_r = anc ? anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)r * anc_ld : nullptr;
   const int src_base = (r / rows_per_src) * (anc ? rows_per_src : 1);
 
-  float qv[HD];
+  float qv[HD], acc[HD];
   const float scale = rsqrtf((float)HD);
 #pragma unroll
   for (int d = 0; d < HD; d += 4) {
     const float4 v = *reinterpret_cast<const float4*>(q + (size_t)r * ldq + h * HD + d);
     qv[d] = v.x * scale; qv[d + 1] = v.y * scale; qv[d + 2] = v.z * scale; qv[d + 3] = v.w * scale;
+    acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
   }
-  // pass 1: one key per lane
-  float mx = -INFINITY;
+  float mx = -INFINITY, sum = 0.f;
   for (int j = lane; j < n_keys; j += 32) {
     const int src = anc_r ? src_base + anc_r[j] : src_base;
-    const float* kp = kv + (size_t)src * row_stride + (size_t)j * pos_stride + h * HD;
+    const float4* kp = reinterpret_cast<const float4*>(kv + (size_t)src * row_stride + (size_t)j * pos_stride + h * HD);
+    const float4* vp = reinterpret_cast<const float4*>(kv + (size_t)src * row_stride + (size_t)j * pos_stride + D + h * HD);
+    float4 k4[HD / 4], v4[HD / 4];
+#pragma unroll
+    for (int i = 0; i < HD / 4; ++i) k4[i] = __ldg(kp + i);
+#pragma unroll
+    for (int i = 0; i < HD / 4; ++i) v4[i] = __ldg(vp + i);
     float s = 0.f;
 #pragma unroll
-    for (int d = 0; d < HD; d += 4) {
-      const float4 k4 = *reinterpret_cast<const float4*>(kp + d);
-      s = fmaf(qv[d], k4.x, s); s = fmaf(qv[d + 1], k4.y, s); s = fmaf(qv[d + 2], k4.z, s); s = fmaf(qv[d + 3], k4.w, s);
+    for (int i = 0; i < HD / 4; ++i) {
+      s = fmaf(qv[4 * i], k4[i].x, s); s = fmaf(qv[4 * i + 1], k4[i].y, s);
+      s = fmaf(qv[4 * i + 2], k4[i].z, s); s = fmaf(qv[4 * i + 3], k4[i].w, s);
     }
-    sc[j] = s;
-    mx = fmaxf(mx, s);
+    const float nm = fmaxf(mx, s);
+    const float corr = expf(mx - nm);   // 0 on the first key (mx = -inf)
+    const float pj = expf(s - nm);
+    sum = sum * corr + pj;
+#pragma unroll
+    for (int i = 0; i < HD / 4; ++i) {
+      acc[4 * i] = fmaf(pj, v4[i].x, acc[4 * i] * corr);
+      acc[4 * i + 1] = fmaf(pj, v4[i].y, acc[4 * i + 1] * corr);
+      acc[4 * i + 2] = fmaf(pj, v4[i].z, acc[4 * i + 2] * corr);
+      acc[4 * i + 3] = fmaf(pj, v4[i].w, acc[4 * i + 3] * corr);
+    }
+    mx = nm;
   }
-  mx = warp_max(mx);
-  float sum = 0.f;
-  for (int j = lane; j < n_keys; j += 32) {
-    const float pj = expf(sc[j] - mx);
-    sc[j] = pj;
-    sum += pj;
-  }
-  sum = warp_sum(sum);
+  // merge the 32 lane states: global max, rescale, sum
+  const float gm = warp_max(mx);
+  const float sc = (mx == -INFINITY) ? 0.f : expf(mx - gm);
+  const float total = warp_sum(sum * sc);
+#pragma unroll
+  for (int d = 0; d < HD; ++d) s_acc[h][lane][d] = acc[d] * sc;
   __syncwarp();
-  // pass 2: lane = output channel, values streamed as coalesced 128-byte rows
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  const float* vb = kv + D + h * HD + lane;
-  int j = 0;
-  for (; j + 4 <= n_keys; j += 4) {
-    const int s0 = anc_r ? src_base + anc_r[j] : src_base;
-    const int s1 = anc_r ? src_base + anc_r[j + 1] : src_base;
-    const int s2 = anc_r ? src_base + anc_r[j + 2] : src_base;
-    const int s3 = anc_r ? src_base + anc_r[j + 3] : src_base;
-    const float v0 = vb[(size_t)s0 * row_stride + (size_t)j * pos_stride];
-    const float v1 = vb[(size_t)s1 * row_stride + (size_t)(j + 1) * pos_stride];
-    const float v2 = vb[(size_t)s2 * row_stride + (size_t)(j + 2) * pos_stride];
-    const float v3 = vb[(size_t)s3 * row_stride + (size_t)(j + 3) * pos_stride];
-    a0 = fmaf(sc[j], v0, a0); a1 = fmaf(sc[j + 1], v1, a1); a2 = fmaf(sc[j + 2], v2, a2); a3 = fmaf(sc[j + 3], v3, a3);
+  float o = 0.f;
+#pragma unroll
+  for (int l = 0; l < 32; ++l) o += s_acc[h][l][lane];
+  o /= total;
+  out[(size_t)r * D + h * HD + lane] = o;
+  if (out_hi) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(o, hi, lo);
+    out_hi[(size_t)r * D + h * HD + lane] = hi;
+    if (out_lo) out_lo[(size_t)r * D + h * HD + lane] = lo;
   }
-  for (; j < n_keys; ++j) {
-    const int s0 = anc_r ? src_base + anc_r[j] : src_base;
-    a0 = fmaf(sc[j], vb[(size_t)s0 * row_stride + (size_t)j * pos_stride], a0);
-  }
-  out[(size_t)r * D + h * HD + lane] = ((a0 + a1) + (a2 + a3)) / sum;
 }
 
 // Greedy pick: next = argmax(softmax(logits[r])) with the lowest index on ties (tfm.py:134-135, quirk Q7).
@@ -110,6 +140,8 @@ __global__ void greedy_pick_kernel(const float* __restrict__ logits, int V, cons
                                    int* __restrict__ tokens, int tok_ld, long long* __restrict__ ids, int ids_ld,
                                    float* __restrict__ logits_out, int* __restrict__ ended, int* __restrict__ n_ended,
                                    int* __restrict__ done_step, int R, int end_id) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red_v[32];
   __shared__ int red_i[32];
   __shared__ float s_max, s_sum;
@@ -162,12 +194,18 @@ __global__ void greedy_pick_kernel(const float* __restrict__ logits, int V, cons
   }
 }
 
-__global__ void advance_step_kernel(int* step) { *step += 1; }
+__global__ void advance_step_kernel(int* step) {
+  pdl_trigger();
+  pdl_wait();
+  *step += 1;
+}
 
 // Decode-state initialisation (one launch per decode call).
 __global__ void init_decode_state_kernel(int* tokens, long long tokens_elems, int tok_ld, int R, int beam, int go_id,
                                          int* anc, int anc_ld, float* scores, int* n_live, int* n_done, int* finished,
                                          int* ended, int* counters /* step, n_ended, done_step, n_finished */) {
+  pdl_trigger();
+  pdl_wait();
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long gsz = (long long)gridDim.x * blockDim.x;
   for (long long i = gtid; i < tokens_elems; i += gsz) tokens[i] = 0;  // PAD
@@ -220,6 +258,8 @@ struct BeamState {
 
 __global__ void __launch_bounds__(256)
 beam_step_kernel(const float* __restrict__ logits, BeamState st) {
+  pdl_trigger();
+  pdl_wait();
   extern __shared__ float s_cand[];  // [beam][V] candidate scores
   __shared__ float s_rowmax[BEAM_MAX], s_rowlse[BEAM_MAX];
   __shared__ float red_v[8];

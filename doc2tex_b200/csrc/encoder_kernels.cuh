@@ -105,7 +105,10 @@ __global__ void assemble_tokens_kernel(const float* __restrict__ tok, const floa
 // Two-pass mean / biased variance in fp32, y = (x - mean) / sqrt(var + eps) * w + b (torch semantics).
 template <int NV4>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
-                                 float* __restrict__ y, int rows, float eps) {
+                                 float* __restrict__ y, int rows, float eps,
+                                 __nv_bfloat16* __restrict__ y_hi = nullptr, __nv_bfloat16* __restrict__ y_lo = nullptr) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int D = 128 * NV4;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -138,6 +141,20 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
     r.z = (v[i].z - mean) * rstd * ww.z + bb.z;
     r.w = (v[i].w - mean) * rstd * ww.w + bb.w;
     *reinterpret_cast<float4*>(yr + o) = r;
+    if (y_hi) {  // bf16 hi/lo operand planes for the next tensor-core GEMM
+      const float f[4] = {r.x, r.y, r.z, r.w};
+      uint32_t hw[2], lw[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * u]), h1 = __float2bfloat16_rn(f[2 * u + 1]);
+        hw[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * u] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * u + 1] - __bfloat162float(h1));
+        lw[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint2*>(y_hi + (size_t)warp * D + o) = make_uint2(hw[0], hw[1]);
+      if (y_lo) *reinterpret_cast<uint2*>(y_lo + (size_t)warp * D + o) = make_uint2(lw[0], lw[1]);
+    }
   }
 }
 

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -93,6 +94,7 @@ struct d2t_engine {
 
   SlotPool enc_pool, dec_pool;
   bool keep_taps = false;
+  bool use_pdl = true;   // D2T_PDL=0 disables programmatic dependent launch in the decode step
   std::map<std::string, Tap> taps;
 
   // decode graph cache
@@ -315,16 +317,18 @@ int basic_block(d2t_engine* e, const std::string& name, Fmap& x, cudaStream_t s)
 }
 
 int layernorm(d2t_engine* e, const float* x, const float* w, const float* b, float* y, int rows, int D, float eps,
-              cudaStream_t s) {
+              cudaStream_t s, __nv_bfloat16* y_hi = nullptr, __nv_bfloat16* y_lo = nullptr) {
   const int threads = 256, wpb = threads / 32;
   const int grid = (rows + wpb - 1) / wpb;
+  cudaError_t st;
   switch (D / 128) {
-    case 1: layernorm_kernel<1><<<grid, threads, 0, s>>>(x, w, b, y, rows, eps); break;
-    case 2: layernorm_kernel<2><<<grid, threads, 0, s>>>(x, w, b, y, rows, eps); break;
-    case 4: layernorm_kernel<4><<<grid, threads, 0, s>>>(x, w, b, y, rows, eps); break;
-    case 8: layernorm_kernel<8><<<grid, threads, 0, s>>>(x, w, b, y, rows, eps); break;
+    case 1: st = launch_kernel(layernorm_kernel<1>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo); break;
+    case 2: st = launch_kernel(layernorm_kernel<2>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo); break;
+    case 4: st = launch_kernel(layernorm_kernel<4>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo); break;
+    case 8: st = launch_kernel(layernorm_kernel<8>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo); break;
     default: return e->fail(D2T_ERR_UNSUPPORTED, "LayerNorm width %d unsupported (need 128/256/512/1024)", D);
   }
+  if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "layernorm launch: %s", cudaGetErrorString(st));
   if (D % 128) return e->fail(D2T_ERR_UNSUPPORTED, "LayerNorm width %d unsupported", D);
   e->launches += 1;
   CUDA_TRY(e, cudaGetLastError());
@@ -393,6 +397,7 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   e->cfg = *cfg;
   e->device = device;
   e->num_sms = prop.multiProcessorCount;
+  if (const char* v = getenv("D2T_PDL")) e->use_pdl = atoi(v) != 0;
   cudaSetDevice(device);
   if (cudaMallocHost(&e->h_counters, 4 * sizeof(int)) != cudaSuccess) {
     g_create_error = "cudaMallocHost failed";
@@ -407,7 +412,6 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
     return D2T_ERR_CUDA;
   }
   // decode attention may need > 48 KB of dynamic shared memory for long encoder memories
-  cudaFuncSetAttribute(decode_attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
   cudaFuncSetAttribute(beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   *out = e;
   return D2T_OK;
@@ -777,6 +781,60 @@ int d2t_debug_gemm(d2t_engine* e, const float* a, const float* w, const float* s
   }
   int rc = run_contraction(e, p, &tw, precision, (cudaStream_t)stream);
   cudaStreamSynchronize((cudaStream_t)stream);
+  for (void* q : tmp) cudaFree(q);
+  return rc;
+}
+
+// Micro-benchmark hook: `iters` back-to-back launches of one contraction (weights prepared once), optionally
+// interleaved with a small LayerNorm launch (the decode-step pattern); returns the average ms per iteration.
+int d2t_debug_gemm_bench(d2t_engine* e, const float* a, const float* w, float* c, int M, int N, int K, int precision,
+                         int iters, int interleave, float* ms_out, d2t_stream stream) {
+  if (!e || !ms_out) return D2T_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  cudaStream_t s = e->work;
+  ConvGemm p = linear_params(a, w, nullptr, c, M, N, K);
+  long long* dbg_dev = nullptr;
+  cudaMalloc(&dbg_dev, 16 * sizeof(long long));
+  cudaMemset(dbg_dev, 0, 16 * sizeof(long long));
+  p.dbg = dbg_dev;
+  if (const char* v = getenv("D2T_DBG_ACT")) p.act = atoi(v);
+  TcWeight tw;
+  std::vector<void*> tmp;
+  if (precision != D2T_PREC_FP32) {
+    cudaError_t st = tc_prepare_weight(w, N, K, precision, &tw, &tmp);
+    if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tc_prepare_weight: %s", cudaGetErrorString(st));
+    cudaDeviceSynchronize();
+  }
+  float *lnw = nullptr, *lnb = nullptr;
+  cudaMalloc(&lnw, 256 * 4); cudaMalloc(&lnb, 256 * 4);
+  cudaMemset(lnw, 0, 256 * 4); cudaMemset(lnb, 0, 256 * 4);
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  int rc = 0;
+  for (int pass = 0; pass < 2 && !rc; ++pass) {
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < iters && !rc; ++i) {
+      rc = run_contraction(e, p, precision != D2T_PREC_FP32 ? &tw : nullptr, precision, s);
+      if (interleave && !rc && N % 128 == 0 && N <= 1024) rc = layernorm(e, c, lnw, lnb, c, M, N > 256 ? 256 : N, 1e-5f, s);
+    }
+    cudaEventRecord(e1, s);
+    cudaStreamSynchronize(s);
+  }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_out = ms / iters;
+  if (precision != D2T_PREC_FP32) {
+    long long h[12];
+    cudaMemcpy(h, dbg_dev, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc dbg epi chunk0] ld start +%lld, ld done +%lld, staged +%lld, stored +%lld\n", h[8] - h[0],
+            h[9] - h[0], h[10] - h[0], h[11] - h[0]);
+    fprintf(stderr, "[tc dbg M=%d N=%d K=%d] prologue %lld ns, first full +%lld, last full +%lld, last commit +%lld, "
+                    "epi start +%lld, epi done +%lld, exit +%lld\n", M, N, K, h[1] - h[0], h[2] - h[0], h[3] - h[0],
+            h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0]);
+  }
+  cudaFree(dbg_dev);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(lnw); cudaFree(lnb);
   for (void* q : tmp) cudaFree(q);
   return rc;
 }

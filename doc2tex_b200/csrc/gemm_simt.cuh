@@ -14,6 +14,8 @@ namespace d2t {
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_gemm_simt_kernel(const ConvGemm p) {
+  pdl_trigger();
+  pdl_wait();
   constexpr int BK = 16;
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int A_F4 = BM * BK / 4;
@@ -182,13 +184,13 @@ inline cudaError_t launch_conv_gemm_simt(const ConvGemm& p, cudaStream_t s, int 
   const long long big_ctas = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128);
   if (big_ctas >= num_sms && p.N >= 96) {
     dim3 grid((p.M + 127) / 128, (p.N + 127) / 128);
-    conv_gemm_simt_kernel<128, 128, 8, 8><<<grid, 256, 0, s>>>(p);
+    return launch_kernel(conv_gemm_simt_kernel<128, 128, 8, 8>, grid, dim3(256), 0, s, p);
   } else if ((long long)((p.M + 63) / 64) * ((p.N + 63) / 64) >= num_sms) {
     dim3 grid((p.M + 63) / 64, (p.N + 63) / 64);
-    conv_gemm_simt_kernel<64, 64, 4, 4><<<grid, 256, 0, s>>>(p);
+    return launch_kernel(conv_gemm_simt_kernel<64, 64, 4, 4>, grid, dim3(256), 0, s, p);
   } else {
     dim3 grid((p.M + 31) / 32, (p.N + 31) / 32);
-    conv_gemm_simt_kernel<32, 32, 4, 4><<<grid, 64, 0, s>>>(p);
+    return launch_kernel(conv_gemm_simt_kernel<32, 32, 4, 4>, grid, dim3(64), 0, s, p);
   }
   return cudaGetLastError();
 }

@@ -31,6 +31,11 @@ namespace d2t {
 // ------------------------------------------------------------------------------------------------
 namespace tc {
 
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -126,12 +131,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int n) {
 // Kernel configuration
 // ------------------------------------------------------------------------------------------------
 constexpr int TC_BM = 128;
-constexpr int TC_EPI_WARPS = 4, TC_PROD_WARPS = 8;
-constexpr int TC_THREADS = (TC_EPI_WARPS + TC_PROD_WARPS + 2) * 32;  // 448
+// warp roles: gather variant = 4 epilogue + 8 A-producer + TMA + MMA warps (448 threads);
+//             TMA-fed-A variant = 8 epilogue + TMA + MMA warps (320 threads; nothing to gather)
+constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_PROD_THREADS = TC_PROD_WARPS * 32;                  // 256
 constexpr int TC_ROWS_PER_THREAD = TC_BM * 8 / TC_PROD_THREADS;      // 4 (8 x 16-byte chunks per 128-byte row)
+constexpr int TC_EPI_PITCH = 36;                                     // floats per staged accumulator row (32 + pad)
+__host__ __device__ constexpr int tc_epi_warps(bool a_tma) { return a_tma ? 8 : 4; }
+__host__ __device__ constexpr int tc_prod_warps(bool a_tma) { return a_tma ? 0 : TC_PROD_WARPS; }
+__host__ __device__ constexpr int tc_threads(bool a_tma) { return (tc_epi_warps(a_tma) + tc_prod_warps(a_tma) + 2) * 32; }
 
-template <bool TF32, int PASSES, int BN>
+template <bool TF32, int PASSES, int BN, bool A_TMA>
 struct TcCfg {
   static constexpr int PLANES = PASSES == 1 ? 1 : 2;
   static constexpr int KB_ELEMS = TF32 ? 32 : 64;   // elements per 128-byte operand row
@@ -139,11 +149,12 @@ struct TcCfg {
   static constexpr int A_BYTES = TC_BM * 128;       // per plane
   static constexpr int B_BYTES = BN * 128;          // per plane
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-  static constexpr int SMEM_BUDGET = 200 * 1024;
+  static constexpr int EPI_STAGE_BYTES = tc_epi_warps(A_TMA) * 32 * TC_EPI_PITCH * 4;   // accumulator transpose tiles
+  static constexpr int SMEM_BUDGET = 225 * 1024 - EPI_STAGE_BYTES - 1280;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two (BN in {64,128,256})
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(STAGES >= 2, "need at least a double buffer");
 };
 
@@ -155,31 +166,40 @@ struct TcWeight {
   CUtensorMap map_hi[3], map_lo[3];  // TMA boxes of 64 / 128 / 256 weight rows
 };
 
-template <bool TF32, int PASSES, int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// A_TMA: the A operand planes already exist in HBM as bf16 [M, K] matrices (written by the producing kernel's
+// epilogue) and are fetched by TMA like the weights; the gather/convert warps then have nothing to do.  This is the
+// low-latency path for the small decode-step GEMMs: every k-block of a tile is in flight at once.
+template <bool TF32, int PASSES, int BN, bool A_TMA>
+__global__ void __launch_bounds__(tc_threads(A_TMA), 1)
 conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi,
-                    const __grid_constant__ CUtensorMap map_lo, int tiles_m, int tiles_n) {
-  using Cfg = TcCfg<TF32, PASSES, BN>;
+                    const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_a_hi,
+                    const __grid_constant__ CUtensorMap map_a_lo, int tiles_m, int tiles_n) {
+  using Cfg = TcCfg<TF32, PASSES, BN, A_TMA>;
   constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES;
+  constexpr int TC_EPI_WARPS = tc_epi_warps(A_TMA), TC_EPI_STAGE_BYTES = Cfg::EPI_STAGE_BYTES;
+  constexpr int TMA_WARP = tc_epi_warps(A_TMA) + tc_prod_warps(A_TMA), MMA_WARP = TMA_WARP + 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - tc::smem_u32(smem_raw));
   // stage s: [A plane 0][A plane 1][B plane 0][B plane 1]
-  const uint32_t bars = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bars = smem_base + STAGES * Cfg::STAGE_BYTES + TC_EPI_STAGE_BYTES;
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + 8 * (2 * STAGES + 4));
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + TC_EPI_STAGE_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_trigger();   // let the next kernel's prologue overlap this one (PDL launches only)
+  const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
+  if (dbg && threadIdx.x == 0) p.dbg[0] = tc::gtime();
   const int num_tiles = tiles_m * tiles_n;
   const int nkb = (p.K + Cfg::KB_ELEMS - 1) / Cfg::KB_ELEMS;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(full_bar(s), TC_PROD_THREADS + 1);   // 256 A-producer arrivals + the TMA thread's expect_tx arrive
+      tc::mbar_init(full_bar(s), A_TMA ? 1 : TC_PROD_THREADS + 1);   // A-producer arrivals + the TMA thread's expect_tx arrive
       tc::mbar_init(empty_bar(s), 1);                     // one tcgen05.commit
     }
     for (int a = 0; a < 2; ++a) {
@@ -188,80 +208,112 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
     }
     tc::fence_barrier_init();
   }
-  if (warp == TC_EPI_WARPS + TC_PROD_WARPS + 1) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-  if (warp == TC_EPI_WARPS + TC_PROD_WARPS && lane == 0) {
+  if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == TMA_WARP && lane == 0) {
     tc::tma_prefetch_desc(&map_hi);
     if (PLANES == 2) tc::tma_prefetch_desc(&map_lo);
+    if (A_TMA) {
+      tc::tma_prefetch_desc(&map_a_hi);
+      if (PLANES == 2) tc::tma_prefetch_desc(&map_a_lo);
+    }
   }
   tc::tcgen05_before_sync();
   __syncthreads();
   tc::tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();      // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the previous kernel
+  if (dbg && threadIdx.x == 0) p.dbg[1] = tc::gtime();
 
   if (warp < TC_EPI_WARPS) {
     // =========================== epilogue ===========================
+    // Warp w owns TMEM lane quadrant (w & 3) = accumulator rows 32*(w&3)..+31; with 8 epilogue warps the 32-column
+    // chunks of a tile alternate between the two warps of a quadrant.  Row-per-thread chunks are transposed through
+    // a per-warp smem tile so global traffic is coalesced (8 lanes = one 128-byte row segment, 4 rows per
+    // instruction).  Parameters are hoisted into registers and the row loop is kept rolled: this code is
+    // instruction-latency bound (one warp per scheduler), not bandwidth bound.
+    const int quad = warp & 3, slot = warp >> 2;
+    constexpr int NSLOT = TC_EPI_WARPS / 4;
+    float* const stg = reinterpret_cast<float*>(smem_gen + (size_t)STAGES * Cfg::STAGE_BYTES) + warp * (32 * TC_EPI_PITCH);
+    const int sub_r = lane >> 3, c4 = (lane & 7) * 4;
+    const int M = p.M, N = p.N, ldc = p.ldc, ldr = p.ldr, ldc2 = p.ldc2, n_split = p.n_split, act = p.act & 15;
+    const float* const scale = p.scale;
+    const float* const shift = p.shift;
+    const float* const res = p.res;
+    float* const out = p.out;
+    float* out2 = nullptr;   // columns >= n_split (KV-cache slot of the current decode step)
+    if (p.out2) out2 = p.out2 + (p.dyn ? (long long)(*p.dyn) * p.dyn_mul2 : 0) - n_split;
+    __nv_bfloat16* const out_hi = p.out_hi;
+    __nv_bfloat16* const out_lo = p.out_lo;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
       const int acc = it & 1;
       tc::mbar_wait(tfull_bar(acc), (it >> 1) & 1);
       tc::tcgen05_after_sync();
-      const int m = tm * TC_BM + warp * 32 + lane;
-      const bool m_ok = m < p.M;
-      float* orow1 = p.out + (size_t)m * p.ldc;
-      float* orow2 = nullptr;   // columns >= n_split (KV-cache slot of the current decode step)
-      if (p.out2) orow2 = p.out2 + (p.dyn ? (long long)(*p.dyn) * p.dyn_mul2 : 0) + (size_t)m * p.ldc2 - p.n_split;
-      const float* rrow = p.res ? p.res + (size_t)m * p.ldr : nullptr;
+      if (dbg && threadIdx.x == 0) p.dbg[5] = tc::gtime();
+      const int m_first = tm * TC_BM + quad * 32 + sub_r;
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
+      for (int j = slot; j < BN / 32; j += NSLOT) {
         uint32_t r[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN + j * 32), r);
+        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + j * 32), r);
         tc::tmem_ld_wait();
-        const int n0 = tn * BN + j * 32;
-        float* orow = (orow2 != nullptr && n0 >= p.n_split) ? orow2 : orow1;
-        if (m_ok && n0 < p.N) {
-          if (n0 + 32 <= p.N) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int n = n0 + q * 4;
-              float4 v = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
-                                     __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
-              if (p.scale) {
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + n));
-                v.x *= sc.x; v.y *= sc.y; v.z *= sc.z; v.w *= sc.w;
-              }
-              if (p.shift) {
-                const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + n));
-                v.x += sh.x; v.y += sh.y; v.z += sh.z; v.w += sh.w;
-              }
-              if (rrow) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(rrow + n));
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(stg + lane * TC_EPI_PITCH + q * 4) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+        __syncwarp();
+        const int n = tn * BN + j * 32 + c4;
+        if (n < N) {
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + n));
+          if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + n));
+          const bool second = out2 != nullptr && n >= n_split;
+          float* dst = second ? out2 + (size_t)m_first * ldc2 + n : out + (size_t)m_first * ldc + n;
+          const size_t dst_step = (size_t)4 * (second ? ldc2 : ldc);
+          const float* rp = res ? res + (size_t)m_first * ldr + n : nullptr;
+          const float* sp = stg + sub_r * TC_EPI_PITCH + c4;
+          const bool planes = out_hi != nullptr && !second;
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            if (m_first + 4 * i < M) {
+              float4 v = *reinterpret_cast<const float4*>(sp + i * 4 * TC_EPI_PITCH);
+              v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+              if (rp) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(rp + (size_t)i * 4 * ldr));
                 v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
               }
-              v.x = apply_act(v.x, p.act); v.y = apply_act(v.y, p.act);
-              v.z = apply_act(v.z, p.act); v.w = apply_act(v.w, p.act);
-              *reinterpret_cast<float4*>(orow + n) = v;
-            }
-          } else {
+              if (act == ACT_RELU) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              } else if (act == ACT_GELU) {
+                v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
+              }
+              *reinterpret_cast<float4*>(dst + i * dst_step) = v;
+              if (planes) {
+                const float f[4] = {v.x, v.y, v.z, v.w};
+                uint32_t hw[2], lw[2];
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const int n = n0 + q;
-              if (n < p.N) {
-                float v = __uint_as_float(r[q]);
-                if (p.scale) v *= __ldg(p.scale + n);
-                if (p.shift) v += __ldg(p.shift + n);
-                if (rrow) v += __ldg(rrow + n);
-                orow[n] = apply_act(v, p.act);
+                for (int u = 0; u < 2; ++u) {
+                  const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * u]), h1 = __float2bfloat16_rn(f[2 * u + 1]);
+                  hw[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                  const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * u] - __bfloat162float(h0));
+                  const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * u + 1] - __bfloat162float(h1));
+                  lw[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                const size_t o = (size_t)(m_first + 4 * i) * ldc + n;
+                *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(hw[0], hw[1]);
+                if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(lw[0], lw[1]);
               }
             }
           }
         }
+        __syncwarp();
       }
       tc::tcgen05_before_sync();
       tc::mbar_arrive(tempty_bar(acc));
+      if (dbg && threadIdx.x == 0) p.dbg[6] = tc::gtime();
     }
-  } else if (warp < TC_EPI_WARPS + TC_PROD_WARPS) {
+  } else if (warp < TMA_WARP) {
     // =========================== A producers (implicit-GEMM gather) ===========================
+    if constexpr (!A_TMA) {
     const int pt = threadIdx.x - TC_EPI_WARPS * 32;       // 0..255
     const int chunk = pt & 7;                             // 16-byte chunk within the 128-byte operand row
     const int rg = pt >> 3;                               // rows rg + 32*i
@@ -361,7 +413,8 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
         }
       }
     }
-  } else if (warp == TC_EPI_WARPS + TC_PROD_WARPS) {
+    }  // !A_TMA
+  } else if (warp == TMA_WARP) {
     // =========================== W producer (TMA) ===========================
     if (lane == 0) {
       int kit = 0;
@@ -370,7 +423,12 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
           const int s = kit % STAGES;
           tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
-          tc::mbar_arrive_expect_tx(full_bar(s), PLANES * Cfg::B_BYTES);
+          tc::mbar_arrive_expect_tx(full_bar(s), PLANES * (Cfg::B_BYTES + (A_TMA ? Cfg::A_BYTES : 0)));
+          if constexpr (A_TMA) {
+            const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
+            tc::tma_load_2d(a_hi, &map_a_hi, full_bar(s), kb * Cfg::KB_ELEMS, tm * TC_BM);
+            if (PLANES == 2) tc::tma_load_2d(a_hi + Cfg::A_BYTES, &map_a_lo, full_bar(s), kb * Cfg::KB_ELEMS, tm * TC_BM);
+          }
           const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES;
           tc::tma_load_2d(b_hi, &map_hi, full_bar(s), kb * Cfg::KB_ELEMS, tn * BN);
           if (PLANES == 2) tc::tma_load_2d(b_hi + Cfg::B_BYTES, &map_lo, full_bar(s), kb * Cfg::KB_ELEMS, tn * BN);
@@ -392,6 +450,8 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
           const int s = kit % STAGES;
           tc::mbar_wait(full_bar(s), (kit / STAGES) & 1);
           tc::tcgen05_after_sync();
+          if (dbg && kb == 0) p.dbg[2] = tc::gtime();
+          if (dbg && kb == nkb - 1) p.dbg[3] = tc::gtime();
           const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t b_hi = a_hi + PLANES * Cfg::A_BYTES;
           const uint64_t da_hi = tc::make_smem_desc(a_hi), db_hi = tc::make_smem_desc(b_hi);
@@ -408,16 +468,18 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
           tc::umma_commit(empty_bar(s));   // frees the smem stage once the MMAs above have read it
         }
         tc::umma_commit(tfull_bar(acc));    // accumulator complete -> epilogue
+        if (dbg) p.dbg[4] = tc::gtime();
       }
     }
     __syncwarp();
   }
   tc::tcgen05_before_sync();
   __syncthreads();
-  if (warp == TC_EPI_WARPS + TC_PROD_WARPS + 1) {
+  if (warp == MMA_WARP) {
     tc::tcgen05_after_sync();
     tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
   }
+  if (dbg && threadIdx.x == 0) p.dbg[7] = tc::gtime();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -509,11 +571,25 @@ inline cudaError_t tc_prepare_weight(const float* w_dev, int N, int K, int preci
   return cudaSuccess;
 }
 
-template <bool TF32, int PASSES, int BN>
+// Tensor map over a bf16 activation plane [M, K] (row-major), box = 64 elements (128 B) x 128 rows, 128B swizzle.
+inline cudaError_t tc_make_act_map(const void* plane, int M, int K, CUtensorMap* out) {
+  PFN_encodeTiled enc = tc_encode_fn();
+  if (!enc) return cudaErrorNotSupported;
+  const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+  const cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  const cuuint32_t box[2] = {64, (cuuint32_t)TC_BM};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(plane), gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+template <bool TF32, int PASSES, int BN, bool A_TMA>
 inline cudaError_t tc_launch_one(const ConvGemm& p, const TcWeight& w, cudaStream_t s, int num_sms) {
-  using Cfg = TcCfg<TF32, PASSES, BN>;
+  using Cfg = TcCfg<TF32, PASSES, BN, A_TMA>;
   static bool attr_set = false;
-  auto kern = conv_gemm_tc_kernel<TF32, PASSES, BN>;
+  auto kern = conv_gemm_tc_kernel<TF32, PASSES, BN, A_TMA>;
   if (!attr_set) {
     cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (st != cudaSuccess) return st;
@@ -522,16 +598,28 @@ inline cudaError_t tc_launch_one(const ConvGemm& p, const TcWeight& w, cudaStrea
   const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = (p.N + BN - 1) / BN;
   const int grid = tiles_m * tiles_n < num_sms ? tiles_m * tiles_n : num_sms;
   constexpr int mi = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(p, w.map_hi[mi], w.map_lo[mi], tiles_m, tiles_n);
-  return cudaGetLastError();
+  const CUtensorMap* ah = A_TMA ? reinterpret_cast<const CUtensorMap*>(p.a_map_hi) : &w.map_hi[mi];
+  const CUtensorMap* al = (A_TMA && p.a_map_lo) ? reinterpret_cast<const CUtensorMap*>(p.a_map_lo) : ah;
+  return launch_kernel(kern, dim3(grid), dim3(tc_threads(A_TMA)), Cfg::SMEM_BYTES, s, p, w.map_hi[mi], w.map_lo[mi], *ah, *al,
+                       tiles_m, tiles_n);
 }
 
 template <bool TF32, int PASSES>
 inline cudaError_t tc_launch_bn(const ConvGemm& p, const TcWeight& w, cudaStream_t s, int num_sms) {
+  if constexpr (!TF32) {
+    // pre-split A planes + plain [M,K] operand -> TMA-fed A (decode-step GEMMs)
+    if (p.a_map_hi != nullptr && p.KH == 1 && p.KW == 1 && p.H == 1 && p.W == 1 && (PASSES == 1 || p.a_map_lo != nullptr)) {
+      switch (tc_pick_bn(p.M, p.N, num_sms)) {   // (a 256-wide 3-pass stage would not leave room for 2 stages here)
+        case 256:
+        case 128: return tc_launch_one<false, PASSES, 128, true>(p, w, s, num_sms);
+        case 64: return tc_launch_one<false, PASSES, 64, true>(p, w, s, num_sms);
+      }
+    }
+  }
   switch (tc_pick_bn(p.M, p.N, num_sms)) {
-    case 256: return tc_launch_one<TF32, PASSES, 256>(p, w, s, num_sms);
-    case 128: return tc_launch_one<TF32, PASSES, 128>(p, w, s, num_sms);
-    case 64: return tc_launch_one<TF32, PASSES, 64>(p, w, s, num_sms);
+    case 256: return tc_launch_one<TF32, PASSES, 256, false>(p, w, s, num_sms);
+    case 128: return tc_launch_one<TF32, PASSES, 128, false>(p, w, s, num_sms);
+    case 64: return tc_launch_one<TF32, PASSES, 64, false>(p, w, s, num_sms);
   }
   return cudaErrorInvalidValue;
 }

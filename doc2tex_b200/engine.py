@@ -193,5 +193,16 @@ class Engine:
                                             _lib.PREC[precision or self.precision], self._stream()), "d2t_debug_gemm")
         return c
 
+    def gemm_bench(self, M: int, N: int, K: int, precision: str, iters: int = 200, interleave: bool = False) -> float:
+        """Average microseconds per launch of an (M,N,K) contraction, warm, back to back."""
+        a = torch.randn(M, K, device=self.device)
+        w = torch.randn(N, K, device=self.device)
+        c = torch.empty(M, N, device=self.device)
+        ms = C.c_float()
+        self._check(self.lib.d2t_debug_gemm_bench(self.h, a.data_ptr(), w.data_ptr(), c.data_ptr(), M, N, K,
+                                                  _lib.PREC[precision], iters, 1 if interleave else 0, C.byref(ms),
+                                                  self._stream()), "d2t_debug_gemm_bench")
+        return ms.value * 1e3
+
     def launch_count(self) -> int:
         return int(self.lib.d2t_launch_count(self.h))

@@ -154,6 +154,10 @@ int d2t_debug_tap(d2t_engine* e, const char* name, float* out_dev, int64_t* nume
 int d2t_debug_gemm(d2t_engine* e, const float* a_dev, const float* w_dev,
                    const float* scale_dev, const float* shift_dev, float* c_dev,
                    int M, int N, int K, int act, int precision, d2t_stream stream);
+/* `iters` back-to-back launches of one contraction (optionally interleaved with a LayerNorm launch, the
+ * decode-step pattern); *ms_out = average milliseconds per iteration (CUDA events). */
+int d2t_debug_gemm_bench(d2t_engine* e, const float* a_dev, const float* w_dev, float* c_dev, int M, int N,
+                         int K, int precision, int iters, int interleave, float* ms_out, d2t_stream stream);
 /* Number of kernel launches issued by this engine since creation (bench bookkeeping;
  * launches replayed from a CUDA graph are counted per replay). */
 int64_t d2t_launch_count(const d2t_engine* e);
