@@ -17,6 +17,7 @@ struct TfmBuffers {
   float *scores = nullptr, *done_score = nullptr, *trace_score = nullptr, *logits_out = nullptr;
   long long* ids = nullptr;
   // bf16 hi/lo operand planes of the decoder activations + their TMA maps (tensor-core precisions only)
+  long long* dbg = nullptr;   // D2T_DBG_DECODE=1: phase timestamps of one decode-step GEMM
   bool planes = false;
   __nv_bfloat16 *x_hi = nullptr, *x_lo = nullptr, *att_hi = nullptr, *att_lo = nullptr, *ffn_hi = nullptr, *ffn_lo = nullptr;
   CUtensorMap map_x_hi, map_x_lo, map_att_hi, map_att_lo, map_ffn_hi, map_ffn_lo;
@@ -75,6 +76,7 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
       ConvGemm g = linear_params(b.x, e->dev[p + "self_attn.in_proj_weight"], e->dev[p + "self_attn.in_proj_bias"], b.q, R, 3 * D, D);
       g.ldc = D; g.n_split = D; g.out2 = selfkv; g.ldc2 = T * 2 * D; g.dyn = step; g.dyn_mul2 = 2 * D;
       from_x(g);
+      if (l == 1) g.dbg = b.dbg;
       if ((rc = dec_linear(e, g, s))) return rc;
     }
     if ((rc = enqueue_attention(e, b.q, selfkv, (long long)T * 2 * D, beam > 0 ? b.anc : nullptr, par, L,
@@ -160,6 +162,10 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
   if ((rc = pool_get(e, &b.ffn, (size_t)R * F))) return rc;
   if ((rc = pool_get(e, &b.logits, (size_t)R * V))) return rc;
   if ((rc = pool_get(e, &b.counters, 4))) return rc;
+  if (getenv("D2T_DBG_DECODE")) {
+    if ((rc = pool_get(e, &b.dbg, 16))) return rc;
+    CUDA_TRY(e, cudaMemsetAsync(b.dbg, 0, 16 * sizeof(long long), s));
+  }
   b.planes = c.precision == D2T_PREC_BF16X3 || c.precision == D2T_PREC_BF16;
   if (b.planes) {
     const bool lo = c.precision == D2T_PREC_BF16X3;
@@ -225,7 +231,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     std::vector<long long> key = {(long long)R, B, ntok, beam, T, want_logits ? 1 : 0};
     const void* ptrs[] = {b.crosskv, b.selfkv, b.x, b.x2, b.q, b.att, b.ffn, b.logits, b.counters, b.tokens, b.anc,
                           b.scores, b.n_live, b.n_done, b.finished, b.done_seq, b.done_len, b.done_score, b.trace,
-                          b.trace_score, b.ended, b.ids, b.logits_out, b.x_hi, b.x_lo, b.att_hi, b.att_lo, b.ffn_hi, b.ffn_lo};
+                          b.trace_score, b.ended, b.ids, b.logits_out, b.dbg, b.x_hi, b.x_lo, b.att_hi, b.att_lo, b.ffn_hi, b.ffn_lo};
     for (const void* q : ptrs) key.push_back((long long)(uintptr_t)q);
     for (auto& g : e->graphs) if (g.key == key) { exec = g.exec; nodes = g.nodes; }
     if (!exec) {
@@ -267,6 +273,13 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
   CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(e, cudaStreamSynchronize(s));
   done_step = e->h_counters[2];
+  if (b.dbg) {
+    long long h[12];
+    cudaMemcpy(h, b.dbg, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[decode gemm dbg R=%d] prologue %lld ns, first full +%lld, last full +%lld, last commit +%lld, "
+                    "epi start +%lld, epi done +%lld, exit +%lld\n", R, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0],
+            h[5] - h[0], h[6] - h[0], h[7] - h[0]);
+  }
   *steps_out = (stop_early && done_step >= 0) ? done_step : executed;
   return 0;
 }

@@ -54,10 +54,11 @@ __global__ void embed_tokens_kernel(const int* __restrict__ tokens, int tok_ld, 
 //   self-attention, greedy:  src = r                      n_keys = *step + 1
 //   self-attention, beam:    src = img*beam + anc[r][j]   n_keys = *step + 1   (ancestry indirection)
 //   cross-attention:         src = r / rows_per_src       n_keys = n_fixed      (memory shared by the beams)
-// HBM-bound single pass: every lane owns the keys j = lane (mod 32) and streams its key AND value head slices
-// as two full 128-byte lines per key (all loads of a key independent -> deep memory-level parallelism), keeping an
-// online-softmax state (running max, sum, 32-wide accumulator); the 32 lane states are merged once at the end
-// through shared memory.  Optional bf16 hi/lo planes of the output feed the tensor-core out-projection.
+// Memory-bound single pass.  A quarter warp (8 lanes x float4) covers one 128-byte key (and value) head slice, so
+// every load instruction moves four complete lines; the four quarter warps walk keys j = g (mod 4) with an
+// online-softmax state each (running max, sum, 4 output channels per lane), two keys in flight per quarter warp,
+// and are merged with shuffles at the end.  Optional bf16 hi/lo planes of the output feed the tensor-core
+// out-projection.
 template <int HD>
 __global__ void __launch_bounds__(256)
 decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kv,
@@ -65,71 +66,82 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __res
                         long long anc_parity_stride, int anc_ld, int rows_per_src,
                         const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
                         __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  static_assert(HD == 32, "8 lanes x float4 per head slice");
   pdl_trigger();
   pdl_wait();
-  static_assert(HD == 32, "one lane per output channel in the merge");
-  __shared__ float s_acc[8][32][HD + 1];
   const int r = blockIdx.x;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 3, c = (lane & 7) * 4;
   const int t = step ? *step : 0;
   const int n_keys = n_fixed > 0 ? n_fixed : t + 1;
   const int* anc_r = anc ? anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)r * anc_ld : nullptr;
   const int src_base = (r / rows_per_src) * (anc ? rows_per_src : 1);
-
-  float qv[HD], acc[HD];
   const float scale = rsqrtf((float)HD);
-#pragma unroll
-  for (int d = 0; d < HD; d += 4) {
-    const float4 v = *reinterpret_cast<const float4*>(q + (size_t)r * ldq + h * HD + d);
-    qv[d] = v.x * scale; qv[d + 1] = v.y * scale; qv[d + 2] = v.z * scale; qv[d + 3] = v.w * scale;
-    acc[d] = acc[d + 1] = acc[d + 2] = acc[d + 3] = 0.f;
-  }
+  float4 q4 = *reinterpret_cast<const float4*>(q + (size_t)r * ldq + h * HD + c);
+  q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
+  const float* kbase = kv + h * HD + c;
+
   float mx = -INFINITY, sum = 0.f;
-  for (int j = lane; j < n_keys; j += 32) {
-    const int src = anc_r ? src_base + anc_r[j] : src_base;
-    const float4* kp = reinterpret_cast<const float4*>(kv + (size_t)src * row_stride + (size_t)j * pos_stride + h * HD);
-    const float4* vp = reinterpret_cast<const float4*>(kv + (size_t)src * row_stride + (size_t)j * pos_stride + D + h * HD);
-    float4 k4[HD / 4], v4[HD / 4];
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const unsigned gmask = 0xFFu << (g * 8);   // quarter warps run different trip counts: group-local shuffles
+  for (int j0 = g; j0 < n_keys; j0 += 8) {
+    const int j1 = j0 + 4;
+    const bool has1 = j1 < n_keys;
+    const int s0 = anc_r ? src_base + anc_r[j0] : src_base;
+    const int s1 = has1 ? (anc_r ? src_base + anc_r[j1] : src_base) : s0;
+    const float* p0 = kbase + (size_t)s0 * row_stride + (size_t)j0 * pos_stride;
+    const float* p1 = kbase + (size_t)s1 * row_stride + (size_t)(has1 ? j1 : j0) * pos_stride;
+    const float4 k0 = __ldg(reinterpret_cast<const float4*>(p0));
+    const float4 k1 = __ldg(reinterpret_cast<const float4*>(p1));
+    const float4 v0 = __ldg(reinterpret_cast<const float4*>(p0 + D));
+    const float4 v1 = __ldg(reinterpret_cast<const float4*>(p1 + D));
+    float d0 = fmaf(q4.x, k0.x, fmaf(q4.y, k0.y, fmaf(q4.z, k0.z, q4.w * k0.w)));
+    float d1 = fmaf(q4.x, k1.x, fmaf(q4.y, k1.y, fmaf(q4.z, k1.z, q4.w * k1.w)));
 #pragma unroll
-    for (int i = 0; i < HD / 4; ++i) k4[i] = __ldg(kp + i);
-#pragma unroll
-    for (int i = 0; i < HD / 4; ++i) v4[i] = __ldg(vp + i);
-    float s = 0.f;
-#pragma unroll
-    for (int i = 0; i < HD / 4; ++i) {
-      s = fmaf(qv[4 * i], k4[i].x, s); s = fmaf(qv[4 * i + 1], k4[i].y, s);
-      s = fmaf(qv[4 * i + 2], k4[i].z, s); s = fmaf(qv[4 * i + 3], k4[i].w, s);
+    for (int o = 1; o < 8; o <<= 1) {
+      d0 += __shfl_xor_sync(gmask, d0, o);
+      d1 += __shfl_xor_sync(gmask, d1, o);
     }
-    const float nm = fmaxf(mx, s);
-    const float corr = expf(mx - nm);   // 0 on the first key (mx = -inf)
-    const float pj = expf(s - nm);
-    sum = sum * corr + pj;
-#pragma unroll
-    for (int i = 0; i < HD / 4; ++i) {
-      acc[4 * i] = fmaf(pj, v4[i].x, acc[4 * i] * corr);
-      acc[4 * i + 1] = fmaf(pj, v4[i].y, acc[4 * i + 1] * corr);
-      acc[4 * i + 2] = fmaf(pj, v4[i].z, acc[4 * i + 2] * corr);
-      acc[4 * i + 3] = fmaf(pj, v4[i].w, acc[4 * i + 3] * corr);
-    }
+    if (!has1) d1 = -INFINITY;
+    const float nm = fmaxf(mx, fmaxf(d0, d1));
+    const float corr = expf(mx - nm);   // 0 on the first iteration (mx = -inf)
+    const float e0 = expf(d0 - nm), e1 = expf(d1 - nm);
+    sum = sum * corr + (e0 + e1);
+    acc.x = fmaf(e1, v1.x, fmaf(e0, v0.x, acc.x * corr));
+    acc.y = fmaf(e1, v1.y, fmaf(e0, v0.y, acc.y * corr));
+    acc.z = fmaf(e1, v1.z, fmaf(e0, v0.z, acc.z * corr));
+    acc.w = fmaf(e1, v1.w, fmaf(e0, v0.w, acc.w * corr));
     mx = nm;
   }
-  // merge the 32 lane states: global max, rescale, sum
-  const float gm = warp_max(mx);
-  const float sc = (mx == -INFINITY) ? 0.f : expf(mx - gm);
-  const float total = warp_sum(sum * sc);
-#pragma unroll
-  for (int d = 0; d < HD; ++d) s_acc[h][lane][d] = acc[d] * sc;
+  // merge the four quarter-warp states
   __syncwarp();
-  float o = 0.f;
+  float gm = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
+  gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 16));
+  const float sc = (mx == -INFINITY) ? 0.f : expf(mx - gm);
+  sum *= sc; acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
 #pragma unroll
-  for (int l = 0; l < 32; ++l) o += s_acc[h][l][lane];
-  o /= total;
-  out[(size_t)r * D + h * HD + lane] = o;
-  if (out_hi) {
-    __nv_bfloat16 hi, lo;
-    split_bf16(o, hi, lo);
-    out_hi[(size_t)r * D + h * HD + lane] = hi;
-    if (out_lo) out_lo[(size_t)r * D + h * HD + lane] = lo;
+  for (int o = 8; o < 32; o <<= 1) {
+    sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if (g == 0) {
+    const float inv = 1.0f / sum;
+    const float4 o4 = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+    const size_t off = (size_t)r * D + h * HD + c;
+    *reinterpret_cast<float4*>(out + off) = o4;
+    if (out_hi) {
+      const float f[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(f[u], hi, lo);
+        out_hi[off + u] = hi;
+        if (out_lo) out_lo[off + u] = lo;
+      }
+    }
   }
 }
 

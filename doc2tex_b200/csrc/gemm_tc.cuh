@@ -31,6 +31,9 @@ namespace d2t {
 // ------------------------------------------------------------------------------------------------
 namespace tc {
 
+__device__ __noinline__ float4 gelu_erf4(float4 v) {
+  return make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
+}
 __device__ __forceinline__ long long gtime() {
   long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -244,10 +247,37 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
     if (p.out2) out2 = p.out2 + (p.dyn ? (long long)(*p.dyn) * p.dyn_mul2 : 0) - n_split;
     __nv_bfloat16* const out_hi = p.out_hi;
     __nv_bfloat16* const out_lo = p.out_lo;
+    // Epilogue operands that do not depend on the accumulator (bias / BN scale+shift, residual rows) are fetched
+    // BEFORE waiting for the MMA, and for the following chunk while the current one is being written, so their
+    // L2 latency is off the critical path of the small decode-step GEMMs.
+    float4 sc, sh, rr0, rr1, rr2, rr3, rr4, rr5, rr6, rr7;
+#define TC_EPI_PREFETCH(TM_, TN_, J_)                                                                              \
+    do {                                                                                                             \
+      const int n_ = (TN_) * BN + (J_) * 32 + c4;                                                                    \
+      const int m0_ = (TM_) * TC_BM + quad * 32 + sub_r;                                                             \
+      const float4 z_ = make_float4(0.f, 0.f, 0.f, 0.f);                                                             \
+      sc = make_float4(1.f, 1.f, 1.f, 1.f);                                                                          \
+      sh = z_;                                                                                                       \
+      if (n_ < N) {                                                                                                  \
+        if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + n_));                                          \
+        if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + n_));                                          \
+      }                                                                                                              \
+      const bool ok_ = res != nullptr && n_ < N;                                                                     \
+      const float* rp_ = res + (size_t)m0_ * ldr + n_;                                                               \
+      rr0 = (ok_ && m0_ + 0 < M) ? __ldg(reinterpret_cast<const float4*>(rp_)) : z_;                                 \
+      rr1 = (ok_ && m0_ + 4 < M) ? __ldg(reinterpret_cast<const float4*>(rp_ + (size_t)4 * ldr)) : z_;               \
+      rr2 = (ok_ && m0_ + 8 < M) ? __ldg(reinterpret_cast<const float4*>(rp_ + (size_t)8 * ldr)) : z_;               \
+      rr3 = (ok_ && m0_ + 12 < M) ? __ldg(reinterpret_cast<const float4*>(rp_ + (size_t)12 * ldr)) : z_;             \
+      rr4 = (ok_ && m0_ + 16 < M) ? __ldg(reinterpret_cast<const float4*>(rp_ + (size_t)16 * ldr)) : z_;             \
+      rr5 = (ok_ && m0_ + 20 < M) ? __ldg(reinterpret_cast<const float4*>(rp_ + (size_t)20 * ldr)) : z_;             \
+      rr6 = (ok_ && m0_ + 24 < M) ? __ldg(reinterpret_cast<const float4*>(rp_ + (size_t)24 * ldr)) : z_;             \
+      rr7 = (ok_ && m0_ + 28 < M) ? __ldg(reinterpret_cast<const float4*>(rp_ + (size_t)28 * ldr)) : z_;             \
+    } while (0)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
       const int acc = it & 1;
+      if (slot < BN / 32) TC_EPI_PREFETCH(tm, tn, slot);
       tc::mbar_wait(tfull_bar(acc), (it >> 1) & 1);
       tc::tcgen05_after_sync();
       if (dbg && threadIdx.x == 0) p.dbg[5] = tc::gtime();
@@ -262,33 +292,38 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
           *reinterpret_cast<uint4*>(stg + lane * TC_EPI_PITCH + q * 4) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
         __syncwarp();
         const int n = tn * BN + j * 32 + c4;
+        float4 v[8];
+        const float4 rr[8] = {rr0, rr1, rr2, rr3, rr4, rr5, rr6, rr7};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          v[i] = *reinterpret_cast<const float4*>(stg + (sub_r + 4 * i) * TC_EPI_PITCH + c4);
+          v[i].x = fmaf(v[i].x, sc.x, sh.x) + rr[i].x; v[i].y = fmaf(v[i].y, sc.y, sh.y) + rr[i].y;
+          v[i].z = fmaf(v[i].z, sc.z, sh.z) + rr[i].z; v[i].w = fmaf(v[i].w, sc.w, sh.w) + rr[i].w;
+        }
+        __syncwarp();
+        if (j + NSLOT < BN / 32) TC_EPI_PREFETCH(tm, tn, j + NSLOT);   // operands of the next chunk, in flight during the stores
         if (n < N) {
-          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + n));
-          if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + n));
           const bool second = out2 != nullptr && n >= n_split;
           float* dst = second ? out2 + (size_t)m_first * ldc2 + n : out + (size_t)m_first * ldc + n;
           const size_t dst_step = (size_t)4 * (second ? ldc2 : ldc);
-          const float* rp = res ? res + (size_t)m_first * ldr + n : nullptr;
-          const float* sp = stg + sub_r * TC_EPI_PITCH + c4;
           const bool planes = out_hi != nullptr && !second;
-#pragma unroll 1
-          for (int i = 0; i < 8; ++i) {
-            if (m_first + 4 * i < M) {
-              float4 v = *reinterpret_cast<const float4*>(sp + i * 4 * TC_EPI_PITCH);
-              v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-              if (rp) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(rp + (size_t)i * 4 * ldr));
-                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-              }
-              if (act == ACT_RELU) {
-                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-              } else if (act == ACT_GELU) {
-                v.x = gelu_erf(v.x); v.y = gelu_erf(v.y); v.z = gelu_erf(v.z); v.w = gelu_erf(v.w);
-              }
-              *reinterpret_cast<float4*>(dst + i * dst_step) = v;
-              if (planes) {
-                const float f[4] = {v.x, v.y, v.z, v.w};
+          if (act == ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[i].x = fmaxf(v[i].x, 0.f); v[i].y = fmaxf(v[i].y, 0.f); v[i].z = fmaxf(v[i].z, 0.f); v[i].w = fmaxf(v[i].w, 0.f);
+            }
+          } else if (act == ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = tc::gelu_erf4(v[i]);   // out-of-line: keeps the unrolled epilogue small
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (m_first + 4 * i < M) *reinterpret_cast<float4*>(dst + i * dst_step) = v[i];
+          if (planes) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (m_first + 4 * i < M) {
+                const float f[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
                 uint32_t hw[2], lw[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -305,12 +340,12 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
             }
           }
         }
-        __syncwarp();
       }
       tc::tcgen05_before_sync();
       tc::mbar_arrive(tempty_bar(acc));
       if (dbg && threadIdx.x == 0) p.dbg[6] = tc::gtime();
     }
+#undef TC_EPI_PREFETCH
   } else if (warp < TMA_WARP) {
     // =========================== A producers (implicit-GEMM gather) ===========================
     if constexpr (!A_TMA) {
