@@ -47,7 +47,17 @@ def parse():
     ap.add_argument("--ref-batch", type=int, default=8, help="images per step of the CPU reference sample")
     ap.add_argument("--cpu-sample", type=int, default=8, help="images of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--no-graphs", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--head", default="TFM", choices=["TFM", "Attnv2"],
+                    help="TFM = HybridViT + transformer decoder (configs 1,2,3,5); Attnv2 = config/train.yaml default stack (config 4)")
+    ap.add_argument("--encoder-sms", type=int, default=0,
+                    help="SMs given to the encoder's persistent kernels; the rest run the overlapped decode of the previous batch")
+    ap.add_argument("--sequential", action="store_true", help="no encode/decode overlap across batches")
+    a = ap.parse_args()
+    if a.encoder_sms <= 0:
+        a.encoder_sms = 112 if a.mode == "greedy" else 88   # measured sweet spots (profiles/r01_pipeline_sweep.txt)
+    if a.head == "Attnv2" and a.mode != "greedy":
+        ap.error("the Attnv2 head is accelerated for greedy decode only (beam is a 'next' row, SURVEY 8f1)")
+    return a
 
 
 def peaks():
@@ -96,11 +106,10 @@ class ClockSampler:
 # reference arm: the reference's algorithm (oracle port — the reference is pure Python/PyTorch and
 # /root/reference does not exist on the GPU box) on the host cores, O(T^2) decode and all.
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_step(sd, img, mode, beam):
+def cpu_reference_step(sd, img, mode, beam, head="TFM"):
     from oracle import oracle_model as om  # the reference arm is the one place bench.py may run oracle/
     if mode == "greedy":
-        _, _, gen = om.recognize_greedy(sd, img, "TFM", 150, True)
-        return gen
+        return om.recognize_greedy(sd, img, head, 150, True)[-1]
     return om.recognize_beam(sd, img, beam, 150)
 
 
@@ -109,16 +118,16 @@ def run_reference(args):
     if rank != 0:
         return
     torch.set_num_threads(os.cpu_count())
-    cfg = synth.make_config("TFM")
+    cfg = synth.make_config(args.head)
     sd = synth.make_state_dict(cfg, seed=1111, suppress_end=True)
     n = args.ref_batch if args.mode == "greedy" else max(1, args.ref_batch // 4)
     img = synth.make_images(n, args.height, args.width, seed=2024)
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_step(sd, img[:1], args.mode, args.beam)
+        cpu_reference_step(sd, img[:1], args.mode, args.beam, args.head)
     times = []
     for _ in range(args.steps):
         t0 = time.perf_counter()
-        cpu_reference_step(sd, img, args.mode, args.beam)
+        cpu_reference_step(sd, img, args.mode, args.beam, args.head)
         times.append(time.perf_counter() - t0)
     total = sum(times)
     value = n * args.steps / total
@@ -138,12 +147,13 @@ def run_reference(args):
 def workload_config(args, batch):
     dec = "greedy" if args.mode == "greedy" else f"beam-{args.beam}"
     return {
-        "workload": f"HybridViT (ResNet stem + 6-block ViT + 4-layer TFM decoder) {dec} decode, batch {batch} per GPU, "
+        "workload": f"HybridViT (ResNet stem + 6-block ViT + "
+                    f"{'4-layer TFM decoder' if args.head == 'TFM' else 'Attnv2 LSTM coverage-attention decoder'}) {dec} decode, batch {batch} per GPU, "
                     f"{args.height}x{args.width} grayscale, max_len 150 (151 full-length steps, END suppressed), "
                     f"{args.precision} mode",
         "batch_per_gpu": batch, "image": [args.height, args.width], "decode": dec, "decode_steps": 151,
-        "precision": args.precision, "vocab": 504,
-        "l2": "activations + KV cache per step (>1 GB) exceed the 126 MB L2; a 256 MiB buffer is also written between timed steps",
+        "precision": args.precision, "vocab": 504 if args.head == "TFM" else 503, "head": args.head,
+        "l2": "inputs larger than L2: activations + KV cache per step (>1 GB) exceed the 126 MB L2",
     }
 
 
@@ -159,7 +169,7 @@ def run_engine(args):
     from doc2tex_b200.engine import Engine
     from doc2tex_b200.modules.build_model import Model
 
-    cfg = synth.make_config("TFM", beam_size=(args.beam if args.mode == "beam" else 1))
+    cfg = synth.make_config(args.head, beam_size=(args.beam if args.mode == "beam" else 1))
     cfg["engine"] = {"precision": args.precision, "use_graphs": not args.no_graphs}
     sd = synth.make_state_dict(cfg, seed=1111, suppress_end=True)
     model = Model(cfg)
@@ -174,28 +184,31 @@ def run_engine(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     T = 151
 
-    def step_device():
-        ctx, _, _ = eng.encode(img_dev)
-        if args.mode == "greedy":
-            ids, _, _ = eng.decode_greedy(ctx, T, is_test=True, return_logits=False)
-            lens = scores = None
-        else:
-            ids, lens, scores, _, _, _ = eng.decode_beam(ctx, args.beam, T)
-        return d2dist.gather_results(ids, lens, scores, n_total=B * world)
+    from doc2tex_b200.pipeline import PipelinedRecognizer
+    pipe = PipelinedRecognizer(eng, args.mode, args.beam, T, encoder_sms=None if args.sequential else args.encoder_sms)
 
-    def step_e2e():
-        x = img_host.to(dev, non_blocking=True)
-        text = torch.full((B, 1), 1, dtype=torch.long, device=dev)
-        if args.mode == "greedy":
-            ctx, _, _ = eng.encode(x)
-            ids, _, _ = eng.decode_greedy(ctx, T, is_test=True, return_logits=False)
-            out = d2dist.gather_results(ids, n_total=B * world)[0]
-        else:
-            ctx, _, _ = eng.encode(x)
-            ids, lens, scores, _, _, _ = eng.decode_beam(ctx, args.beam, T)
-            out = d2dist.gather_results(ids, lens, scores, n_total=B * world)[0]
-        del text
-        return out.cpu()
+    def gather(res):
+        return d2dist.gather_results(res["ids"], res.get("lens"), res.get("scores"), n_total=B * world)
+
+    def step_device():     # one batch, strictly sequential (latency view)
+        ctx, _, _ = eng.encode(img_dev)
+        return gather(pipe._decode(ctx))
+
+    def run_steps(k, host):
+        """k batches through the public pipelined API; host=True adds the H2D copy of every batch (pinned memory)
+        and a D2H read of every result to the timed region."""
+        src = img_host if host else img_dev
+        if args.sequential:
+            for _ in range(k):
+                ctx, _, _ = eng.encode(src.to(dev, non_blocking=True))
+                out = gather(pipe._decode(ctx))[0]
+                if host:
+                    out.cpu()
+            return
+        for res in pipe.run([src] * k):
+            out = gather(res)[0]
+            if host:
+                out.cpu()
 
     def barrier():
         if world > 1:
@@ -204,24 +217,27 @@ def run_engine(args):
 
     for _ in range(max(args.warmup, 3)):
         step_device()
+    run_steps(2, False)
     barrier()
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    # ---- timed region: exactly K steps (batches), one bracket; working set per step (activations + KV cache,
+    # > 1 GB) exceeds the 126 MB L2, the flush buffer is written once before the bracket ----
+    flush.fill_(1)
+    barrier()
     l0 = eng.launch_count()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for a, b in ev:
-        flush.fill_(1)
-        barrier()
-        a.record()
-        step_device()
-        b.record()
-        barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    run_steps(args.steps, False)
+    ev1.record()
+    barrier()
     launches = eng.launch_count() - l0
-    t_ms = sum(a.elapsed_time(b) for a, b in ev)
-    # stage split (separate pass, same workload): encoder vs decode, CUDA events on the launching stream
-    enc_ms = dec_ms = 0.0
+    t_ms = ev0.elapsed_time(ev1)
+    # stage split (separate sequential pass, same workload): encoder vs decode, CUDA events on the launching stream
+    enc_ms = dec_ms = seq_ms = 0.0
+    eng.set_option("encoder_sms", torch.cuda.get_device_properties(dev).multi_processor_count)
     for _ in range(args.steps):
         flush.fill_(1)
         torch.cuda.synchronize()
@@ -229,23 +245,21 @@ def run_engine(args):
         e0.record()
         ctx, _, _ = eng.encode(img_dev)
         e1.record()
-        if args.mode == "greedy":
-            eng.decode_greedy(ctx, T, is_test=True, return_logits=False)
-        else:
-            eng.decode_beam(ctx, args.beam, T)
+        pipe._decode(ctx)
         e2.record()
         torch.cuda.synchronize()
         enc_ms += e0.elapsed_time(e1)
         dec_ms += e1.elapsed_time(e2)
     enc_ms /= args.steps
     dec_ms /= args.steps
+    seq_ms = enc_ms + dec_ms
+    if not args.sequential:
+        eng.set_option("encoder_sms", args.encoder_sms)
     # end to end through the public API with host buffers
-    for _ in range(2):
-        step_e2e()
+    run_steps(2, True)
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step_e2e()
+    run_steps(args.steps, True)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
@@ -277,7 +291,10 @@ def run_engine(args):
         "metric": "formulas/sec", "value": value, "unit": "formulas/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": t_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16x3": "bf16x3", "bf16": "bf16"}[args.precision],
-        "data": "synthetic", "config": workload_config(args, B), "clocks": clocks,
+        "data": "synthetic", "config": dict(workload_config(args, B), schedule=(
+            "sequential" if args.sequential else
+            f"pipelined: encode(i+1) on {args.encoder_sms} SMs overlaps decode(i); one batch alone takes {seq_ms:.1f} ms")),
+        "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "formulas/s", "h2d_bytes_per_step": img_host.numel() * 4,
                 "d2h_bytes_per_step": B * world * (T + 2) * 8 if world > 1 else B * T * 8},
         "gpu_launches": int(launches), "roofline": roof,
@@ -287,7 +304,7 @@ def run_engine(args):
         n = args.cpu_sample if args.mode == "greedy" else max(1, args.cpu_sample // 4)
         sub = synth.make_images(n, H, W, seed=2024)
         t0 = time.perf_counter()
-        cpu_reference_step(sd, sub, args.mode, args.beam)
+        cpu_reference_step(sd, sub, args.mode, args.beam, args.head)
         dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": n / dt, "unit": "formulas/s", "cores": torch.get_num_threads(), "kind": "port",
                                 "sample": f"{n} images, one pass, {args.mode} full-length (151 steps), {H}x{W}; "

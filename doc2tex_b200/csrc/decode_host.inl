@@ -147,6 +147,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     return e->fail(D2T_ERR_INVALID, "max_steps %d exceeds max_seq_len+1 = %d", max_steps, c.max_seq_len + 1);
   if (beam > BEAM_MAX) return e->fail(D2T_ERR_UNSUPPORTED, "beam size %d > %d", beam, BEAM_MAX);
   CUDA_TRY(e, cudaSetDevice(e->device));
+  e->active_sms = e->num_sms;
   const int D = c.hidden, F = c.dec_ff, V = c.vocab, T = max_steps, L = T + 1;
   const int R = beam > 0 ? B * beam : B;
   const int nl = c.dec_layers;

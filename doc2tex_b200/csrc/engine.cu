@@ -82,6 +82,8 @@ struct d2t_engine {
   d2t_config cfg{};
   int device = 0;
   int num_sms = 148;
+  int enc_sms = 148;     // SMs the encoder's persistent kernels may occupy (the rest stay free for a concurrent decode)
+  int active_sms = 148;  // grid-sizing budget of the API call being enqueued
   std::string err;
   bool finalized = false;
   int64_t launches = 0;
@@ -235,12 +237,12 @@ int run_contraction(d2t_engine* e, const ConvGemm& p, const TcWeight* tcw, int p
     if (it != e->tcw.end()) tcw = &it->second;
   }
   if (precision != D2T_PREC_FP32 && tcw != nullptr && tcw->ready && tcw->N == p.N && tcw->K == p.K && tc_supported(p)) {
-    cudaError_t st = launch_conv_gemm_tc(p, *tcw, precision, s, e->num_sms);
+    cudaError_t st = launch_conv_gemm_tc(p, *tcw, precision, s, e->active_sms);
     if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tcgen05 contraction launch failed: %s", cudaGetErrorString(st));
     e->launches += 1;
     return 0;
   }
-  cudaError_t st = launch_conv_gemm_simt(p, s, e->num_sms);
+  cudaError_t st = launch_conv_gemm_simt(p, s, e->active_sms);
   if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "contraction launch failed: %s", cudaGetErrorString(st));
   e->launches += 1;
   return 0;
@@ -289,7 +291,7 @@ int pool_layer(d2t_engine* e, const Fmap& x, Fmap* y, int sh, int sw, int ph, in
   const int OH = (x.H + 2 * ph - 2) / sh + 1, OW = (x.W + 2 * pw - 2) / sw + 1;
   if (int rc = alloc_act(e, e->enc_pool, y, x.B, OH, OW, x.C)) return rc;
   const long long total = (long long)y->numel() / 4;
-  maxpool2x2_nhwc_kernel<<<grid_for(total, 256, e->num_sms), 256, 0, s>>>(x.p, y->p, x.B, x.H, x.W, x.C, OH, OW, sh, sw, ph, pw);
+  maxpool2x2_nhwc_kernel<<<grid_for(total, 256, e->active_sms), 256, 0, s>>>(x.p, y->p, x.B, x.H, x.W, x.C, OH, OW, sh, sw, ph, pw);
   e->launches += 1;
   CUDA_TRY(e, cudaGetLastError());
   return 0;
@@ -397,6 +399,7 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   e->cfg = *cfg;
   e->device = device;
   e->num_sms = prop.multiProcessorCount;
+  e->enc_sms = e->active_sms = e->num_sms;
   if (const char* v = getenv("D2T_PDL")) e->use_pdl = atoi(v) != 0;
   cudaSetDevice(device);
   if (cudaMallocHost(&e->h_counters, 4 * sizeof(int)) != cudaSuccess) {
@@ -404,7 +407,9 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
     delete e;
     return D2T_ERR_CUDA;
   }
-  if (cudaStreamCreateWithFlags(&e->work, cudaStreamNonBlocking) != cudaSuccess ||
+  int prio_lo = 0, prio_hi = 0;   // decode chain = highest priority: its small kernels get the free SMs first
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&e->work, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
     g_create_error = "stream/event creation failed";
@@ -635,6 +640,20 @@ int d2t_encoder_geometry(const d2t_engine* e, int H, int W, int* gh, int* gw, in
   return D2T_OK;
 }
 
+int d2t_set_option(d2t_engine* e, const char* key, int value) {
+  if (!e || !key) return D2T_ERR_INVALID;
+  const std::string k = key;
+  if (k == "encoder_sms") {
+    if (value < 8 || value > e->num_sms) return e->fail(D2T_ERR_INVALID, "encoder_sms must be in [8, %d]", e->num_sms);
+    e->enc_sms = value;
+  } else if (k == "pdl") {
+    e->use_pdl = value != 0;
+  } else {
+    return e->fail(D2T_ERR_INVALID, "unknown option '%s'", key);
+  }
+  return D2T_OK;
+}
+
 int d2t_set_debug(d2t_engine* e, int keep_taps) {
   if (!e) return D2T_ERR_INVALID;
   e->keep_taps = keep_taps != 0;
@@ -651,6 +670,7 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
     return e->fail(D2T_ERR_INVALID, "image %dx%d needs %d tokens but pos_embed has %d rows (max_dimension)", H, W, ntok, e->cfg.max_tokens);
   CUDA_TRY(e, cudaSetDevice(e->device));
   cudaStream_t s = (cudaStream_t)stream;
+  e->active_sms = e->enc_sms;
   e->enc_pool.release_all();
   e->taps.clear();
   const d2t_config& c = e->cfg;
@@ -664,7 +684,7 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
     if ((rc = alloc_act(e, e->enc_pool, &x, B, H, W, c0.cout))) return rc;
     const long long total = (long long)B * H * W * (c0.cout / 4);
     const size_t smem = (size_t)11 * c0.cout * sizeof(float);
-    conv0_direct_kernel<<<grid_for(total, 256, e->num_sms), 256, smem, s>>>(img, c0.w, c0.scale, c0.shift, x.p, B, H, W, c0.cout);
+    conv0_direct_kernel<<<grid_for(total, 256, e->active_sms), 256, smem, s>>>(img, c0.w, c0.scale, c0.shift, x.p, B, H, W, c0.cout);
     e->launches += 1;
     CUDA_TRY(e, cudaGetLastError());
     tap(e, "conv0_1", x);
@@ -712,7 +732,7 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
   if ((rc = alloc_act(e, e->enc_pool, &qkv, B, 1, T, 3 * D))) return rc;
   if ((rc = alloc_act(e, e->enc_pool, &att, B, 1, T, D))) return rc;
   if ((rc = alloc_act(e, e->enc_pool, &ff, B, 1, T, 4 * D))) return rc;
-  assemble_tokens_kernel<<<grid_for((long long)rows * D / 4, 256, e->num_sms), 256, 0, s>>>(
+  assemble_tokens_kernel<<<grid_for((long long)rows * D / 4, 256, e->active_sms), 256, 0, s>>>(
       tok.p, e->dev[SEQ + "cls_token"], e->dev[SEQ + "pos_embed"], xs.p, B, N, D);
   e->launches += 1;
   CUDA_TRY(e, cudaGetLastError());
@@ -767,6 +787,7 @@ int d2t_debug_gemm(d2t_engine* e, const float* a, const float* w, const float* s
                    int M, int N, int K, int act, int precision, d2t_stream stream) {
   if (!e) return D2T_ERR_INVALID;
   CUDA_TRY(e, cudaSetDevice(e->device));
+  e->active_sms = e->num_sms;
   ConvGemm p = linear_params(a, w, shift, c, M, N, K);
   p.scale = scale; p.act = act;
   if (precision == D2T_PREC_FP32) return run_contraction(e, p, nullptr, precision, (cudaStream_t)stream);
@@ -792,6 +813,7 @@ int d2t_debug_gemm_bench(d2t_engine* e, const float* a, const float* w, float* c
   if (!e || !ms_out) return D2T_ERR_INVALID;
   CUDA_TRY(e, cudaSetDevice(e->device));
   cudaStream_t s = e->work;
+  e->active_sms = e->num_sms;
   ConvGemm p = linear_params(a, w, nullptr, c, M, N, K);
   long long* dbg_dev = nullptr;
   cudaMalloc(&dbg_dev, 16 * sizeof(long long));

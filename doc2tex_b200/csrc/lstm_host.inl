@@ -102,6 +102,7 @@ extern "C" int d2t_decode_attn_greedy(d2t_engine* e, const float* ctx, int B, in
   CUDA_TRY(e, cudaSetDevice(e->device));
   WorkStream ws(e, (cudaStream_t)stream);
   cudaStream_t s = ws.get();
+  e->active_sms = e->num_sms;
   const int D = c.hidden, Hs = c.attn_hidden, V = c.vocab, T = max_steps, L = T + 1, Kc = 2 * D + Hs, S = ntok - 1;
   const bool want_logits = logits != nullptr;
   e->dec_pool.release_all();

@@ -167,6 +167,10 @@ class Engine:
                     "d2t_decode_beam")
         return ids, lens, score, steps.value, tr, trs
 
+    def set_option(self, key: str, value: int):
+        """Engine knobs: "encoder_sms" (SM budget of the encoder's persistent kernels), "pdl" (0/1)."""
+        self._check(self.lib.d2t_set_option(self.h, key.encode(), int(value)), f"d2t_set_option({key})")
+
     # ---- test / profiling hooks ----
     def set_debug(self, keep_taps: bool):
         self._check(self.lib.d2t_set_debug(self.h, 1 if keep_taps else 0), "d2t_set_debug")

@@ -138,6 +138,13 @@ int d2t_decode_attn_greedy(d2t_engine* e, const float* ctx_dev, int B, int ntok,
                            float* logits_dev, int* steps_out, d2t_stream stream);
 
 /*
+ * Engine knobs (no reference counterpart).  key = "encoder_sms": number of SMs the encoder's persistent
+ * tensor-core kernels may occupy (default: all) — leaving a few SMs free lets the latency-bound decode of
+ * batch i overlap the encode of batch i+1 on another stream (doc2tex_b200/pipeline.py); "pdl": 0/1.
+ */
+int d2t_set_option(d2t_engine* e, const char* key, int value);
+
+/*
  * Test / profiling hooks (not part of the reference surface).
  */
 /* keep_taps != 0: d2t_encode keeps every intermediate activation alive for d2t_debug_tap. */

@@ -192,3 +192,97 @@ def test_model_dropin_surface(built_lib):
         seq, score, _ = m(img[:1], text[:1], is_train=False, is_test=True)
     assert seq.device.type == "cpu" and seq.shape[0] == 1 and isinstance(score, float)
     assert seq[0].tolist() == g["beam_seq"][0, : int(g["beam_len"][0])].tolist()
+
+
+def test_pipelined_schedule_equals_sequential(built_lib):
+    """encode(i+1) overlapped with decode(i) on a reduced SM budget gives exactly the sequential results."""
+    from doc2tex_b200.pipeline import PipelinedRecognizer
+    e = engine_for("TFM", 1.5, "bf16x3")
+    batches = [synth.make_images(3, 64, 256, seed=100 + 7 * i).cuda() for i in range(3)]
+    seq = []
+    for x in batches:
+        ctx, _, _ = e.encode(x)
+        ids, _, steps = e.decode_greedy(ctx, is_test=True, return_logits=False)
+        b = e.decode_beam(ctx, 5)
+        seq.append((ids[:, :steps].clone(), b[0].clone(), b[1].clone()))
+    for mode in ("greedy", "beam"):
+        pipe = PipelinedRecognizer(e, mode, 5, None, encoder_sms=96)
+        outs = list(pipe.run([x.cpu().pin_memory() if i == 1 else x for i, x in enumerate(batches)]))
+        assert len(outs) == 3
+        for (g_ids, b_ids, b_len), res in zip(seq, outs):
+            if mode == "greedy":
+                assert torch.equal(res["ids"], g_ids)
+            else:
+                assert torch.equal(res["ids"], b_ids) and torch.equal(res["lens"], b_len)
+    e.set_option("encoder_sms", 148)
+
+
+def test_full_batch_properties_b256(built_lib):
+    """BASELINE config size (B=256, 151 steps): size-independent properties.
+    (1) the tensor-core fp32-parity mode (bf16x3) and the FFMA anchor (fp32) produce identical greedy tokens for all
+        256 images; (2) row i of the batch equals the same image decoded alone (batch independence, what makes the
+        rank sharding exact); (3) the oracle agrees on a 2-image subset."""
+    from oracle import oracle_model as om
+    cfg, sd = state_dict_for("TFM", -1e4)
+    img = synth.make_images(256, 64, 256, seed=2024)
+    ids = {}
+    for prec in ("fp32", "bf16x3"):
+        e = engine_for("TFM", -1e4, prec)
+        ctx, _, _ = e.encode(img.cuda())
+        out, _, steps = e.decode_greedy(ctx, is_test=True, return_logits=False)
+        assert steps == 151
+        ids[prec] = out.cpu()
+        if prec == "bf16x3":
+            one, _, _ = e.decode_greedy(ctx[200:201].contiguous(), is_test=True, return_logits=False)
+            assert torch.equal(one.cpu()[0], ids[prec][200])
+    same = (ids["fp32"] == ids["bf16x3"]).all(dim=1)
+    assert bool(same.all()), f"{int((~same).sum())} of 256 rows differ between fp32 and bf16x3"
+    ctx_or, _, _ = om.encoder_forward(sd, img[:2])
+    _, _, gen = om.TFMHead(sd, max_seq_len=150).greedy(ctx_or, True)
+    assert torch.equal(gen, ids["bf16x3"][:2])
+
+
+@pytest.mark.parametrize("H,W", [(192, 896), (160, 704), (32, 32)])
+def test_extreme_image_sizes_match_oracle(built_lib, H, W):
+    """Largest (679 tokens) and smallest (1 patch + cls) geometries of the YAML surface against the live oracle."""
+    from oracle import oracle_model as om
+    cfg, sd = state_dict_for("TFM", 1.5)
+    e = engine_for("TFM", 1.5)
+    img = synth.make_images(1, H, W, seed=77)
+    ctx, grid, pad = e.encode(img.cuda())
+    ctx_or, grid_or, pad_or = om.encoder_forward(sd, img)
+    assert tuple(grid) == tuple(grid_or) and tuple(pad) == tuple(pad_or)
+    assert ctx.shape[1] == 1 + grid[0] * grid[1]
+    assert rel_err(ctx.cpu(), ctx_or) < REL_TOL_FP32
+    head = om.TFMHead(sd, max_seq_len=150)
+    _, logits_or, gen_or = head.greedy(ctx_or, is_test=True, max_steps=12)
+    ids, logits, steps = e.decode_greedy(ctx, max_steps=12, is_test=True)
+    assert steps == gen_or.shape[1] and torch.equal(ids[:, :steps].cpu(), gen_or)
+    assert rel_err(logits[:, steps - 1].cpu(), logits_or[:, steps - 1]) < REL_TOL_FP32
+    seq, score = head.beam(ctx_or, 5)
+    bids, blen, bscore, _, _, _ = e.decode_beam(ctx, 5)
+    assert bids[0, : int(blen[0])].cpu().tolist() == seq
+
+
+def test_error_paths(built_lib):
+    """Bad shapes / call order are reported through status codes + d2t_last_error, never a crash."""
+    from doc2tex_b200.engine import Engine, EngineError
+    cfg, sd = state_dict_for("TFM", None)
+    e = Engine(cfg, "cuda:0")
+    with pytest.raises(EngineError, match="finalize"):
+        e.encode(torch.zeros(1, 1, 64, 256, device="cuda"))
+    bad = dict(sd)
+    bad.pop(synth.PRED + "proj.weight")
+    with pytest.raises(EngineError, match="proj.weight"):
+        e.load_state_dict(bad)
+    e.load_state_dict(sd)
+    with pytest.raises(EngineError, match="multiples of 32"):
+        e.encode(torch.zeros(1, 1, 60, 256, device="cuda"))
+    with pytest.raises(EngineError, match="tokens"):
+        e.encode(torch.zeros(1, 1, 224, 896, device="cuda"))       # larger than max_dimension's pos_embed
+    ctx, _, _ = e.encode(torch.zeros(1, 1, 64, 256, device="cuda"))
+    with pytest.raises(EngineError, match="max_steps"):
+        e.decode_greedy(ctx, max_steps=400)
+    with pytest.raises(EngineError):
+        e.decode_beam(ctx, 32)
+    e.close()
