@@ -1,0 +1,217 @@
+#!/usr/bin/env python
+"""Inference entry point with the reference's CLI surface (api/infer.py:358-415), on the B200 engine.
+
+    python api/infer.py --config cfg.yaml --csv_dir labels.tsv --data_dir images/ --log_path run.log --batch_size 256
+
+Same flags (--config --csv_dir --start_idx --data_dir --amp --resizer --log_path --batch_size --num_workers
+--strong_log --console), same YAML keys, same printed / logged summary lines (infer.py:332-354) and the same CSV
+row layout (:230-236).  Differences, on purpose:
+  * ``--batch_size`` is honoured: images are bucketed by their exact (H, W) — the reference's sampler contract
+    (torch_dataset.py:46-66) — and every bucket runs batched through ``Model`` (the reference iterates the Dataset
+    itself, so its batch is always 1: api/infer.py:94);
+  * the model is ``doc2tex_b200.modules.build_model.Model`` (no CPU fallback);
+  * ``--synthetic N`` runs N seeded synthetic images when no dataset is at hand (GPU box smoke test);
+  * metrics: exact match and token edit distance are computed in-process (the reference needs nltk / Levenshtein,
+    which are not part of the hot path); BLEU is omitted.
+The image preprocessing of the reference (utils/predict_utils.py::resize — crop to ink, pad to /32, normalise)
+is a 'next' row; here an image is converted to grayscale, padded with white to the next multiple
+of 32 and normalised with the YAML's mean/std.
+"""
+from __future__ import annotations
+
+import argparse
+import csv
+import os
+import random
+import sys
+import time
+from collections import defaultdict
+
+import numpy as np
+import torch
+import yaml
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from doc2tex_b200 import synth  # noqa: E402
+from doc2tex_b200.modules.build_model import Model  # noqa: E402
+from doc2tex_b200.modules.converter import builder  # noqa: E402
+
+DELIMITER = "\t"  # doc2tex/data/data_const.py:18
+
+
+def edit_distance(a, b) -> int:
+    prev = list(range(len(b) + 1))
+    for i, x in enumerate(a, 1):
+        cur = [i]
+        for j, y in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (x != y)))
+        prev = cur
+    return prev[-1]
+
+
+def load_image(path: str, config: dict) -> torch.Tensor:
+    from PIL import Image
+    img = Image.open(path).convert("L")
+    w, h = img.size
+    min_h, min_w = config.get("min_dimension", [32, 32])
+    H = max(min_h, (h + 31) // 32 * 32)
+    W = max(min_w, (w + 31) // 32 * 32)
+    canvas = Image.new("L", (W, H), 255)
+    canvas.paste(img, (0, 0))
+    x = torch.from_numpy(np.asarray(canvas, dtype=np.float32) / 255.0)
+    return ((x - config.get("mean", 0.5)) / config.get("std", 0.5))[None]
+
+
+def read_rows(args, config):
+    if args.synthetic:
+        imgs = synth.make_images(args.synthetic, 64, 256, seed=int(config.get("manualSeed", 1111)))
+        return [(f"synthetic_{i}", None, imgs[i]) for i in range(args.synthetic)]
+    rows = []
+    with open(args.csv_dir, newline="") as f:
+        for i, r in enumerate(csv.DictReader(f, delimiter=DELIMITER)):
+            if i < args.start_idx:
+                continue
+            label = r.get("label", "")
+            toks = str(label).strip().split() if config.get("token_level", "word") == "word" else list(str(label))
+            rows.append((r["id"], toks, None))
+    return rows
+
+
+def run_infer(model, rows, converter, config, args):
+    is_attn = "Attn" in config["Prediction"]["name"]
+    max_len = config["batch_max_length"]
+    device = config["device"]
+    buckets = defaultdict(list)
+    pre_t = 0.0
+    for name, label, tensor in rows:
+        if config.get("data_filtering", True) and label is not None and len(label) > max_len:
+            continue
+        t0 = time.time()
+        x = tensor if tensor is not None else load_image(os.path.join(config["eval_data"], name), config)
+        pre_t += time.time() - t0
+        buckets[tuple(x.shape[-2:])].append((name, label, x))
+    n = n_correct = 0
+    norm_ed = word_ed = 0.0
+    infer_time = post_time = 0.0
+    writer = fo = None
+    if config.get("export_csv"):
+        os.makedirs(os.path.dirname(args.export_path) or ".", exist_ok=True)
+        fo = open(args.export_path, "wt" if args.start_idx == 0 else "at", newline="")
+        writer = csv.writer(fo)
+    for (H, W), items in buckets.items():
+        for lo in range(0, len(items), config["batch_size"]):
+            chunk = items[lo: lo + config["batch_size"]]
+            image = torch.stack([c[2] for c in chunk]).to(device)
+            B = image.size(0)
+            text = torch.zeros(B, max_len + 1, dtype=torch.long, device=device) if is_attn \
+                else torch.full((B, 1), 1, dtype=torch.long, device=device)
+            torch.cuda.synchronize()
+            t0 = time.time()
+            preds_index, _, _ = model(image, text, is_train=False, is_test=True)
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+            infer_time += dt
+            t0 = time.time()
+            if isinstance(preds_index, torch.Tensor) and preds_index.dim() == 2:
+                pred_tokens = converter.detokenize(preds_index.cpu())
+            else:
+                pred_tokens = converter.detokenize(torch.as_tensor(preds_index).reshape(B, -1))
+            post_time += time.time() - t0
+            for (name, label, _), pred in zip(chunk, pred_tokens):
+                n += 1
+                if label is None:
+                    if writer:
+                        writer.writerow([name, " ".join(pred), "", "", dt / B])
+                    continue
+                ed = edit_distance(pred, label)
+                n_correct += int(pred == label)
+                word_ed += 1.0 - ed / max(len(pred), len(label), 1)
+                ps, ls = " ".join(pred), " ".join(label)
+                norm_ed += 1.0 - edit_distance(ps, ls) / max(len(ps), len(ls), 1) if len(ps) + len(ls) < 2000 else 0.0
+                if writer:
+                    writer.writerow([name, ps, ls, int(pred == label), dt / B])
+    if fo:
+        fo.close()
+    n = max(n, 1)
+    mem = torch.cuda.max_memory_allocated() / 2 ** 20
+    return n_correct / n * 100, norm_ed / n, word_ed / n, mem, infer_time, post_time, pre_t, n
+
+
+def infer(config, args):
+    if args.synthetic and not config.get("vocab"):
+        config["character"] = synth.make_vocab()
+    converter = builder.create_converter(config, config["device"])
+    config["num_class"] = len(converter.character)
+    model = Model(config)
+    if config.get("saved_model") and os.path.exists(config["saved_model"]):
+        ckpt = torch.load(config["saved_model"], map_location="cpu")
+        model.load_state_dict(ckpt.get("model", ckpt), strict=True)
+    elif not args.synthetic:
+        raise FileNotFoundError(f"saved_model {config.get('saved_model')!r} not found")
+    model = model.to(config["device"]).eval()
+    params_num = sum(int(np.prod(p.size())) for p in model.parameters())
+    rows = read_rows(args, config)
+    with torch.no_grad():
+        acc, norm_ED, word_ED, mem, infer_time, post_time, pre_time, n = run_infer(model, rows, converter, config, args)
+    lines_print = [
+        f"Acc: {acc:0.3f}", f"Norm Edit Distance: {norm_ED:0.5f}", f"Symbol Match (Word Edit Distance): {word_ED:0.5f}",
+        f"Infer time {infer_time} s", f"Avg infer time {infer_time / float(n)} s", f"Preprocess time: {pre_time} s",
+        f"Avg pre time: {pre_time / float(n)}", f"Postprocess time: {post_time} s", f"Avg post time {post_time / float(n)} s",
+        f"Memory used: {mem} MB\n"]
+    print("\n".join(lines_print))
+    if not args.console:
+        os.makedirs(os.path.dirname(args.log_path) or ".", exist_ok=True)
+        with open(args.log_path, "w") as log:
+            log.write(f"Trainable params num: {params_num}\n")
+            log.write(f"Acc: {acc:0.3f}\n")
+            log.write(f"Norm Edit Distance: {norm_ED:0.5f}\n")
+            log.write(f"Symbol Match (Word Edit Distance): {word_ED:0.5f}\n")
+            log.write(f"Total Infer Time: {infer_time} s\n")
+            log.write(f"Avg Infer Time: {infer_time / float(n)} s\n")
+            log.write(f"Postprocess time: {post_time} s\n")
+            log.write(f"Avg post time {post_time / float(n)} s\n")
+            log.write(f"Memory used: {mem} MB\n")
+    return acc, n
+
+
+def main(argv=None):
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--config", required=True, help="Path to config yaml file")
+    parser.add_argument("--csv_dir", default="", help="Path to csv file (tab separated: id, label)")
+    parser.add_argument("--start_idx", type=int, default=0, help="Index to start from csv file")
+    parser.add_argument("--data_dir", default="", help="Path to image folder to infer")
+    parser.add_argument("--amp", type=bool, default=False)
+    parser.add_argument("--resizer", action="store_true", default=False)
+    parser.add_argument("--log_path", required=True, help="Path to save evaluation result")
+    parser.add_argument("--batch_size", required=True, type=int, help="test on batch or with single sample")
+    parser.add_argument("--num_workers", type=int, default=-1, help="number of workers")
+    parser.add_argument("--strong_log", action="store_true", default=False)
+    parser.add_argument("--console", default=False)
+    parser.add_argument("--synthetic", type=int, default=0, help="run N seeded synthetic 64x256 images instead of a dataset")
+    parser.add_argument("--precision", default=None, choices=[None, "fp32", "tf32x3", "bf16x3", "bf16"])
+    args = parser.parse_args(argv)
+    if not args.synthetic and not (args.csv_dir and args.data_dir):
+        parser.error("--csv_dir and --data_dir are required unless --synthetic N is given")
+    config = yaml.load(open(args.config), Loader=yaml.FullLoader)
+    config["batch_size"] = args.batch_size
+    config["workers"] = args.num_workers
+    config["use_amp"] = bool(args.amp)
+    config["use_resizer"] = args.resizer
+    config["eval_data"] = args.data_dir
+    if args.precision or args.amp:
+        config.setdefault("engine", {})["precision"] = args.precision or "bf16"   # --amp maps to the bf16 mode
+    seed = int(config.get("manualSeed", 1111) or 1111)
+    random.seed(seed); np.random.seed(seed); torch.manual_seed(seed)
+    if not torch.cuda.is_available():
+        raise RuntimeError("doc2tex_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    config["num_gpu"] = torch.cuda.device_count()
+    config["device"] = "cuda"
+    args.export_path = os.path.splitext(args.log_path)[0] + ".csv"
+    return infer(config, args)
+
+
+if __name__ == "__main__":
+    main()

@@ -32,6 +32,11 @@ struct ConvGemm {
   const void* a_map_hi;    // optional host pointers to CUtensorMap of pre-split A planes [M, K] (TMA-fed A operand)
   const void* a_map_lo;
   long long* dbg;          // optional: CTA 0 writes phase timestamps (globaltimer ns) for latency debugging
+  // optional fused LayerNorm over the full output row (N == 256, TMA-fed-A tensor-core path only):
+  // out = LN(acc*scale + shift + res) * ln_w + ln_b   (post-norm decoder layers: norm(x + sublayer(x)))
+  const float* ln_w;
+  const float* ln_b;
+  float ln_eps;
 };
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start
@@ -46,15 +51,32 @@ inline bool& pdl_enabled() {
   return on;
 }
 
+inline int& launch_cluster_x() {   // thread-block cluster width of the next launch_kernel call (1 = none)
+  static thread_local int c = 1;
+  return c;
+}
+
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  if (launch_cluster_x() > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = launch_cluster_x();
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+    launch_cluster_x() = 1;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = n;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 

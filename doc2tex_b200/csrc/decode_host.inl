@@ -46,6 +46,21 @@ int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long 
 
 // One decoder step for R rows (tfm.py:125-135 / 152-169 with a KV cache):
 // nn.TransformerDecoderLayer defaults = post-norm, ReLU, eps 1e-5.
+// x = LayerNorm(g) with g = sublayer GEMM + bias + residual (post-norm decoder layer).  On the tensor-core path the
+// LayerNorm is fused into the GEMM epilogue (4-CTA cluster per row block); the result replaces b.x in place — safe
+// because each CTA reads its residual tile (prefetched before the MMA wait) before any CTA of its cluster stores.
+// Otherwise: GEMM -> b.x2, then the stand-alone LayerNorm kernel.
+int linear_ln(d2t_engine* e, ConvGemm g, const TfmBuffers& b, const float* lw, const float* lb, int R, int D, cudaStream_t s) {
+  const bool tc = e->cfg.precision == D2T_PREC_BF16X3 || e->cfg.precision == D2T_PREC_BF16;
+  if (tc && b.planes && e->fuse_ln && tc_can_fuse_ln(g, e->active_sms) && e->tcw.count(g.w)) {
+    g.ln_w = lw; g.ln_b = lb; g.ln_eps = 1e-5f;
+    g.out = b.x; g.out_hi = b.x_hi; g.out_lo = b.x_lo;
+    return dec_linear(e, g, s);
+  }
+  if (int rc = dec_linear(e, g, s)) return rc;
+  return layernorm(e, b.x2, lw, lb, b.x, R, D, 1e-5f, s, b.x_hi, b.x_lo);
+}
+
 struct PdlScope {   // kernels enqueued inside the scope are chained with programmatic dependent launch
   bool prev;
   explicit PdlScope(bool on) : prev(pdl_enabled()) { pdl_enabled() = on; }
@@ -84,9 +99,8 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
     {
       ConvGemm g = linear_params(b.att, e->dev[p + "self_attn.out_proj.weight"], e->dev[p + "self_attn.out_proj.bias"], b.x2, R, D, D);
       g.res = b.x; g.ldr = D; from_att(g);
-      if ((rc = dec_linear(e, g, s))) return rc;
+      if ((rc = linear_ln(e, g, b, e->dev[p + "norm1.weight"], e->dev[p + "norm1.bias"], R, D, s))) return rc;
     }
-    if ((rc = layernorm(e, b.x2, e->dev[p + "norm1.weight"], e->dev[p + "norm1.bias"], b.x, R, D, 1e-5f, s, b.x_hi, b.x_lo))) return rc;
     // cross-attention over the encoder memory (K/V projected once per image, shared by its beams), norm2
     {
       ConvGemm g = linear_params(b.x, e->dev[p + "multihead_attn.in_proj_weight"], e->dev[p + "multihead_attn.in_proj_bias"], b.q, R, D, D);
@@ -98,9 +112,8 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
     {
       ConvGemm g = linear_params(b.att, e->dev[p + "multihead_attn.out_proj.weight"], e->dev[p + "multihead_attn.out_proj.bias"], b.x2, R, D, D);
       g.res = b.x; g.ldr = D; from_att(g);
-      if ((rc = dec_linear(e, g, s))) return rc;
+      if ((rc = linear_ln(e, g, b, e->dev[p + "norm2.weight"], e->dev[p + "norm2.bias"], R, D, s))) return rc;
     }
-    if ((rc = layernorm(e, b.x2, e->dev[p + "norm2.weight"], e->dev[p + "norm2.bias"], b.x, R, D, 1e-5f, s, b.x_hi, b.x_lo))) return rc;
     // feed-forward, norm3
     {
       ConvGemm g = linear_params(b.x, e->dev[p + "linear1.weight"], e->dev[p + "linear1.bias"], b.ffn, R, F, D);
@@ -111,9 +124,8 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
     {
       ConvGemm g = linear_params(b.ffn, e->dev[p + "linear2.weight"], e->dev[p + "linear2.bias"], b.x2, R, D, F);
       g.res = b.x; g.ldr = D; from_ffn(g);
-      if ((rc = dec_linear(e, g, s))) return rc;
+      if ((rc = linear_ln(e, g, b, e->dev[p + "norm3.weight"], e->dev[p + "norm3.bias"], R, D, s))) return rc;
     }
-    if ((rc = layernorm(e, b.x2, e->dev[p + "norm3.weight"], e->dev[p + "norm3.bias"], b.x, R, D, 1e-5f, s, b.x_hi, b.x_lo))) return rc;
   }
   {
     ConvGemm g = linear_params(b.x, e->dev[PRED + "proj.weight"], e->dev[PRED + "proj.bias"], b.logits, R, V, D);

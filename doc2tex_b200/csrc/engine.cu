@@ -97,6 +97,7 @@ struct d2t_engine {
   SlotPool enc_pool, dec_pool;
   bool keep_taps = false;
   bool use_pdl = true;   // D2T_PDL=0 disables programmatic dependent launch in the decode step
+  bool fuse_ln = true;   // D2T_FUSE_LN=0: stand-alone LayerNorm kernels instead of the cluster-fused epilogue
   std::map<std::string, Tap> taps;
 
   // decode graph cache
@@ -401,6 +402,7 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   e->num_sms = prop.multiProcessorCount;
   e->enc_sms = e->active_sms = e->num_sms;
   if (const char* v = getenv("D2T_PDL")) e->use_pdl = atoi(v) != 0;
+  if (const char* v = getenv("D2T_FUSE_LN")) e->fuse_ln = atoi(v) != 0;
   cudaSetDevice(device);
   if (cudaMallocHost(&e->h_counters, 4 * sizeof(int)) != cudaSuccess) {
     g_create_error = "cudaMallocHost failed";

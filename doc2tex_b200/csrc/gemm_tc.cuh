@@ -31,6 +31,21 @@ namespace d2t {
 // ------------------------------------------------------------------------------------------------
 namespace tc {
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// store two floats into the shared memory of CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ void st_cluster_f32x2(uint32_t local_smem_addr, uint32_t rank, float a, float b) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
+}
 __device__ __noinline__ float4 gelu_erf4(float4 v) {
   return make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
 }
@@ -152,13 +167,20 @@ struct TcCfg {
   static constexpr int A_BYTES = TC_BM * 128;       // per plane
   static constexpr int B_BYTES = BN * 128;          // per plane
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-  static constexpr int EPI_STAGE_BYTES = tc_epi_warps(A_TMA) * 32 * TC_EPI_PITCH * 4;   // accumulator transpose tiles
+  // accumulator transpose tiles of the epilogue.  The TMA-fed-A variant runs ONE tile per CTA (host guarantees
+  // grid == tiles), so by epilogue time every operand stage is free and the transpose tiles alias stage memory:
+  // that buys a 4th stage, i.e. all of a K=256 tile's operands in flight at once.
+  static constexpr int EPI_TILE_BYTES = tc_epi_warps(A_TMA) * 32 * TC_EPI_PITCH * 4;
+  static constexpr int EPI_STAGE_BYTES = A_TMA ? 0 : EPI_TILE_BYTES;
   static constexpr int SMEM_BUDGET = 225 * 1024 - EPI_STAGE_BYTES - 1280;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two (BN in {64,128,256})
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int LN_PART_BYTES = 8 * TC_BM * 2 * 4;   // [4 CTAs x 2 epilogue slots][128 rows][sum, sumsq]
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
+                                       (A_TMA ? LN_PART_BYTES : 0);
   static_assert(STAGES >= 2, "need at least a double buffer");
+  static_assert(!A_TMA || STAGES * STAGE_BYTES >= EPI_TILE_BYTES, "epilogue tiles must fit in the aliased stage memory");
 };
 
 struct TcWeight {
@@ -172,7 +194,9 @@ struct TcWeight {
 // A_TMA: the A operand planes already exist in HBM as bf16 [M, K] matrices (written by the producing kernel's
 // epilogue) and are fetched by TMA like the weights; the gather/convert warps then have nothing to do.  This is the
 // low-latency path for the small decode-step GEMMs: every k-block of a tile is in flight at once.
-template <bool TF32, int PASSES, int BN, bool A_TMA>
+// LN_FUSE (TMA-fed-A, BN = 64, N = 256 only): the four n-tile CTAs of one m-tile form a thread-block cluster, exchange
+// per-row partial sums through distributed shared memory and apply the post-norm LayerNorm in the epilogue.
+template <bool TF32, int PASSES, int BN, bool A_TMA, bool LN_FUSE = false>
 __global__ void __launch_bounds__(tc_threads(A_TMA), 1)
 conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi,
                     const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_a_hi,
@@ -194,6 +218,8 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + TC_EPI_STAGE_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t ln_part = bars + 256;                                              // LN_FUSE: [8][128][2] floats
+  float* const ln_part_gen = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + TC_EPI_STAGE_BYTES + 256);
   pdl_trigger();   // let the next kernel's prologue overlap this one (PDL launches only)
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
   if (dbg && threadIdx.x == 0) p.dbg[0] = tc::gtime();
@@ -236,7 +262,7 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
     // instruction-latency bound (one warp per scheduler), not bandwidth bound.
     const int quad = warp & 3, slot = warp >> 2;
     constexpr int NSLOT = TC_EPI_WARPS / 4;
-    float* const stg = reinterpret_cast<float*>(smem_gen + (size_t)STAGES * Cfg::STAGE_BYTES) + warp * (32 * TC_EPI_PITCH);
+    float* const stg = reinterpret_cast<float*>(smem_gen + (A_TMA ? (size_t)0 : (size_t)STAGES * Cfg::STAGE_BYTES)) + warp * (32 * TC_EPI_PITCH);
     const int sub_r = lane >> 3, c4 = (lane & 7) * 4;
     const int M = p.M, N = p.N, ldc = p.ldc, ldr = p.ldr, ldc2 = p.ldc2, n_split = p.n_split, act = p.act & 15;
     const float* const scale = p.scale;
@@ -315,6 +341,45 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
           } else if (act == ACT_GELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = tc::gelu_erf4(v[i]);   // out-of-line: keeps the unrolled epilogue small
+          }
+          if constexpr (LN_FUSE) {
+            // row statistics over this warp's 32 columns -> all four CTAs of the cluster (distributed shared memory)
+            const uint32_t my_rank = tc::cluster_ctarank();
+            const float4 lw = __ldg(reinterpret_cast<const float4*>(p.ln_w + n));
+            const float4 lb = __ldg(reinterpret_cast<const float4*>(p.ln_b + n));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float s1 = (v[i].x + v[i].y) + (v[i].z + v[i].w);
+              float s2 = (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+#pragma unroll
+              for (int o = 1; o < 8; o <<= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+              }
+              if ((lane & 7) == 0) {
+                const int row = quad * 32 + sub_r + 4 * i;
+                const uint32_t a = ln_part + (uint32_t)(((my_rank * 2 + slot) * TC_BM + row) * 8);
+#pragma unroll
+                for (uint32_t rk = 0; rk < 4; ++rk) tc::st_cluster_f32x2(a, rk, s1, s2);
+              }
+            }
+            tc::cluster_sync_all();   // every thread of the four CTAs (the TMA / MMA warps arrive after their loops)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = quad * 32 + sub_r + 4 * i;
+              const float2 pr = *reinterpret_cast<const float2*>(ln_part_gen + ((lane & 7) * TC_BM + row) * 2);
+              float s1 = pr.x, s2 = pr.y;
+#pragma unroll
+              for (int o = 1; o < 8; o <<= 1) {
+                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+              }
+              const float mean = s1 * (1.0f / 256.0f);
+              const float var = fmaxf(s2 * (1.0f / 256.0f) - mean * mean, 0.f);
+              const float rstd = 1.0f / sqrtf(var + p.ln_eps);
+              v[i].x = (v[i].x - mean) * rstd * lw.x + lb.x; v[i].y = (v[i].y - mean) * rstd * lw.y + lb.y;
+              v[i].z = (v[i].z - mean) * rstd * lw.z + lb.z; v[i].w = (v[i].w - mean) * rstd * lw.w + lb.w;
+            }
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i)
@@ -471,6 +536,7 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
       }
     }
     __syncwarp();
+    if constexpr (LN_FUSE) tc::cluster_sync_all();
   } else {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
@@ -507,6 +573,7 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
       }
     }
     __syncwarp();
+    if constexpr (LN_FUSE) tc::cluster_sync_all();
   }
   tc::tcgen05_before_sync();
   __syncthreads();
@@ -620,11 +687,11 @@ inline cudaError_t tc_make_act_map(const void* plane, int M, int K, CUtensorMap*
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <bool TF32, int PASSES, int BN, bool A_TMA>
+template <bool TF32, int PASSES, int BN, bool A_TMA, bool LN_FUSE = false>
 inline cudaError_t tc_launch_one(const ConvGemm& p, const TcWeight& w, cudaStream_t s, int num_sms) {
   using Cfg = TcCfg<TF32, PASSES, BN, A_TMA>;
   static bool attr_set = false;
-  auto kern = conv_gemm_tc_kernel<TF32, PASSES, BN, A_TMA>;
+  auto kern = conv_gemm_tc_kernel<TF32, PASSES, BN, A_TMA, LN_FUSE>;
   if (!attr_set) {
     cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (st != cudaSuccess) return st;
@@ -635,20 +702,29 @@ inline cudaError_t tc_launch_one(const ConvGemm& p, const TcWeight& w, cudaStrea
   constexpr int mi = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
   const CUtensorMap* ah = A_TMA ? reinterpret_cast<const CUtensorMap*>(p.a_map_hi) : &w.map_hi[mi];
   const CUtensorMap* al = (A_TMA && p.a_map_lo) ? reinterpret_cast<const CUtensorMap*>(p.a_map_lo) : ah;
+  if (LN_FUSE) launch_cluster_x() = 4;   // the four 64-column tiles of a 256-wide row block form one cluster
   return launch_kernel(kern, dim3(grid), dim3(tc_threads(A_TMA)), Cfg::SMEM_BYTES, s, p, w.map_hi[mi], w.map_lo[mi], *ah, *al,
                        tiles_m, tiles_n);
+}
+
+// Fused residual + LayerNorm epilogue: 256-wide rows, TMA-fed A planes, one 4-CTA cluster per 128-row block.
+inline bool tc_can_fuse_ln(const ConvGemm& p, int num_sms) {
+  return p.N == 256 && p.a_map_hi != nullptr && p.out2 == nullptr && p.act == ACT_NONE && p.KH == 1 && p.KW == 1 &&
+         ((p.M + TC_BM - 1) / TC_BM) * 4 <= num_sms;
 }
 
 template <bool TF32, int PASSES>
 inline cudaError_t tc_launch_bn(const ConvGemm& p, const TcWeight& w, cudaStream_t s, int num_sms) {
   if constexpr (!TF32) {
-    // pre-split A planes + plain [M,K] operand -> TMA-fed A (decode-step GEMMs)
+    // pre-split A planes + plain [M,K] operand -> TMA-fed A (decode-step GEMMs), one tile per CTA
     if (p.a_map_hi != nullptr && p.KH == 1 && p.KW == 1 && p.H == 1 && p.W == 1 && (PASSES == 1 || p.a_map_lo != nullptr)) {
-      switch (tc_pick_bn(p.M, p.N, num_sms)) {   // (a 256-wide 3-pass stage would not leave room for 2 stages here)
-        case 256:
-        case 128: return tc_launch_one<false, PASSES, 128, true>(p, w, s, num_sms);
-        case 64: return tc_launch_one<false, PASSES, 64, true>(p, w, s, num_sms);
+      const int tiles_m = (p.M + TC_BM - 1) / TC_BM;
+      if (p.ln_w != nullptr) {
+        if (!tc_can_fuse_ln(p, num_sms)) return cudaErrorInvalidValue;
+        return tc_launch_one<false, PASSES, 64, true, true>(p, w, s, num_sms);
       }
+      if (tiles_m * ((p.N + 63) / 64) <= num_sms) return tc_launch_one<false, PASSES, 64, true>(p, w, s, num_sms);
+      if (tiles_m * ((p.N + 127) / 128) <= num_sms) return tc_launch_one<false, PASSES, 128, true>(p, w, s, num_sms);
     }
   }
   switch (tc_pick_bn(p.M, p.N, num_sms)) {

@@ -286,3 +286,20 @@ def test_error_paths(built_lib):
     with pytest.raises(EngineError):
         e.decode_beam(ctx, 32)
     e.close()
+
+
+def test_infer_cli_synthetic(built_lib, tmp_path):
+    """api/infer.py keeps the reference's flags and summary lines; --synthetic runs without a dataset."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    log = tmp_path / "run.log"
+    out = subprocess.run([sys.executable, os.path.join(root, "api", "infer.py"), "--config",
+                          os.path.join(root, "doc2tex_b200", "configs", "hybridvit_tfm.yaml"), "--log_path", str(log),
+                          "--batch_size", "4", "--synthetic", "6"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    for line in ("Acc:", "Norm Edit Distance:", "Infer time", "Avg infer time", "Memory used:"):
+        assert line in out.stdout
+    text = log.read_text()
+    assert "Trainable params num:" in text and "Total Infer Time:" in text
