@@ -23,8 +23,8 @@ __global__ void embed_tokens_kernel(const int* __restrict__ tokens, int tok_ld, 
                                     const float* __restrict__ emb, const float* __restrict__ pe, float* __restrict__ x,
                                     int R, int D, float mult, __nv_bfloat16* __restrict__ x_hi,
                                     __nv_bfloat16* __restrict__ x_lo) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // PDL: everything above overlapped the predecessor
+  pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
   const int t = *step;
   const int* tk = tokens + (parity_stride ? (long long)(t & 1) * parity_stride : 0);
   const int d4n = D / 4;
@@ -67,8 +67,8 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __res
                         const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
                         __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
   static_assert(HD == 32, "8 lanes x float4 per head slice");
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // PDL: everything above overlapped the predecessor
+  pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
   const int r = blockIdx.x;
   const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 3, c = (lane & 7) * 4;
@@ -152,8 +152,8 @@ __global__ void greedy_pick_kernel(const float* __restrict__ logits, int V, cons
                                    int* __restrict__ tokens, int tok_ld, long long* __restrict__ ids, int ids_ld,
                                    float* __restrict__ logits_out, int* __restrict__ ended, int* __restrict__ n_ended,
                                    int* __restrict__ done_step, int R, int end_id) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // PDL: everything above overlapped the predecessor
+  pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
   __shared__ float red_v[32];
   __shared__ int red_i[32];
   __shared__ float s_max, s_sum;
@@ -207,8 +207,8 @@ __global__ void greedy_pick_kernel(const float* __restrict__ logits, int V, cons
 }
 
 __global__ void advance_step_kernel(int* step) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // PDL: everything above overlapped the predecessor
+  pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
   *step += 1;
 }
 
@@ -216,8 +216,8 @@ __global__ void advance_step_kernel(int* step) {
 __global__ void init_decode_state_kernel(int* tokens, long long tokens_elems, int tok_ld, int R, int beam, int go_id,
                                          int* anc, int anc_ld, float* scores, int* n_live, int* n_done, int* finished,
                                          int* ended, int* counters /* step, n_ended, done_step, n_finished */) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // PDL: everything above overlapped the predecessor
+  pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
   const long long gtid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long gsz = (long long)gridDim.x * blockDim.x;
   for (long long i = gtid; i < tokens_elems; i += gsz) tokens[i] = 0;  // PAD
@@ -270,8 +270,8 @@ struct BeamState {
 
 __global__ void __launch_bounds__(256)
 beam_step_kernel(const float* __restrict__ logits, BeamState st) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // PDL: everything above overlapped the predecessor
+  pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
   extern __shared__ float s_cand[];  // [beam][V] candidate scores
   __shared__ float s_rowmax[BEAM_MAX], s_rowlse[BEAM_MAX];
   __shared__ float red_v[8];

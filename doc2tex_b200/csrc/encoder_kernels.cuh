@@ -107,8 +107,8 @@ template <int NV4>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                  float* __restrict__ y, int rows, float eps,
                                  __nv_bfloat16* __restrict__ y_hi = nullptr, __nv_bfloat16* __restrict__ y_lo = nullptr) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // PDL: everything above overlapped the predecessor
+  pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
   constexpr int D = 128 * NV4;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;

@@ -97,7 +97,8 @@ struct d2t_engine {
   SlotPool enc_pool, dec_pool;
   bool keep_taps = false;
   bool use_pdl = true;   // D2T_PDL=0 disables programmatic dependent launch in the decode step
-  bool fuse_ln = true;   // D2T_FUSE_LN=0: stand-alone LayerNorm kernels instead of the cluster-fused epilogue
+  bool fuse_ln = false;  // D2T_FUSE_LN=1: cluster-fused residual+LayerNorm epilogue (measured slower than the stand-alone
+                         // LayerNorm kernel on B200: cluster launch + DSMEM exchange cost more than the saved launch)
   std::map<std::string, Tap> taps;
 
   // decode graph cache

@@ -14,8 +14,8 @@ namespace d2t {
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 conv_gemm_simt_kernel(const ConvGemm p) {
-  pdl_trigger();
-  pdl_wait();
+  pdl_wait();      // PDL: everything above overlapped the predecessor
+  pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
   constexpr int BK = 16;
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int A_F4 = BM * BK / 4;

@@ -220,7 +220,6 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t ln_part = bars + 256;                                              // LN_FUSE: [8][128][2] floats
   float* const ln_part_gen = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + TC_EPI_STAGE_BYTES + 256);
-  pdl_trigger();   // let the next kernel's prologue overlap this one (PDL launches only)
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
   if (dbg && threadIdx.x == 0) p.dbg[0] = tc::gtime();
   const int num_tiles = tiles_m * tiles_n;
@@ -251,6 +250,7 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
   tc::tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot_gen;
   pdl_wait();      // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the previous kernel
+  pdl_trigger();   // now let ONE successor pre-launch (pre-launched CTAs pin 200 KB of smem each while they wait)
   if (dbg && threadIdx.x == 0) p.dbg[1] = tc::gtime();
 
   if (warp < TC_EPI_WARPS) {

@@ -21,6 +21,7 @@ class PipelinedRecognizer:
         self.eng, self.mode, self.beam, self.max_steps = engine, mode, beam, max_steps
         self.is_test, self.return_logits = is_test, return_logits
         self.enc_stream = torch.cuda.Stream(device=engine.device)
+        self.timing = None   # set to [] to collect (encode_ms, decode_ms) per batch (CUDA events; adds two syncs per batch)
         if encoder_sms is not None:
             engine.set_option("encoder_sms", encoder_sms)
 
@@ -41,18 +42,29 @@ class PipelinedRecognizer:
             self.enc_stream.wait_stream(main)
             with torch.cuda.stream(self.enc_stream):
                 x = img.to(self.eng.device, non_blocking=True)
+                t0 = torch.cuda.Event(enable_timing=True) if self.timing is not None else None
+                if t0 is not None:
+                    t0.record(self.enc_stream)
                 ctx, _, _ = self.eng.encode(x)
-                done = torch.cuda.Event()
+                done = torch.cuda.Event(enable_timing=self.timing is not None)
                 done.record(self.enc_stream)
             ctx.record_stream(main)
             x.record_stream(self.enc_stream)
             if pending is not None:
                 yield self._finish(pending, main)
-            pending = (ctx, done)
+            pending = (ctx, done, t0)
         if pending is not None:
             yield self._finish(pending, main)
 
     def _finish(self, pending, main):
-        ctx, done = pending
+        ctx, done, t0 = pending
         main.wait_event(done)          # decode(i) starts when encode(i) is done; encode(i+1) is already enqueued
-        return self._decode(ctx)
+        if self.timing is None:
+            return self._decode(ctx)
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(main)
+        out = self._decode(ctx)
+        d1.record(main)
+        d1.synchronize()
+        self.timing.append((t0.elapsed_time(done), d0.elapsed_time(d1)))
+        return out
