@@ -136,7 +136,7 @@ def run_reference(args):
         "impl": "reference", "metric": "formulas/sec", "value": value, "unit": "formulas/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args, n),
+        "config": dict(workload_config(args, args.batch), schedule="reference algorithm on host CPU cores (bounded sample)"),
         "cpu_baseline": {"value": value, "unit": "formulas/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "formulas/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -316,6 +316,19 @@ def run_engine(args):
 
 if __name__ == "__main__":
     a = parse()
+    # stdout carries exactly ONE JSON line: anything libraries print there (e.g. "NCCL version ...") goes to stderr
+    _real_stdout = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    _print = print
+
+    def print(*args, **kw):  # noqa: A001  (the two JSON prints below)
+        if kw.get("file") is None:
+            sys.stdout.flush()
+            os.write(_real_stdout, (" ".join(str(x) for x in args) + "\n").encode())
+        else:
+            _print(*args, **kw)
+
     if a.impl == "reference":
         run_reference(a)
     else:
