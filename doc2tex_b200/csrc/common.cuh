@@ -37,6 +37,9 @@ struct ConvGemm {
   const float* ln_w;
   const float* ln_b;
   float ln_eps;
+  // optional bf16 hi/lo NHWC planes of the INPUT activation (cp.async-fed A operand of conv_gemm_tc3_kernel)
+  const __nv_bfloat16* x_hi;
+  const __nv_bfloat16* x_lo;
 };
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start

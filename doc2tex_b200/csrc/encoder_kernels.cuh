@@ -5,12 +5,29 @@
 
 namespace d2t {
 
+// bf16 hi/lo planes of four consecutive fp32 values (A operand of the next tensor-core convolution)
+__device__ __forceinline__ void store_planes4(float4 v, __nv_bfloat16* hi, __nv_bfloat16* lo, size_t off) {
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  uint32_t hw[2], lw[2];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * u]), h1 = __float2bfloat16_rn(f[2 * u + 1]);
+    hw[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * u] - __bfloat162float(h0));
+    const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * u + 1] - __bfloat162float(h1));
+    lw[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+  }
+  *reinterpret_cast<uint2*>(hi + off) = make_uint2(hw[0], hw[1]);
+  if (lo) *reinterpret_cast<uint2*>(lo + off) = make_uint2(lw[0], lw[1]);
+}
+
 // conv0_1: Conv2d(1 -> Cout, 3x3, s1, p1, bias=False) + BN(eval) + ReLU  (resnet.py:206-208).
 // K = 9 is not tensor-core work: direct conv, output-bandwidth bound.  x: [B,H,W] (NCHW with C=1),
 // out: NHWC [B,H,W,Cout].  One thread = one pixel x 4 output channels (float4 store, coalesced).
 __global__ void conv0_direct_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cout][9]*/,
                                     const float* __restrict__ scale, const float* __restrict__ shift,
-                                    float* __restrict__ out, int B, int H, int W, int Cout) {
+                                    float* __restrict__ out, int B, int H, int W, int Cout,
+                                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
   extern __shared__ float sm[];  // [9][Cout] weights, [Cout] scale, [Cout] shift
   float* sw = sm;
   float* ssc = sm + 9 * Cout;
@@ -49,13 +66,15 @@ __global__ void conv0_direct_kernel(const float* __restrict__ x, const float* __
     o.z = fmaxf(a2 * ssc[c4 + 2] + ssh[c4 + 2], 0.f);
     o.w = fmaxf(a3 * ssc[c4 + 3] + ssh[c4 + 3], 0.f);
     *reinterpret_cast<float4*>(out + pix * Cout + c4) = o;
+    if (out_hi) store_planes4(o, out_hi, out_lo, (size_t)(pix * Cout + c4));
   }
 }
 
 // MaxPool2d(kernel 2x2, stride (SH,SW), padding (PH,PW)) on NHWC; padding behaves as -inf
 // (resnet.py:97,107,120: maxpool3 is k2 s(2,1) p(0,1)).
 __global__ void maxpool2x2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W,
-                                       int C, int OH, int OW, int SH, int SW, int PH, int PW) {
+                                       int C, int OH, int OW, int SH, int SW, int PH, int PW,
+                                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
   const int c4n = C / 4;
   const long long total = (long long)B * OH * OW * c4n;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
@@ -79,6 +98,7 @@ __global__ void maxpool2x2_nhwc_kernel(const float* __restrict__ x, float* __res
       }
     }
     *reinterpret_cast<float4*>(out + pix * C + c4) = m;
+    if (out_hi) store_planes4(m, out_hi, out_lo, (size_t)(pix * C + c4));
   }
 }
 

@@ -24,6 +24,8 @@
 #include "gemm_simt.cuh"
 #include "lstm_kernels.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
+#include "gemm_tc3.cuh"
 
 using namespace d2t;
 
@@ -43,8 +45,10 @@ struct ConvW {
   int cout = 0, cin = 0, kh = 0, kw = 0;
 };
 
-struct Fmap {  // NHWC activation
+struct Fmap {  // NHWC activation (+ optional bf16 hi/lo planes for the cp.async-fed tensor-core convolutions)
   float* p = nullptr;
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
   int B = 0, H = 0, W = 0, C = 0;
   size_t numel() const { return (size_t)B * H * W * C; }
 };
@@ -93,10 +97,13 @@ struct d2t_engine {
   std::map<std::string, ConvW> conv;
   std::map<std::string, float*> dev;  // linear weights, biases, LN params, embeddings (by reference key)
   std::map<const float*, TcWeight> tcw;  // tensor-core operand planes + TMA maps, keyed by the fp32 weight matrix
+  std::map<const float*, Tc3Maps> tc3;   // 64-byte-row weight maps of the cp.async-fed stem-convolution kernel
 
   SlotPool enc_pool, dec_pool;
   bool keep_taps = false;
   bool use_pdl = true;   // D2T_PDL=0 disables programmatic dependent launch in the decode step
+  bool use_tc3 = true;   // D2T_TC3=0 / option "tc3": stem convolutions fed from bf16 activation planes by cp.async
+  bool use_tc2 = false;  // D2T_TC2=1 / option "tc2": CTA-pair (cta_group::2) kernel for the large stem convolutions
   bool fuse_ln = false;  // D2T_FUSE_LN=1: cluster-fused residual+LayerNorm epilogue (measured slower than the stand-alone
                          // LayerNorm kernel on B200: cluster launch + DSMEM exchange cost more than the saved launch)
   std::map<std::string, Tap> taps;
@@ -239,6 +246,21 @@ int run_contraction(d2t_engine* e, const ConvGemm& p, const TcWeight* tcw, int p
     if (it != e->tcw.end()) tcw = &it->second;
   }
   if (precision != D2T_PREC_FP32 && tcw != nullptr && tcw->ready && tcw->N == p.N && tcw->K == p.K && tc_supported(p)) {
+    if (e->use_tc3 && tc3_supported(p, precision)) {
+      auto m3 = e->tc3.find(p.w);
+      if (m3 != e->tc3.end() && m3->second.ready) {
+        cudaError_t st3 = launch_conv_gemm_tc3(p, m3->second, precision, s, e->active_sms);
+        if (st3 != cudaSuccess) return e->fail(D2T_ERR_CUDA, "cp.async-fed contraction launch failed: %s", cudaGetErrorString(st3));
+        e->launches += 1;
+        return 0;
+      }
+    }
+    if (e->use_tc2 && tc2_supported(p, *tcw, precision, e->active_sms)) {
+      cudaError_t st2 = launch_conv_gemm_tc2(p, *tcw, precision, s, e->active_sms);
+      if (st2 != cudaSuccess) return e->fail(D2T_ERR_CUDA, "cta_group::2 contraction launch failed: %s", cudaGetErrorString(st2));
+      e->launches += 1;
+      return 0;
+    }
     cudaError_t st = launch_conv_gemm_tc(p, *tcw, precision, s, e->active_sms);
     if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tcgen05 contraction launch failed: %s", cudaGetErrorString(st));
     e->launches += 1;
@@ -259,17 +281,31 @@ ConvGemm linear_params(const float* x, const float* w, const float* bias, float*
   return p;
 }
 
-int alloc_act(d2t_engine* e, SlotPool& pool, Fmap* a, int B, int H, int W, int C) {
+int alloc_act(d2t_engine* e, SlotPool& pool, Fmap* a, int B, int H, int W, int C, bool planes = false) {
   cudaError_t st = cudaSuccess;
   a->B = B; a->H = H; a->W = W; a->C = C;
+  a->hi = a->lo = nullptr;
   a->p = (float*)pool.get(a->numel() * sizeof(float), &st);
   if (!a->p) return e->fail(D2T_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", a->numel() * 4, cudaGetErrorString(st));
+  if (planes) {
+    a->hi = (__nv_bfloat16*)pool.get(a->numel() * 2, &st);
+    if (a->hi && e->cfg.precision == D2T_PREC_BF16X3) a->lo = (__nv_bfloat16*)pool.get(a->numel() * 2, &st);
+    if (!a->hi || (e->cfg.precision == D2T_PREC_BF16X3 && !a->lo))
+      return e->fail(D2T_ERR_CUDA, "cudaMalloc of activation planes failed: %s", cudaGetErrorString(st));
+  }
   return 0;
 }
 
 void free_act(d2t_engine* e, SlotPool& pool, Fmap& a) {
   if (!e->keep_taps && a.p) pool.release(a.p);
-  a.p = nullptr;
+  if (a.hi) pool.release(a.hi);
+  if (a.lo) pool.release(a.lo);
+  a.p = nullptr; a.hi = a.lo = nullptr;
+}
+
+// the stem convolutions read their input from bf16 planes when the cp.async-fed kernel is on
+inline bool stem_planes(const d2t_engine* e) {
+  return e->use_tc3 && (e->cfg.precision == D2T_PREC_BF16X3 || e->cfg.precision == D2T_PREC_BF16);
 }
 
 int conv_layer(d2t_engine* e, const std::string& name, const Fmap& x, Fmap* y, int sh, int sw, int ph, int pw,
@@ -279,9 +315,10 @@ int conv_layer(d2t_engine* e, const std::string& name, const Fmap& x, Fmap* y, i
   const ConvW& c = it->second;
   const int OH = oh_override > 0 ? oh_override : (x.H + 2 * ph - c.kh) / sh + 1;
   const int OW = ow_override > 0 ? ow_override : (x.W + 2 * pw - c.kw) / sw + 1;
-  if (int rc = alloc_act(e, e->enc_pool, y, x.B, OH, OW, c.cout)) return rc;
+  if (int rc = alloc_act(e, e->enc_pool, y, x.B, OH, OW, c.cout, stem_planes(e) && name != "patch_embed.proj")) return rc;
   ConvGemm p{};
-  p.x = x.p; p.w = c.w; p.scale = c.scale; p.shift = c.shift; p.res = res ? res->p : nullptr;
+  p.x = x.p; p.x_hi = x.hi; p.x_lo = x.lo; p.out_hi = y->hi; p.out_lo = y->lo;
+  p.w = c.w; p.scale = c.scale; p.shift = c.shift; p.res = res ? res->p : nullptr;
   p.out = y->p; p.out2 = nullptr; p.dyn = nullptr; p.dyn_mul2 = 0;
   p.ldc = c.cout; p.ldc2 = 0; p.ldr = c.cout; p.n_split = c.cout;
   p.B = x.B; p.H = x.H; p.W = x.W; p.C = x.C; p.KH = c.kh; p.KW = c.kw; p.SH = sh; p.SW = sw; p.PH = ph; p.PW = pw;
@@ -291,9 +328,10 @@ int conv_layer(d2t_engine* e, const std::string& name, const Fmap& x, Fmap* y, i
 
 int pool_layer(d2t_engine* e, const Fmap& x, Fmap* y, int sh, int sw, int ph, int pw, cudaStream_t s) {
   const int OH = (x.H + 2 * ph - 2) / sh + 1, OW = (x.W + 2 * pw - 2) / sw + 1;
-  if (int rc = alloc_act(e, e->enc_pool, y, x.B, OH, OW, x.C)) return rc;
+  if (int rc = alloc_act(e, e->enc_pool, y, x.B, OH, OW, x.C, stem_planes(e))) return rc;
   const long long total = (long long)y->numel() / 4;
-  maxpool2x2_nhwc_kernel<<<grid_for(total, 256, e->active_sms), 256, 0, s>>>(x.p, y->p, x.B, x.H, x.W, x.C, OH, OW, sh, sw, ph, pw);
+  maxpool2x2_nhwc_kernel<<<grid_for(total, 256, e->active_sms), 256, 0, s>>>(x.p, y->p, x.B, x.H, x.W, x.C, OH, OW, sh, sw, ph, pw,
+                                                                           y->hi, y->lo);
   e->launches += 1;
   CUDA_TRY(e, cudaGetLastError());
   return 0;
@@ -404,6 +442,8 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   e->enc_sms = e->active_sms = e->num_sms;
   if (const char* v = getenv("D2T_PDL")) e->use_pdl = atoi(v) != 0;
   if (const char* v = getenv("D2T_FUSE_LN")) e->fuse_ln = atoi(v) != 0;
+  if (const char* v = getenv("D2T_TC2")) e->use_tc2 = atoi(v) != 0;
+  if (const char* v = getenv("D2T_TC3")) e->use_tc3 = atoi(v) != 0;
   cudaSetDevice(device);
   if (cudaMallocHost(&e->h_counters, 4 * sizeof(int)) != cudaSuccess) {
     g_create_error = "cudaMallocHost failed";
@@ -465,7 +505,7 @@ int d2t_finalize_weights(d2t_engine* e) {
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaDeviceSynchronize());
   for (void* p : e->owned) cudaFree(p);
-  e->owned.clear(); e->conv.clear(); e->dev.clear(); e->tcw.clear();
+  e->owned.clear(); e->conv.clear(); e->dev.clear(); e->tcw.clear(); e->tc3.clear();
   for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   e->graphs.clear();
   const d2t_config& c = e->cfg;
@@ -603,6 +643,12 @@ int d2t_finalize_weights(d2t_engine* e) {
     for (auto& kv : e->conv) {
       if (kv.first == "conv0_1") continue;
       if ((rc = prep(kv.second.w, kv.second.cout, kv.second.kh * kv.second.kw * kv.second.cin))) return rc;
+      if (c.precision == D2T_PREC_BF16X3 || c.precision == D2T_PREC_BF16) {
+        Tc3Maps m3;
+        cudaError_t st = tc3_prepare_maps(e->tcw[kv.second.w], &m3);
+        if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tc3_prepare_maps(%s): %s", kv.first.c_str(), cudaGetErrorString(st));
+        e->tc3[kv.second.w] = m3;
+      }
     }
     for (int i = 0; i < c.depth; ++i) {
       const std::string p = SEQ + "blocks." + std::to_string(i) + ".";
@@ -651,6 +697,10 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
     e->enc_sms = value;
   } else if (k == "pdl") {
     e->use_pdl = value != 0;
+  } else if (k == "tc2") {
+    e->use_tc2 = value != 0;
+  } else if (k == "tc3") {
+    e->use_tc3 = value != 0;
   } else {
     return e->fail(D2T_ERR_INVALID, "unknown option '%s'", key);
   }
@@ -684,10 +734,10 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
   Fmap x, y;
   {
     const ConvW& c0 = e->conv["conv0_1"];
-    if ((rc = alloc_act(e, e->enc_pool, &x, B, H, W, c0.cout))) return rc;
+    if ((rc = alloc_act(e, e->enc_pool, &x, B, H, W, c0.cout, stem_planes(e)))) return rc;
     const long long total = (long long)B * H * W * (c0.cout / 4);
     const size_t smem = (size_t)11 * c0.cout * sizeof(float);
-    conv0_direct_kernel<<<grid_for(total, 256, e->active_sms), 256, smem, s>>>(img, c0.w, c0.scale, c0.shift, x.p, B, H, W, c0.cout);
+    conv0_direct_kernel<<<grid_for(total, 256, e->active_sms), 256, smem, s>>>(img, c0.w, c0.scale, c0.shift, x.p, B, H, W, c0.cout, x.hi, x.lo);
     e->launches += 1;
     CUDA_TRY(e, cudaGetLastError());
     tap(e, "conv0_1", x);

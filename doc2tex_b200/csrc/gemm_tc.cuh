@@ -420,7 +420,7 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
     constexpr int RPT = TC_ROWS_PER_THREAD;
     constexpr int LD4 = TF32 ? 1 : 2;                     // float4 loads per (row, chunk)
     int kit = 0;                                          // running k-block counter across tiles (ring position)
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = blockIdx.x; tile < num_tiles && !(p.act & 64); tile += gridDim.x) {
       const int tm = tile / tiles_n;
       const float* base[RPT];
       int ih0[RPT], iw0[RPT];
@@ -518,7 +518,7 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
     // =========================== W producer (TMA) ===========================
     if (lane == 0) {
       int kit = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < num_tiles && !(p.act & 64); tile += gridDim.x) {
         const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
           const int s = kit % STAGES;
@@ -549,7 +549,7 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
         const uint32_t d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
           const int s = kit % STAGES;
-          tc::mbar_wait(full_bar(s), (kit / STAGES) & 1);
+          if (!(p.act & 64)) tc::mbar_wait(full_bar(s), (kit / STAGES) & 1);
           tc::tcgen05_after_sync();
           if (dbg && kb == 0) p.dbg[2] = tc::gtime();
           if (dbg && kb == nkb - 1) p.dbg[3] = tc::gtime();

@@ -1,0 +1,348 @@
+// Stem-convolution variant of the tcgen05 implicit-GEMM contraction with an ASYNCHRONOUS A operand.
+//
+// conv_gemm_tc_kernel gathers fp32 activations through registers (LDG -> split -> STS), one k-block ahead; on the
+// large 3x3 convolutions that path, not the tensor pipe, sets the pace (measured: 1.67 us per k-block against a
+// 0.81 us MMA floor, 0.34 us in single-pass bf16).  Here the activations already exist in HBM as bf16 hi/lo NHWC
+// planes — written by the epilogue of the producing layer — and the eight producer warps only issue 16-byte
+// cp.async (LDGSTS, zero-fill at borders / tails) straight into the swizzled operand stage and arm the stage's
+// mbarrier with cp.async.mbarrier.arrive: no registers, no conversion, as many k-blocks in flight as there are
+// stages.  Stages are half as deep (64-byte rows, 64B swizzle, 32 bf16 per k-block) so that twice as many fit:
+// 4 x 48 KB for the 3-pass 256-wide tile.
+#pragma once
+#include "gemm_tc.cuh"
+
+namespace d2t {
+namespace tc {
+
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+// K-major operand tile with 64-byte rows and 64B swizzle: 8-row atoms of 512 B
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)4 << 61;   // SWIZZLE_64B
+  return d;
+}
+
+}  // namespace tc
+
+template <int PASSES, int BN>
+struct Tc3Cfg {
+  static constexpr int PLANES = PASSES == 1 ? 1 : 2;
+  static constexpr int KB_ELEMS = 32, CH_ELEMS = 8;        // 64-byte operand rows = 4 chunks of 16 B
+  static constexpr int A_BYTES = TC_BM * 64;
+  static constexpr int B_BYTES = BN * 64;
+  static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
+  static constexpr int EPI_STAGE_BYTES = 4 * 32 * TC_EPI_PITCH * 4;
+  static constexpr int STAGES_RAW = (225 * 1024 - EPI_STAGE_BYTES - 1280) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
+  static_assert(STAGES >= 2, "need at least a double buffer");
+};
+
+template <int PASSES, int BN>
+__global__ void __launch_bounds__(448, 1)
+conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi,
+                     const __grid_constant__ CUtensorMap map_lo, int tiles_m, int tiles_n) {
+  using Cfg = Tc3Cfg<PASSES, BN>;
+  constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES;
+  constexpr int EPI_WARPS = 4, TMA_WARP = 12, MMA_WARP = 13;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem_gen = smem_raw + (smem_base - tc::smem_u32(smem_raw));
+  const uint32_t bars = smem_base + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGE_BYTES;
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
+  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGE_BYTES + 8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = tiles_m * tiles_n;
+  const int nkb = (p.K + Cfg::KB_ELEMS - 1) / Cfg::KB_ELEMS;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      tc::mbar_init(full_bar(s), TC_PROD_THREADS + 1);   // 256 cp.async completion arrivals + the TMA thread's expect_tx
+      tc::mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      tc::mbar_init(tfull_bar(a), 1);
+      tc::mbar_init(tempty_bar(a), EPI_WARPS * 32);
+    }
+    tc::fence_barrier_init();
+  }
+  if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+  if (warp == TMA_WARP && lane == 0) {
+    tc::tma_prefetch_desc(&map_hi);
+    if (PLANES == 2) tc::tma_prefetch_desc(&map_lo);
+  }
+  tc::tcgen05_before_sync();
+  __syncthreads();
+  tc::tcgen05_after_sync();
+  const uint32_t tmem_base = *tmem_slot_gen;
+  pdl_wait();
+  pdl_trigger();
+
+  if (warp < EPI_WARPS) {
+    // =========================== epilogue ===========================
+    const int quad = warp & 3;
+    float* const stg = reinterpret_cast<float*>(smem_gen + (size_t)STAGES * Cfg::STAGE_BYTES) + warp * (32 * TC_EPI_PITCH);
+    const int sub_r = lane >> 3, c4 = (lane & 7) * 4;
+    const int M = p.M, N = p.N, ldc = p.ldc, ldr = p.ldr, act = p.act & 15;
+    const float* const scale = p.scale;
+    const float* const shift = p.shift;
+    const float* const res = p.res;
+    float* const out = p.out;
+    __nv_bfloat16* const out_hi = p.out_hi;
+    __nv_bfloat16* const out_lo = p.out_lo;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+      const int acc = it & 1;
+      tc::mbar_wait(tfull_bar(acc), (it >> 1) & 1);
+      tc::tcgen05_after_sync();
+      const int m_first = tm * TC_BM + quad * 32 + sub_r;
+#pragma unroll 1
+      for (int j = 0; j < BN / 32; ++j) {
+        uint32_t r[32];
+        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + j * 32), r);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          *reinterpret_cast<uint4*>(stg + lane * TC_EPI_PITCH + q * 4) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
+        __syncwarp();
+        const int n = tn * BN + j * 32 + c4;
+        if (n < N) {
+          float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + n));
+          if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + n));
+#pragma unroll 2
+          for (int i = 0; i < 8; ++i) {
+            const int m = m_first + 4 * i;
+            if (m < M) {
+              float4 v = *reinterpret_cast<const float4*>(stg + (sub_r + 4 * i) * TC_EPI_PITCH + c4);
+              v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+              if (res) {
+                const float4 rr = __ldg(reinterpret_cast<const float4*>(res + (size_t)m * ldr + n));
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+              }
+              if (act == ACT_RELU) {
+                v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+              } else if (act == ACT_GELU) {
+                v = tc::gelu_erf4(v);
+              }
+              const size_t o = (size_t)m * ldc + n;
+              *reinterpret_cast<float4*>(out + o) = v;
+              if (out_hi) {
+                const float f[4] = {v.x, v.y, v.z, v.w};
+                uint32_t hw[2], lw[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * u]), h1 = __float2bfloat16_rn(f[2 * u + 1]);
+                  hw[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                  const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * u] - __bfloat162float(h0));
+                  const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * u + 1] - __bfloat162float(h1));
+                  lw[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                }
+                *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(hw[0], hw[1]);
+                if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(lw[0], lw[1]);
+              }
+            }
+          }
+        }
+        __syncwarp();
+      }
+      tc::tcgen05_before_sync();
+      tc::mbar_arrive(tempty_bar(acc));
+    }
+  } else if (warp < TMA_WARP) {
+    // =========================== A producers: cp.async from the bf16 NHWC planes ===========================
+    // 128 rows x 4 chunks (16 B) per plane and k-block = 512 copies: 2 rows per thread.
+    const int pt = threadIdx.x - EPI_WARPS * 32;   // 0..255
+    const int chunk = pt & 3;                      // 16-byte chunk of the 64-byte operand row
+    const int rg = pt >> 2;                        // rows rg and rg + 64
+    const __nv_bfloat16* const xh = p.x_hi;
+    const __nv_bfloat16* const xl = p.x_lo;
+    int kit = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / tiles_n;
+      long long base[2];
+      int ih0[2], iw0[2];
+      bool ok[2];
+      uint32_t soff[2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int r = rg + 64 * i;
+        const int m = tm * TC_BM + r;
+        ok[i] = m < p.M;
+        const int mm = ok[i] ? m : 0;
+        const int ow = mm % p.OW;
+        const int t = mm / p.OW;
+        const int oh = t % p.OH;
+        const int b = t / p.OH;
+        ih0[i] = oh * p.SH - p.PH;
+        iw0[i] = ow * p.SW - p.PW;
+        base[i] = (long long)b * p.H * p.W * p.C;
+        soff[i] = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u + (uint32_t)((chunk ^ ((r >> 1) & 3)) << 4);
+      }
+      for (int kb = 0; kb < nkb; ++kb, ++kit) {
+        const int s = kit % STAGES;
+        const int k = kb * Cfg::KB_ELEMS + chunk * Cfg::CH_ELEMS;
+        const bool kok = k < p.K;
+        const int tap = kok ? k / p.C : 0;
+        const int ci = k - tap * p.C;
+        const int kh = tap / p.KW, kw = tap - kh * p.KW;
+        tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
+        const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int ih = ih0[i] + kh, iw = iw0[i] + kw;
+          const bool valid = kok && ok[i] && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
+          const long long e = valid ? base[i] + ((long long)ih * p.W + iw) * p.C + ci : 0;
+          tc::cp_async_16(a_hi + soff[i], xh + e, valid ? 16u : 0u);
+          if (PLANES == 2) tc::cp_async_16(a_hi + Cfg::A_BYTES + soff[i], xl + e, valid ? 16u : 0u);
+        }
+        tc::cp_async_mbar_arrive_noinc(full_bar(s));   // arrives when this thread's copies above have landed
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp == TMA_WARP) {
+    // =========================== W producer (TMA, 64-byte rows) ===========================
+    if (lane == 0) {
+      int kit = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+        for (int kb = 0; kb < nkb; ++kb, ++kit) {
+          const int s = kit % STAGES;
+          tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
+          tc::mbar_arrive_expect_tx(full_bar(s), PLANES * Cfg::B_BYTES);
+          const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES;
+          tc::tma_load_2d(b_hi, &map_hi, full_bar(s), kb * Cfg::KB_ELEMS, tn * BN);
+          if (PLANES == 2) tc::tma_load_2d(b_hi + Cfg::B_BYTES, &map_lo, full_bar(s), kb * Cfg::KB_ELEMS, tn * BN);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(1, BN);
+      int kit = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        tc::mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+        tc::tcgen05_after_sync();
+        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < nkb; ++kb, ++kit) {
+          const int s = kit % STAGES;
+          tc::mbar_wait(full_bar(s), (kit / STAGES) & 1);
+          tc::tcgen05_after_sync();
+          const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
+          const uint32_t b_hi = a_hi + PLANES * Cfg::A_BYTES;
+          const uint64_t da_hi = tc::make_smem_desc_sw64(a_hi), db_hi = tc::make_smem_desc_sw64(b_hi);
+          const uint64_t da_lo = tc::make_smem_desc_sw64(a_hi + Cfg::A_BYTES), db_lo = tc::make_smem_desc_sw64(b_hi + Cfg::B_BYTES);
+#pragma unroll
+          for (int k = 0; k < 2; ++k)   // 2 x 32 B = one 64-byte row
+            tc::umma<false>(d, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb | k) != 0);
+          if constexpr (PASSES == 3) {
+#pragma unroll
+            for (int k = 0; k < 2; ++k) tc::umma<false>(d, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+#pragma unroll
+            for (int k = 0; k < 2; ++k) tc::umma<false>(d, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+          }
+          tc::umma_commit(empty_bar(s));
+        }
+        tc::umma_commit(tfull_bar(acc));
+      }
+    }
+    __syncwarp();
+  }
+  tc::tcgen05_before_sync();
+  __syncthreads();
+  if (warp == MMA_WARP) {
+    tc::tcgen05_after_sync();
+    tc::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// host side ---------------------------------------------------------------------------------------------------------
+// Extra weight tensor maps with 64-byte boxes (32 bf16) and 64B swizzle, for 64 / 128 / 256 weight rows.
+struct Tc3Maps {
+  bool ready = false;
+  CUtensorMap hi[3], lo[3];
+};
+
+inline cudaError_t tc3_prepare_maps(const TcWeight& w, Tc3Maps* out) {
+  out->ready = false;
+  if (!w.ready || (w.precision != 2 && w.precision != 3)) return cudaSuccess;
+  PFN_encodeTiled enc = tc_encode_fn();
+  if (!enc) return cudaErrorNotSupported;
+  const cuuint64_t gdim[2] = {(cuuint64_t)w.K, (cuuint64_t)w.N};
+  const cuuint64_t gstr[1] = {(cuuint64_t)w.K * 2};
+  const cuuint32_t estr[2] = {1, 1};
+  for (int i = 0; i < 3; ++i) {
+    const cuuint32_t box[2] = {32, (cuuint32_t)(64 << i)};
+    CUresult r = enc(&out->hi[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.hi, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    out->lo[i] = out->hi[i];
+    if (w.lo) {
+      r = enc(&out->lo[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w.lo, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+    }
+  }
+  out->ready = true;
+  return cudaSuccess;
+}
+
+inline bool tc3_supported(const ConvGemm& p, int precision) {
+  if (precision != 2 && precision != 3) return false;
+  if (p.x_hi == nullptr || (precision == 2 && p.x_lo == nullptr)) return false;
+  return p.out2 == nullptr && p.a_map_hi == nullptr && p.ln_w == nullptr && p.C % 8 == 0 && p.K % 8 == 0 && p.ldc % 4 == 0 &&
+         (p.res == nullptr || p.ldr % 4 == 0) && p.N % 4 == 0;
+}
+
+template <int PASSES, int BN>
+inline cudaError_t tc3_launch_one(const ConvGemm& p, const Tc3Maps& m, cudaStream_t s, int num_sms) {
+  using Cfg = Tc3Cfg<PASSES, BN>;
+  static bool attr_set = false;
+  auto kern = conv_gemm_tc3_kernel<PASSES, BN>;
+  if (!attr_set) {
+    cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (st != cudaSuccess) return st;
+    attr_set = true;
+  }
+  const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = (p.N + BN - 1) / BN;
+  const int grid = tiles_m * tiles_n < num_sms ? tiles_m * tiles_n : num_sms;
+  constexpr int mi = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
+  return launch_kernel(kern, dim3(grid), dim3(448), Cfg::SMEM_BYTES, s, p, m.hi[mi], m.lo[mi], tiles_m, tiles_n);
+}
+
+inline cudaError_t launch_conv_gemm_tc3(const ConvGemm& p, const Tc3Maps& m, int precision, cudaStream_t s, int num_sms) {
+  const int bn = tc_pick_bn(p.M, p.N, num_sms);
+  if (precision == 2) {
+    switch (bn) {
+      case 256: return tc3_launch_one<3, 256>(p, m, s, num_sms);
+      case 128: return tc3_launch_one<3, 128>(p, m, s, num_sms);
+      default: return tc3_launch_one<3, 64>(p, m, s, num_sms);
+    }
+  }
+  switch (bn) {
+    case 256: return tc3_launch_one<1, 256>(p, m, s, num_sms);
+    case 128: return tc3_launch_one<1, 128>(p, m, s, num_sms);
+    default: return tc3_launch_one<1, 64>(p, m, s, num_sms);
+  }
+}
+
+}  // namespace d2t
