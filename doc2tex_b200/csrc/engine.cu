@@ -444,6 +444,7 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   if (const char* v = getenv("D2T_FUSE_LN")) e->fuse_ln = atoi(v) != 0;
   if (const char* v = getenv("D2T_TC2")) e->use_tc2 = atoi(v) != 0;
   if (const char* v = getenv("D2T_TC3")) e->use_tc3 = atoi(v) != 0;
+  if (const char* v = getenv("D2T_TC3_MT2")) tc3_two_mtiles() = atoi(v) != 0;
   cudaSetDevice(device);
   if (cudaMallocHost(&e->h_counters, 4 * sizeof(int)) != cudaSuccess) {
     g_create_error = "cudaMallocHost failed";

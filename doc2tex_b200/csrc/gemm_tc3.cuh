@@ -33,26 +33,32 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
 
 }  // namespace tc
 
-template <int PASSES, int BN>
+// MT = 128-row m-tiles per CTA.  MT = 2 keeps TWO accumulators (2 x 256 TMEM columns) and runs both against the same
+// weight stage, halving the weight bytes each SM has to pull from L2 per FLOP (the per-SM L2->SM fill rate, ~83 GB/s,
+// is what bounds these kernels); the price is a non-overlapped epilogue (no spare TMEM for double buffering).
+template <int PASSES, int BN, int MT = 1>
 struct Tc3Cfg {
   static constexpr int PLANES = PASSES == 1 ? 1 : 2;
   static constexpr int KB_ELEMS = 32, CH_ELEMS = 8;        // 64-byte operand rows = 4 chunks of 16 B
-  static constexpr int A_BYTES = TC_BM * 64;
+  static constexpr int A_HALF_BYTES = TC_BM * 64;          // one m-tile, one plane
+  static constexpr int A_BYTES = MT * A_HALF_BYTES;
   static constexpr int B_BYTES = BN * 64;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
   static constexpr int EPI_STAGE_BYTES = 4 * 32 * TC_EPI_PITCH * 4;
   static constexpr int STAGES_RAW = (225 * 1024 - EPI_STAGE_BYTES - 1280) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = 2 * BN;
+  static constexpr int TMEM_COLS = 2 * BN;                 // MT=1: two buffers of one tile; MT=2: one buffer of two tiles
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 + 256;
   static_assert(STAGES >= 2, "need at least a double buffer");
+  static_assert(MT == 1 || MT == 2, "MT");
 };
 
-template <int PASSES, int BN>
+template <int PASSES, int BN, int MT>
 __global__ void __launch_bounds__(448, 1)
 conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi,
                      const __grid_constant__ CUtensorMap map_lo, int tiles_m, int tiles_n) {
-  using Cfg = Tc3Cfg<PASSES, BN>;
+  using Cfg = Tc3Cfg<PASSES, BN, MT>;
+  constexpr int ROWS = MT * TC_BM;                          // output rows per CTA tile
   constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES;
   constexpr int EPI_WARPS = 4, TMA_WARP = 12, MMA_WARP = 13;
   extern __shared__ uint8_t smem_raw[];
@@ -108,14 +114,15 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
-      const int acc = it & 1;
-      tc::mbar_wait(tfull_bar(acc), (it >> 1) & 1);
+      const int acc = MT == 1 ? (it & 1) : 0;
+      tc::mbar_wait(tfull_bar(acc), MT == 1 ? ((it >> 1) & 1) : (it & 1));
       tc::tcgen05_after_sync();
-      const int m_first = tm * TC_BM + quad * 32 + sub_r;
 #pragma unroll 1
-      for (int j = 0; j < BN / 32; ++j) {
+      for (int hj = 0; hj < MT * (BN / 32); ++hj) {
+        const int h = hj / (BN / 32), j = hj - h * (BN / 32);   // m-tile of the CTA tile, 32-column chunk
+        const int m_first = tm * ROWS + h * TC_BM + quad * 32 + sub_r;
         uint32_t r[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + j * 32), r);
+        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)((MT == 1 ? acc : h) * BN + j * 32), r);
         tc::tmem_ld_wait();
 #pragma unroll
         for (int q = 0; q < 8; ++q)
@@ -167,23 +174,24 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
     }
   } else if (warp < TMA_WARP) {
     // =========================== A producers: cp.async from the bf16 NHWC planes ===========================
-    // 128 rows x 4 chunks (16 B) per plane and k-block = 512 copies: 2 rows per thread.
+    // ROWS rows x 4 chunks (16 B) per plane and k-block: 2 * MT rows per thread.
+    constexpr int RPT = 2 * MT;
     const int pt = threadIdx.x - EPI_WARPS * 32;   // 0..255
     const int chunk = pt & 3;                      // 16-byte chunk of the 64-byte operand row
-    const int rg = pt >> 2;                        // rows rg and rg + 64
+    const int rg = pt >> 2;                        // rows rg + 64*i
     const __nv_bfloat16* const xh = p.x_hi;
     const __nv_bfloat16* const xl = p.x_lo;
     int kit = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / tiles_n;
-      long long base[2];
-      int ih0[2], iw0[2];
-      bool ok[2];
-      uint32_t soff[2];
+      long long base[RPT];
+      int ih0[RPT], iw0[RPT];
+      bool ok[RPT];
+      uint32_t soff[RPT];
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
+      for (int i = 0; i < RPT; ++i) {
         const int r = rg + 64 * i;
-        const int m = tm * TC_BM + r;
+        const int m = tm * ROWS + r;
         ok[i] = m < p.M;
         const int mm = ok[i] ? m : 0;
         const int ow = mm % p.OW;
@@ -193,7 +201,7 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
         ih0[i] = oh * p.SH - p.PH;
         iw0[i] = ow * p.SW - p.PW;
         base[i] = (long long)b * p.H * p.W * p.C;
-        soff[i] = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u + (uint32_t)((chunk ^ ((r >> 1) & 3)) << 4);
+        soff[i] = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u + (uint32_t)((chunk ^ ((r >> 1) & 3)) << 4);   // m-tiles are contiguous 8 KB blocks
       }
       for (int kb = 0; kb < nkb; ++kb, ++kit) {
         const int s = kit % STAGES;
@@ -205,7 +213,7 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
         tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
         const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < RPT; ++i) {
           const int ih = ih0[i] + kh, iw = iw0[i] + kw;
           const bool valid = kok && ok[i] && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
           const long long e = valid ? base[i] + ((long long)ih * p.W + iw) * p.C + ci : 0;
@@ -239,26 +247,30 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
       constexpr uint32_t idesc = tc::make_idesc(1, BN);
       int kit = 0, it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        tc::mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+        const int acc = MT == 1 ? (it & 1) : 0;
+        tc::mbar_wait(tempty_bar(acc), (MT == 1 ? ((it >> 1) & 1) : (it & 1)) ^ 1);
         tc::tcgen05_after_sync();
-        const uint32_t d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
           const int s = kit % STAGES;
           tc::mbar_wait(full_bar(s), (kit / STAGES) & 1);
           tc::tcgen05_after_sync();
           const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t b_hi = a_hi + PLANES * Cfg::A_BYTES;
-          const uint64_t da_hi = tc::make_smem_desc_sw64(a_hi), db_hi = tc::make_smem_desc_sw64(b_hi);
-          const uint64_t da_lo = tc::make_smem_desc_sw64(a_hi + Cfg::A_BYTES), db_lo = tc::make_smem_desc_sw64(b_hi + Cfg::B_BYTES);
+          const uint64_t db_hi = tc::make_smem_desc_sw64(b_hi), db_lo = tc::make_smem_desc_sw64(b_hi + Cfg::B_BYTES);
 #pragma unroll
-          for (int k = 0; k < 2; ++k)   // 2 x 32 B = one 64-byte row
-            tc::umma<false>(d, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb | k) != 0);
-          if constexpr (PASSES == 3) {
+          for (int h = 0; h < MT; ++h) {   // the m-tiles of this CTA share the weight stage
+            const uint32_t d = tmem_base + (uint32_t)((MT == 1 ? acc : h) * BN);
+            const uint64_t da_hi = tc::make_smem_desc_sw64(a_hi + h * Cfg::A_HALF_BYTES);
+            const uint64_t da_lo = tc::make_smem_desc_sw64(a_hi + Cfg::A_BYTES + h * Cfg::A_HALF_BYTES);
 #pragma unroll
-            for (int k = 0; k < 2; ++k) tc::umma<false>(d, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+            for (int k = 0; k < 2; ++k)   // 2 x 32 B = one 64-byte row
+              tc::umma<false>(d, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (PASSES == 3) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) tc::umma<false>(d, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+              for (int k = 0; k < 2; ++k) tc::umma<false>(d, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < 2; ++k) tc::umma<false>(d, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+            }
           }
           tc::umma_commit(empty_bar(s));
         }
@@ -313,24 +325,35 @@ inline bool tc3_supported(const ConvGemm& p, int precision) {
          (p.res == nullptr || p.ldr % 4 == 0) && p.N % 4 == 0;
 }
 
-template <int PASSES, int BN>
+template <int PASSES, int BN, int MT = 1>
 inline cudaError_t tc3_launch_one(const ConvGemm& p, const Tc3Maps& m, cudaStream_t s, int num_sms) {
-  using Cfg = Tc3Cfg<PASSES, BN>;
+  using Cfg = Tc3Cfg<PASSES, BN, MT>;
   static bool attr_set = false;
-  auto kern = conv_gemm_tc3_kernel<PASSES, BN>;
+  auto kern = conv_gemm_tc3_kernel<PASSES, BN, MT>;
   if (!attr_set) {
     cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (st != cudaSuccess) return st;
     attr_set = true;
   }
-  const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = (p.N + BN - 1) / BN;
+  const int tiles_m = (p.M + MT * TC_BM - 1) / (MT * TC_BM), tiles_n = (p.N + BN - 1) / BN;
   const int grid = tiles_m * tiles_n < num_sms ? tiles_m * tiles_n : num_sms;
   constexpr int mi = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
   return launch_kernel(kern, dim3(grid), dim3(448), Cfg::SMEM_BYTES, s, p, m.hi[mi], m.lo[mi], tiles_m, tiles_n);
 }
 
+// D2T_TC3_MT2=1: two m-tiles per CTA.  Measured SLOWER on B200 (encoder 34.7 -> 39.9 ms in bf16x3): halving the
+// weight fill does not pay for the lost epilogue overlap, because the binding resource is shared-memory bandwidth
+// (operand fill writes + tcgen05 operand reads exceed 128 B/clk per SM), not the L2->SM fill.  Off by default.
+inline bool& tc3_two_mtiles() {
+  static bool on = false;
+  return on;
+}
+
 inline cudaError_t launch_conv_gemm_tc3(const ConvGemm& p, const Tc3Maps& m, int precision, cudaStream_t s, int num_sms) {
   const int bn = tc_pick_bn(p.M, p.N, num_sms);
+  // two m-tiles per CTA when the 256-row x 256-column tiles still give every SM at least two tiles
+  const bool mt2 = tc3_two_mtiles() && bn == 256 && (long long)((p.M + 255) / 256) * (p.N / 256) >= 2LL * num_sms;
+  if (mt2) return precision == 2 ? tc3_launch_one<3, 256, 2>(p, m, s, num_sms) : tc3_launch_one<1, 256, 2>(p, m, s, num_sms);
   if (precision == 2) {
     switch (bn) {
       case 256: return tc3_launch_one<3, 256>(p, m, s, num_sms);
