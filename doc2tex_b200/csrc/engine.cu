@@ -26,6 +26,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "gemm_tc3.cuh"
+#include "gemm_tc4.cuh"
 
 using namespace d2t;
 
@@ -103,6 +104,7 @@ struct d2t_engine {
   bool keep_taps = false;
   bool use_pdl = true;   // D2T_PDL=0 disables programmatic dependent launch in the decode step
   bool use_tc3 = true;   // D2T_TC3=0 / option "tc3": stem convolutions fed from bf16 activation planes by cp.async
+  bool use_tc4 = false;  // D2T_TC4=1 / option "tc4": CTA-pair + cp.async planes kernel for the 256-wide stem convolutions
   bool use_tc2 = false;  // D2T_TC2=1 / option "tc2": CTA-pair (cta_group::2) kernel for the large stem convolutions
   bool fuse_ln = false;  // D2T_FUSE_LN=1: cluster-fused residual+LayerNorm epilogue (measured slower than the stand-alone
                          // LayerNorm kernel on B200: cluster launch + DSMEM exchange cost more than the saved launch)
@@ -249,6 +251,12 @@ int run_contraction(d2t_engine* e, const ConvGemm& p, const TcWeight* tcw, int p
     if (e->use_tc3 && tc3_supported(p, precision)) {
       auto m3 = e->tc3.find(p.w);
       if (m3 != e->tc3.end() && m3->second.ready) {
+        if (e->use_tc4 && tc4_supported(p, precision, e->active_sms)) {
+          cudaError_t st4 = launch_conv_gemm_tc4(p, m3->second, precision, s, e->active_sms);
+          if (st4 != cudaSuccess) return e->fail(D2T_ERR_CUDA, "pair + cp.async contraction launch failed: %s", cudaGetErrorString(st4));
+          e->launches += 1;
+          return 0;
+        }
         cudaError_t st3 = launch_conv_gemm_tc3(p, m3->second, precision, s, e->active_sms);
         if (st3 != cudaSuccess) return e->fail(D2T_ERR_CUDA, "cp.async-fed contraction launch failed: %s", cudaGetErrorString(st3));
         e->launches += 1;
@@ -444,6 +452,7 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   if (const char* v = getenv("D2T_FUSE_LN")) e->fuse_ln = atoi(v) != 0;
   if (const char* v = getenv("D2T_TC2")) e->use_tc2 = atoi(v) != 0;
   if (const char* v = getenv("D2T_TC3")) e->use_tc3 = atoi(v) != 0;
+  if (const char* v = getenv("D2T_TC4")) e->use_tc4 = atoi(v) != 0;
   if (const char* v = getenv("D2T_TC3_MT2")) tc3_two_mtiles() = atoi(v) != 0;
   cudaSetDevice(device);
   if (cudaMallocHost(&e->h_counters, 4 * sizeof(int)) != cudaSuccess) {
@@ -702,6 +711,8 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
     e->use_tc2 = value != 0;
   } else if (k == "tc3") {
     e->use_tc3 = value != 0;
+  } else if (k == "tc4") {
+    e->use_tc4 = value != 0;
   } else {
     return e->fail(D2T_ERR_INVALID, "unknown option '%s'", key);
   }
