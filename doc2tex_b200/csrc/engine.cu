@@ -679,6 +679,15 @@ int d2t_finalize_weights(d2t_engine* e) {
         if ((rc = prep(e->dev[p + "linear2.weight"], D, c.dec_ff))) return rc;
       }
       if ((rc = prep(e->dev[PRED + "proj.weight"], c.vocab, D))) return rc;
+    } else if (c.head == D2T_HEAD_ATTNV2) {
+      const int Hs = c.attn_hidden;
+      const std::string a = PRED + "attention_cell.attn.";
+      if ((rc = prep(e->dev[a + "key_proj.weight"], Hs, D))) return rc;
+      if ((rc = prep(e->dev[a + "query_proj.weight"], Hs, Hs))) return rc;
+      if ((rc = prep(e->dev["lstm.w_cat"], 4 * Hs, 2 * D + Hs))) return rc;
+      if ((rc = prep(e->dev[PRED + "attention_cell.generator.weight"], c.vocab, Hs))) return rc;
+      if ((rc = prep(e->dev[PRED + "proj_init_h.weight"], Hs, D))) return rc;
+      if ((rc = prep(e->dev[PRED + "proj_init_c.weight"], Hs, D))) return rc;
     }
   }
   CUDA_TRY(e, cudaDeviceSynchronize());

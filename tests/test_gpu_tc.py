@@ -83,3 +83,23 @@ def test_tc_fp32_parity_modes_decode_token_exact(built_lib, precision):
             n = int(g["beam_len"][i])
             assert int(blen[i]) == n and bids[i, :n].cpu().tolist() == g["beam_seq"][i, :n].tolist()
         e.close()
+
+
+def test_attnv2_head_on_tensor_cores_matches_golden(built_lib):
+    """config/train.yaml default stack with the contractions on the tensor-core path (bf16x3)."""
+    from doc2tex_b200.engine import Engine
+    from tests.util import REL_TOL_FP32, end_bias_of, load_golden
+    for case in ("attnv2_64x256_full", "attnv2_64x256_end"):
+        g = load_golden(case)
+        cfg, sd = state_dict_for("Attnv2", end_bias_of(g))
+        e = Engine(cfg, "cuda:0", precision="bf16x3")
+        e.load_state_dict(sd)
+        img = synth.make_images(2, 64, 256, seed=2024)
+        ctx, _, _ = e.encode(img.cuda())
+        ids, logits, steps = e.decode_greedy(ctx, max_steps=151, is_test=True)
+        assert torch.equal(ids.cpu(), torch.from_numpy(g["ids"]))
+        ref = torch.from_numpy(g["logits"])
+        for j, s in enumerate(g["logit_steps"].tolist()):
+            if ref[:, j].abs().max() > 0:
+                assert rel_err(logits[:, s].cpu(), ref[:, j]) < REL_TOL_FP32, s
+        e.close()
