@@ -51,8 +51,14 @@ def parse():
                     help="TFM = HybridViT + transformer decoder (configs 1,2,3,5); Attnv2 = config/train.yaml default stack (config 4)")
     ap.add_argument("--encoder-sms", type=int, default=0,
                     help="SMs given to the encoder's persistent kernels; the rest run the overlapped decode of the previous batch")
+    ap.add_argument("--decode-groups", type=int, default=0,
+                    help="concurrent row groups of a decode call (0 = engine default)")
+    ap.add_argument("--decode-merge", type=int, default=0,
+                    help="encoded batches handed to one decode call by the pipelined schedule (0 = default for the mode)")
     ap.add_argument("--sequential", action="store_true", help="no encode/decode overlap across batches")
     a = ap.parse_args()
+    if a.decode_merge <= 0:
+        a.decode_merge = 1
     if a.encoder_sms <= 0:
         a.encoder_sms = 112 if a.mode == "greedy" else 88   # measured sweet spots (profiles/r01_pipeline_sweep.txt)
     if a.head == "Attnv2" and a.mode != "greedy":
@@ -176,6 +182,8 @@ def run_engine(args):
     model.load_state_dict(sd, strict=True)
     model = model.to(dev)
     eng: Engine = model.engine
+    if args.decode_groups > 0:
+        eng.set_option("decode_groups", args.decode_groups)
 
     B, H, W = args.batch, args.height, args.width
     # rank r holds images [r*B, (r+1)*B) of the global batch (seeded per image)
@@ -185,7 +193,8 @@ def run_engine(args):
     T = 151
 
     from doc2tex_b200.pipeline import PipelinedRecognizer
-    pipe = PipelinedRecognizer(eng, args.mode, args.beam, T, encoder_sms=None if args.sequential else args.encoder_sms)
+    pipe = PipelinedRecognizer(eng, args.mode, args.beam, T, encoder_sms=None if args.sequential else args.encoder_sms,
+                               decode_merge=1 if args.sequential else args.decode_merge)
 
     def gather(res):
         return d2dist.gather_results(res["ids"], res.get("lens"), res.get("scores"), n_total=B * world)
@@ -293,7 +302,8 @@ def run_engine(args):
         "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16x3": "bf16x3", "bf16": "bf16"}[args.precision],
         "data": "synthetic", "config": dict(workload_config(args, B), schedule=(
             "sequential" if args.sequential else
-            f"pipelined: encode(i+1) on {args.encoder_sms} SMs overlaps decode(i); one batch alone takes {seq_ms:.1f} ms")),
+            f"pipelined: encode on {args.encoder_sms} SMs overlaps the decode of the previous batches, {args.decode_merge} encoded "
+            f"batch(es) per decode call; one batch alone takes {seq_ms:.1f} ms")),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "formulas/s", "h2d_bytes_per_step": img_host.numel() * 4,
                 "d2h_bytes_per_step": B * world * (T + 2) * 8 if world > 1 else B * T * 8},

@@ -23,6 +23,15 @@ struct TfmBuffers {
   CUtensorMap map_x_hi, map_x_lo, map_att_hi, map_att_lo, map_ffn_hi, map_ffn_lo;
 };
 
+// Rows of one decode call are independent (greedy) or interact only inside one image (beam), so a call is cut into
+// `decode_groups` contiguous image slices that run the same step sequence concurrently on side streams: the step is a
+// chain of ~37 dependent launches of a few CTAs each, and concurrent chains fill SMs the single chain leaves idle.
+struct TfmGroup {
+  TfmBuffers b;
+  int B0 = 0, Bg = 0;   // first image, number of images
+  int R0 = 0, Rg = 0;   // first row, number of rows (images x beam)
+};
+
 template <typename T>
 int pool_get(d2t_engine* e, T** out, size_t n) {
   cudaError_t st = cudaSuccess;
@@ -149,22 +158,21 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
   return 0;
 }
 
-int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int max_steps, bool stop_early,
-               bool want_logits, TfmBuffers* bufs, int* steps_out, cudaStream_t s) {
+int choose_groups(const d2t_engine* e, int B, int R) {
+  int g = e->decode_groups;
+  // auto = one chain: measured on B200 (B=256, 151 steps) groups of 1/2/4/8 decode in 47.2/49.1/47.1/48.4 ms (greedy) and
+  // 70.8/68.1/66.6/67.0 ms (beam-5) — a step's duration is set by the length of the dependent chain, not by its rows
+  if (g <= 0) g = 1;
+  if (g > D2T_MAX_GROUPS) g = D2T_MAX_GROUPS;
+  if (g > B) g = B;
+  return g < 1 ? 1 : g;
+}
+
+int alloc_group(d2t_engine* e, TfmGroup& grp, int ntok, int beam, int T, bool want_logits, int* counters, cudaStream_t s) {
   const d2t_config& c = e->cfg;
-  if (c.head != D2T_HEAD_TFM) return e->fail(D2T_ERR_STATE, "engine was not configured with the TFM head");
-  if (!e->finalized) return e->fail(D2T_ERR_STATE, "decode before d2t_finalize_weights");
-  if (!ctx || B <= 0 || ntok <= 0 || max_steps <= 0) return e->fail(D2T_ERR_INVALID, "bad decode arguments");
-  if (max_steps > c.max_seq_len + 1)
-    return e->fail(D2T_ERR_INVALID, "max_steps %d exceeds max_seq_len+1 = %d", max_steps, c.max_seq_len + 1);
-  if (beam > BEAM_MAX) return e->fail(D2T_ERR_UNSUPPORTED, "beam size %d > %d", beam, BEAM_MAX);
-  CUDA_TRY(e, cudaSetDevice(e->device));
-  e->active_sms = e->num_sms;
-  const int D = c.hidden, F = c.dec_ff, V = c.vocab, T = max_steps, L = T + 1;
-  const int R = beam > 0 ? B * beam : B;
-  const int nl = c.dec_layers;
-  e->dec_pool.release_all();
-  TfmBuffers& b = *bufs;
+  const int D = c.hidden, F = c.dec_ff, V = c.vocab, L = T + 1, nl = c.dec_layers;
+  const int B = grp.Bg, R = grp.Rg;
+  TfmBuffers& b = grp.b;
   int rc;
   if ((rc = pool_get(e, &b.crosskv, (size_t)nl * B * ntok * 2 * D))) return rc;
   if ((rc = pool_get(e, &b.selfkv, (size_t)nl * R * T * 2 * D))) return rc;
@@ -174,8 +182,8 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
   if ((rc = pool_get(e, &b.att, (size_t)R * D))) return rc;
   if ((rc = pool_get(e, &b.ffn, (size_t)R * F))) return rc;
   if ((rc = pool_get(e, &b.logits, (size_t)R * V))) return rc;
-  if ((rc = pool_get(e, &b.counters, 4))) return rc;
-  if (getenv("D2T_DBG_DECODE")) {
+  b.counters = counters;
+  if (getenv("D2T_DBG_DECODE") && grp.B0 == 0) {
     if ((rc = pool_get(e, &b.dbg, 16))) return rc;
     CUDA_TRY(e, cudaMemsetAsync(b.dbg, 0, 16 * sizeof(long long), s));
   }
@@ -228,30 +236,94 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
   set_go_tokens_kernel<<<(R + 255) / 256, 256, 0, s>>>(b.tokens, L, beam > 0 ? (long long)R * L : 0, R, TFM_GO);
   e->launches += 2;
   CUDA_TRY(e, cudaGetLastError());
+  return 0;
+}
+
+// Fork the groups' work onto the side streams (group 0 stays on s) and join them back on s.  Works both eagerly and
+// under stream capture, where it becomes a graph with one parallel branch per group.
+template <typename Fn>
+int for_each_group_parallel(d2t_engine* e, std::vector<TfmGroup>& groups, cudaStream_t s, Fn&& fn) {
+  const int G = (int)groups.size();
+  if (G > 1) {
+    CUDA_TRY(e, cudaEventRecord(e->ev_fork, s));
+    for (int g = 1; g < G; ++g) CUDA_TRY(e, cudaStreamWaitEvent(e->side[g], e->ev_fork, 0));
+  }
+  int rc = 0;
+  for (int g = 0; g < G && !rc; ++g) rc = fn(groups[g], g == 0 ? s : e->side[g]);
+  for (int g = 1; g < G; ++g) {   // always join, also after an error, so that a capture can be ended cleanly
+    cudaError_t st = cudaEventRecord(e->ev_join[g], e->side[g]);
+    if (st == cudaSuccess) st = cudaStreamWaitEvent(s, e->ev_join[g], 0);
+    if (st != cudaSuccess && !rc) rc = e->fail(D2T_ERR_CUDA, "group join failed: %s", cudaGetErrorString(st));
+  }
+  return rc;
+}
+
+int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int max_steps, bool stop_early,
+               bool want_logits, std::vector<TfmGroup>* groups_out, int* steps_out, cudaStream_t s) {
+  const d2t_config& c = e->cfg;
+  if (c.head != D2T_HEAD_TFM) return e->fail(D2T_ERR_STATE, "engine was not configured with the TFM head");
+  if (!e->finalized) return e->fail(D2T_ERR_STATE, "decode before d2t_finalize_weights");
+  if (!ctx || B <= 0 || ntok <= 0 || max_steps <= 0) return e->fail(D2T_ERR_INVALID, "bad decode arguments");
+  if (max_steps > c.max_seq_len + 1)
+    return e->fail(D2T_ERR_INVALID, "max_steps %d exceeds max_seq_len+1 = %d", max_steps, c.max_seq_len + 1);
+  if (beam > BEAM_MAX) return e->fail(D2T_ERR_UNSUPPORTED, "beam size %d > %d", beam, BEAM_MAX);
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  e->active_sms = e->num_sms;
+  const int D = c.hidden, T = max_steps;
+  const int rows_per_img = beam > 0 ? beam : 1;
+  const int nl = c.dec_layers;
+  const int G = choose_groups(e, B, B * rows_per_img);
+  e->dec_pool.release_all();
+  std::vector<TfmGroup>& groups = *groups_out;
+  groups.assign(G, TfmGroup());
+  int rc;
+  int* counters_all = nullptr;
+  if ((rc = pool_get(e, &counters_all, (size_t)4 * G))) return rc;
+  for (int g = 0; g < G; ++g) {
+    TfmGroup& grp = groups[g];
+    grp.B0 = (int)((long long)B * g / G);
+    grp.Bg = (int)((long long)B * (g + 1) / G) - grp.B0;
+    grp.R0 = grp.B0 * rows_per_img;
+    grp.Rg = grp.Bg * rows_per_img;
+    if ((rc = alloc_group(e, grp, ntok, beam, T, want_logits, counters_all + 4 * g, s))) return rc;
+  }
   // cross-attention K/V of the encoder memory, once per image and layer (the reference re-projects
   // them at every step: nn.MultiheadAttention inside tfm.py:130 / :165)
-  for (int l = 0; l < nl; ++l) {
-    const std::string p = PRED + "model.layers." + std::to_string(l) + ".multihead_attn.";
-    ConvGemm g = linear_params(ctx, e->dev[p + "in_proj_weight"] + (size_t)D * D, e->dev[p + "in_proj_bias"] + D,
-                               b.crosskv + (size_t)l * B * ntok * 2 * D, B * ntok, 2 * D, D);
-    if ((rc = dec_linear(e, g, s))) return rc;
-  }
+  rc = for_each_group_parallel(e, groups, s, [&](TfmGroup& grp, cudaStream_t gs) -> int {
+    for (int l = 0; l < nl; ++l) {
+      const std::string p = PRED + "model.layers." + std::to_string(l) + ".multihead_attn.";
+      ConvGemm g = linear_params(ctx + (size_t)grp.B0 * ntok * D, e->dev[p + "in_proj_weight"] + (size_t)D * D,
+                                 e->dev[p + "in_proj_bias"] + D, grp.b.crosskv + (size_t)l * grp.Bg * ntok * 2 * D,
+                                 grp.Bg * ntok, 2 * D, D);
+      if (int r = dec_linear(e, g, gs)) return r;
+    }
+    return 0;
+  });
+  if (rc) return rc;
+  auto enqueue_step = [&]() -> int {
+    return for_each_group_parallel(e, groups, s, [&](TfmGroup& grp, cudaStream_t gs) -> int {
+      return enqueue_tfm_step(e, grp.b, grp.Rg, grp.Bg, ntok, beam, T, want_logits, gs);
+    });
+  };
 
   // ---- step graph ----
   cudaGraphExec_t exec = nullptr;
   int nodes = 0;
   if (c.use_graphs) {
-    std::vector<long long> key = {(long long)R, B, ntok, beam, T, want_logits ? 1 : 0};
-    const void* ptrs[] = {b.crosskv, b.selfkv, b.x, b.x2, b.q, b.att, b.ffn, b.logits, b.counters, b.tokens, b.anc,
-                          b.scores, b.n_live, b.n_done, b.finished, b.done_seq, b.done_len, b.done_score, b.trace,
-                          b.trace_score, b.ended, b.ids, b.logits_out, b.dbg, b.x_hi, b.x_lo, b.att_hi, b.att_lo, b.ffn_hi, b.ffn_lo};
-    for (const void* q : ptrs) key.push_back((long long)(uintptr_t)q);
+    std::vector<long long> key = {(long long)B, G, ntok, beam, T, want_logits ? 1 : 0};
+    for (const TfmGroup& grp : groups) {
+      const TfmBuffers& b = grp.b;
+      const void* ptrs[] = {b.crosskv, b.selfkv, b.x, b.x2, b.q, b.att, b.ffn, b.logits, b.counters, b.tokens, b.anc,
+                            b.scores, b.n_live, b.n_done, b.finished, b.done_seq, b.done_len, b.done_score, b.trace,
+                            b.trace_score, b.ended, b.ids, b.logits_out, b.dbg, b.x_hi, b.x_lo, b.att_hi, b.att_lo, b.ffn_hi, b.ffn_lo};
+      for (const void* q : ptrs) key.push_back((long long)(uintptr_t)q);
+    }
     for (auto& g : e->graphs) if (g.key == key) { exec = g.exec; nodes = g.nodes; }
     if (!exec) {
       cudaGraph_t graph = nullptr;
       CUDA_TRY(e, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
       const int64_t before = e->launches;
-      rc = enqueue_tfm_step(e, b, R, B, ntok, beam, T, want_logits, s);
+      rc = enqueue_step();
       nodes = (int)(e->launches - before);
       e->launches = before;
       cudaError_t st = cudaStreamEndCapture(s, &graph);
@@ -268,29 +340,39 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
       e->graphs.push_back(ge);
     }
   }
-  int executed = 0, done_step = -1;
+  // the reference stops when EVERY row / image of the batch is done: all groups done, at the latest group's step
+  auto all_done_step = [&]() -> int {
+    int last = 0;
+    for (int g = 0; g < G; ++g) {
+      const int d = e->h_counters[4 * g + 2];
+      if (d < 0) return -1;
+      if (d > last) last = d;
+    }
+    return last;
+  };
+  int executed = 0;
   for (int t = 0; t < T; ++t) {
     if (exec) {
       CUDA_TRY(e, cudaGraphLaunch(exec, s));
       e->launches += nodes;
-    } else if ((rc = enqueue_tfm_step(e, b, R, B, ntok, beam, T, want_logits, s))) {
+    } else if ((rc = enqueue_step())) {
       return rc;
     }
     executed = t + 1;
     if (stop_early && (executed % POLL_EVERY == 0) && executed < T) {
-      CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+      CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, counters_all, (size_t)4 * G * sizeof(int), cudaMemcpyDeviceToHost, s));
       CUDA_TRY(e, cudaStreamSynchronize(s));
-      if (e->h_counters[2] >= 0) break;
+      if (all_done_step() >= 0) break;
     }
   }
-  CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, counters_all, (size_t)4 * G * sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(e, cudaStreamSynchronize(s));
-  done_step = e->h_counters[2];
-  if (b.dbg) {
+  const int done_step = all_done_step();
+  if (groups[0].b.dbg) {
     long long h[12];
-    cudaMemcpy(h, b.dbg, sizeof h, cudaMemcpyDeviceToHost);
+    cudaMemcpy(h, groups[0].b.dbg, sizeof h, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[decode gemm dbg R=%d] prologue %lld ns, first full +%lld, last full +%lld, last commit +%lld, "
-                    "epi start +%lld, epi done +%lld, exit +%lld\n", R, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0],
+                    "epi start +%lld, epi done +%lld, exit +%lld\n", groups[0].Rg, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0],
             h[5] - h[0], h[6] - h[0], h[7] - h[0]);
   }
   *steps_out = (stop_early && done_step >= 0) ? done_step : executed;
@@ -308,12 +390,16 @@ int d2t_decode_greedy(d2t_engine* e, const float* ctx, int B, int ntok, int max_
   CUDA_TRY(e, cudaSetDevice(e->device));
   WorkStream ws(e, (cudaStream_t)stream);
   cudaStream_t s = ws.get();
-  TfmBuffers b;
+  std::vector<TfmGroup> groups;
   int steps = 0;
-  if (int rc = tfm_decode(e, ctx, B, ntok, 0, max_steps, stop_on_all_eos != 0, logits != nullptr, &b, &steps, s)) return rc;
-  CUDA_TRY(e, cudaMemcpyAsync(ids, b.ids, (size_t)B * max_steps * sizeof(int64_t), cudaMemcpyDeviceToDevice, s));
-  if (logits)
-    CUDA_TRY(e, cudaMemcpyAsync(logits, b.logits_out, (size_t)B * max_steps * e->cfg.vocab * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (int rc = tfm_decode(e, ctx, B, ntok, 0, max_steps, stop_on_all_eos != 0, logits != nullptr, &groups, &steps, s)) return rc;
+  for (const TfmGroup& grp : groups) {
+    CUDA_TRY(e, cudaMemcpyAsync(ids + (size_t)grp.R0 * max_steps, grp.b.ids, (size_t)grp.Rg * max_steps * sizeof(int64_t),
+                                cudaMemcpyDeviceToDevice, s));
+    if (logits)
+      CUDA_TRY(e, cudaMemcpyAsync(logits + (size_t)grp.R0 * max_steps * e->cfg.vocab, grp.b.logits_out,
+                                  (size_t)grp.Rg * max_steps * e->cfg.vocab * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
   CUDA_TRY(e, cudaStreamSynchronize(s));
   *steps_out = steps;
   return D2T_OK;
@@ -328,22 +414,28 @@ int d2t_decode_beam(d2t_engine* e, const float* ctx, int B, int ntok, int beam, 
   CUDA_TRY(e, cudaSetDevice(e->device));
   WorkStream ws(e, (cudaStream_t)stream);
   cudaStream_t s = ws.get();
-  TfmBuffers b;
+  std::vector<TfmGroup> groups;
   int steps = 0;
-  if (int rc = tfm_decode(e, ctx, B, ntok, beam, max_steps, true, false, &b, &steps, s)) return rc;
-  BeamState st{};
-  st.tokens = b.tokens; st.anc = b.anc; st.scores = b.scores; st.n_live = b.n_live; st.n_done = b.n_done;
-  st.finished = b.finished; st.done_seq = b.done_seq; st.done_len = b.done_len; st.done_score = b.done_score;
-  st.counters = b.counters; st.L = max_steps + 1; st.beam = beam; st.B = B; st.V = e->cfg.vocab; st.end_id = TFM_END;
-  st.max_steps = max_steps;
-  // device step counter == number of executed steps == parity of the live token buffer
-  beam_finalize_kernel<<<B, 128, 0, s>>>(st, e->h_counters[0], (long long*)best_ids, max_steps, best_len, best_score);
-  e->launches += 1;
-  CUDA_TRY(e, cudaGetLastError());
-  if (trace)
-    CUDA_TRY(e, cudaMemcpyAsync(trace, b.trace, (size_t)B * max_steps * beam * 2 * sizeof(int), cudaMemcpyDeviceToDevice, s));
-  if (trace_score)
-    CUDA_TRY(e, cudaMemcpyAsync(trace_score, b.trace_score, (size_t)B * max_steps * beam * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (int rc = tfm_decode(e, ctx, B, ntok, beam, max_steps, true, false, &groups, &steps, s)) return rc;
+  for (const TfmGroup& grp : groups) {
+    const TfmBuffers& b = grp.b;
+    BeamState st{};
+    st.tokens = b.tokens; st.anc = b.anc; st.scores = b.scores; st.n_live = b.n_live; st.n_done = b.n_done;
+    st.finished = b.finished; st.done_seq = b.done_seq; st.done_len = b.done_len; st.done_score = b.done_score;
+    st.counters = b.counters; st.L = max_steps + 1; st.beam = beam; st.B = grp.Bg; st.V = e->cfg.vocab; st.end_id = TFM_END;
+    st.max_steps = max_steps;
+    // device step counter == number of executed steps == parity of the live token buffer
+    beam_finalize_kernel<<<grp.Bg, 128, 0, s>>>(st, e->h_counters[0], (long long*)best_ids + (size_t)grp.B0 * max_steps, max_steps,
+                                                best_len + grp.B0, best_score + grp.B0);
+    e->launches += 1;
+    CUDA_TRY(e, cudaGetLastError());
+    if (trace)
+      CUDA_TRY(e, cudaMemcpyAsync(trace + (size_t)grp.B0 * max_steps * beam * 2, b.trace,
+                                  (size_t)grp.Bg * max_steps * beam * 2 * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    if (trace_score)
+      CUDA_TRY(e, cudaMemcpyAsync(trace_score + (size_t)grp.B0 * max_steps * beam, b.trace_score,
+                                  (size_t)grp.Bg * max_steps * beam * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
   CUDA_TRY(e, cudaStreamSynchronize(s));
   *steps_out = steps;
   return D2T_OK;

@@ -83,6 +83,8 @@ struct Tap { Fmap a; bool tokens; };
 
 }  // namespace
 
+constexpr int D2T_MAX_GROUPS = 8;
+
 struct d2t_engine {
   d2t_config cfg{};
   int device = 0;
@@ -113,7 +115,10 @@ struct d2t_engine {
   // decode graph cache
   struct GraphEntry { std::vector<long long> key; cudaGraphExec_t exec = nullptr; int nodes = 0; };
   std::vector<GraphEntry> graphs;
-  int* h_counters = nullptr;  // pinned [4]
+  int* h_counters = nullptr;  // pinned [D2T_MAX_GROUPS][4]
+  int decode_groups = 0;      // D2T_DECODE_GROUPS / option "decode_groups": concurrent row groups of a decode call (0 = auto)
+  cudaStream_t side[D2T_MAX_GROUPS] = {};   // side[g], g >= 1: stream of row group g (group 0 runs on `work`)
+  cudaEvent_t ev_fork = nullptr, ev_join[D2T_MAX_GROUPS] = {};
   cudaStream_t work = nullptr;   // engine-owned stream for the decode loop (the legacy default stream cannot be captured)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
@@ -455,7 +460,8 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   if (const char* v = getenv("D2T_TC4")) e->use_tc4 = atoi(v) != 0;
   if (const char* v = getenv("D2T_TC3_MT2")) tc3_two_mtiles() = atoi(v) != 0;
   cudaSetDevice(device);
-  if (cudaMallocHost(&e->h_counters, 4 * sizeof(int)) != cudaSuccess) {
+  if (const char* v = getenv("D2T_DECODE_GROUPS")) e->decode_groups = atoi(v);
+  if (cudaMallocHost(&e->h_counters, 4 * D2T_MAX_GROUPS * sizeof(int)) != cudaSuccess) {
     g_create_error = "cudaMallocHost failed";
     delete e;
     return D2T_ERR_CUDA;
@@ -467,6 +473,15 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
       cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
     g_create_error = "stream/event creation failed";
     delete e;
+    return D2T_ERR_CUDA;
+  }
+  bool side_ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int g = 1; g < D2T_MAX_GROUPS && side_ok; ++g)
+    side_ok = cudaStreamCreateWithPriority(&e->side[g], cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
+              cudaEventCreateWithFlags(&e->ev_join[g], cudaEventDisableTiming) == cudaSuccess;
+  if (!side_ok) {
+    g_create_error = "side stream/event creation failed";
+    d2t_destroy(e);
     return D2T_ERR_CUDA;
   }
   // decode attention may need > 48 KB of dynamic shared memory for long encoder memories
@@ -487,6 +502,11 @@ int d2t_destroy(d2t_engine* e) {
   if (e->work) cudaStreamDestroy(e->work);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  for (int g = 0; g < D2T_MAX_GROUPS; ++g) {
+    if (e->side[g]) cudaStreamDestroy(e->side[g]);
+    if (e->ev_join[g]) cudaEventDestroy(e->ev_join[g]);
+  }
   delete e;
   return D2T_OK;
 }
@@ -714,6 +734,9 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
   if (k == "encoder_sms") {
     if (value < 8 || value > e->num_sms) return e->fail(D2T_ERR_INVALID, "encoder_sms must be in [8, %d]", e->num_sms);
     e->enc_sms = value;
+  } else if (k == "decode_groups") {
+    if (value < 0 || value > D2T_MAX_GROUPS) return e->fail(D2T_ERR_INVALID, "decode_groups must be in [0, %d]", D2T_MAX_GROUPS);
+    e->decode_groups = value;
   } else if (k == "pdl") {
     e->use_pdl = value != 0;
   } else if (k == "tc2") {

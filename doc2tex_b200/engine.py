@@ -167,6 +167,11 @@ class Engine:
                     "d2t_decode_beam")
         return ids, lens, score, steps.value, tr, trs
 
+    @property
+    def end_id(self) -> int:
+        """[s]/END token id of the head's converter (tfm_converter.py:8, attn_converter.py:8)."""
+        return 2 if self.cfg.head == _lib.HEAD["TFM"] else 1
+
     def set_option(self, key: str, value: int):
         """Engine knobs: "encoder_sms" (SM budget of the encoder's persistent kernels), "pdl" (0/1)."""
         self._check(self.lib.d2t_set_option(self.h, key.encode(), int(value)), f"d2t_set_option({key})")

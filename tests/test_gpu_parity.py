@@ -217,6 +217,55 @@ def test_pipelined_schedule_equals_sequential(built_lib):
     e.set_option("encoder_sms", 148)
 
 
+@pytest.mark.parametrize("merge", [2, 3])
+def test_merged_decode_schedule_equals_sequential(built_lib, merge):
+    """decode_merge hands several encoded batches to one decode call; every batch must still get exactly its own
+    sequential result, including the reference's early-exit step count (natural END, batches that finish at
+    different steps) and a ragged tail (5 batches, merge 2 / 3)."""
+    from doc2tex_b200.pipeline import PipelinedRecognizer
+    e = engine_for("TFM", 1.5, "bf16x3")
+    batches = [synth.make_images(2 + (i % 2), 64, 256, seed=300 + 11 * i).cuda() for i in range(5)]
+    seq = []
+    for x in batches:
+        ctx, _, _ = e.encode(x)
+        ids, _, steps = e.decode_greedy(ctx, is_test=True, return_logits=False)
+        b = e.decode_beam(ctx, 5)
+        seq.append((ids[:, :steps].clone(), steps, b[0].clone(), b[1].clone(), b[2].clone()))
+    assert len({s[1] for s in seq}) > 1, "fixture should exercise different early-exit steps per batch"
+    for mode in ("greedy", "beam"):
+        pipe = PipelinedRecognizer(e, mode, 5, None, encoder_sms=120, decode_merge=merge)
+        outs = list(pipe.run(batches))
+        assert len(outs) == 5
+        for (g_ids, g_steps, b_ids, b_len, b_sc), res in zip(seq, outs):
+            if mode == "greedy":
+                assert res["steps"] == g_steps and torch.equal(res["ids"], g_ids)
+            else:
+                assert torch.equal(res["ids"], b_ids) and torch.equal(res["lens"], b_len) and torch.equal(res["scores"], b_sc)
+    e.set_option("encoder_sms", 148)
+
+
+@pytest.mark.parametrize("groups", [2, 3, 8])
+def test_decode_row_groups_equal_single_chain(built_lib, groups):
+    """decode_groups cuts one decode call into concurrent image slices (side streams, one graph with parallel
+    branches); tokens, early-exit step, beams and traces must not depend on it."""
+    e = engine_for("TFM", 1.5, "bf16x3")
+    ctx, _, _ = e.encode(synth.make_images(7, 64, 256, seed=77).cuda())
+    e.set_option("decode_groups", 1)
+    ids0, lg0, st0 = e.decode_greedy(ctx, is_test=True)
+    b0 = e.decode_beam(ctx, 5, trace=True)
+    e.set_option("decode_groups", groups)
+    try:
+        ids1, lg1, st1 = e.decode_greedy(ctx, is_test=True)
+        b1 = e.decode_beam(ctx, 5, trace=True)
+    finally:
+        e.set_option("decode_groups", 0)
+    assert st0 == st1 and torch.equal(ids0[:, :st0], ids1[:, :st1]) and torch.equal(lg0[:, :st0], lg1[:, :st1])
+    assert b0[3] == b1[3]
+    for a, b in zip((b0[0], b0[1], b0[2]), (b1[0], b1[1], b1[2])):
+        assert torch.equal(a, b)
+    assert torch.equal(b0[4][:, :b0[3]], b1[4][:, :b1[3]])
+
+
 def test_full_batch_properties_b256(built_lib):
     """BASELINE config size (B=256, 151 steps): size-independent properties.
     (1) the tensor-core fp32-parity mode (bf16x3) and the FFMA anchor (fp32) produce identical greedy tokens for all

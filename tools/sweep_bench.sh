@@ -1,7 +1,10 @@
 #!/bin/bash
+# usage: tools/sweep_bench.sh  (on the GPU box) — merged-decode sweep of the pipelined schedule
 show='import json,sys
 d=json.load(sys.stdin)
 print(sys.argv[1], "value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "ms/step", round(d["ms_per_step"],1), "enc", round(d["roofline"]["encode_ms"],1), "dec", round(d["roofline"]["decode_ms"],1), d["clocks"]["sm_mhz"], d["clocks"]["reasons"])'
-timeout 300 python bench.py --steps 6 --warmup 3 --cpu-sample 0 --head Attnv2 --batch 512 --sequential 2>> gpurun_out/bench_err.log | python -c "$show" "attnv2 B=512 sequential"
-timeout 300 python bench.py --steps 6 --warmup 3 --cpu-sample 0 --head Attnv2 --batch 512 2>> gpurun_out/bench_err.log | python -c "$show" "attnv2 B=512 pipelined"
+for cfg in "greedy 2 124" "greedy 4 124" "greedy 4 136" "greedy 4 148" "greedy 6 140" "beam 2 116" "beam 2 132" "beam 3 132" "beam 4 140"; do
+set -- $cfg
+timeout 300 python bench.py --steps 12 --warmup 3 --cpu-sample 0 --mode $1 --decode-merge $2 --encoder-sms $3 2>> gpurun_out/bench_err.log | python -c "$show" "$1 merge=$2 sms=$3"
+done
 tail -5 gpurun_out/bench_err.log
