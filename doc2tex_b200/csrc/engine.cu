@@ -27,6 +27,7 @@
 #include "gemm_tc2.cuh"
 #include "gemm_tc3.cuh"
 #include "gemm_tc4.cuh"
+#include "decode_cluster.cuh"
 
 using namespace d2t;
 
@@ -116,6 +117,12 @@ struct d2t_engine {
   struct GraphEntry { std::vector<long long> key; cudaGraphExec_t exec = nullptr; int nodes = 0; };
   std::vector<GraphEntry> graphs;
   int* h_counters = nullptr;  // pinned [D2T_MAX_GROUPS][4]
+  // cluster-resident decode step (decode_cluster.cuh): one launch per step instead of the ~37-launch chain
+  ClusterStepPlan cs_plan;
+  // Off by default: measured 330 us per step against the chain's 292 us (B=256, step 99) — at N = 16/32 rows per cluster a
+  // tcgen05.mma retires every ~90 ns whatever its N, so the 48 MMAs of a K=256 bf16x3 projection cost as much as the
+  // chain's wide tiles, and the 40 cluster hand-offs per step add another ~60 us.
+  bool use_cluster_step = false;  // D2T_CLUSTER_STEP=1 / option "cluster_step"
   int decode_groups = 0;      // D2T_DECODE_GROUPS / option "decode_groups": concurrent row groups of a decode call (0 = auto)
   cudaStream_t side[D2T_MAX_GROUPS] = {};   // side[g], g >= 1: stream of row group g (group 0 runs on `work`)
   cudaEvent_t ev_fork = nullptr, ev_join[D2T_MAX_GROUPS] = {};
@@ -131,6 +138,7 @@ struct d2t_engine {
 };
 
 int finalize_attn_extras(d2t_engine* e);
+int prepare_cluster_step(d2t_engine* e);
 
 #define CUDA_TRY(e, call)                                                                          \
   do {                                                                                             \
@@ -461,6 +469,7 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   if (const char* v = getenv("D2T_TC3_MT2")) tc3_two_mtiles() = atoi(v) != 0;
   cudaSetDevice(device);
   if (const char* v = getenv("D2T_DECODE_GROUPS")) e->decode_groups = atoi(v);
+  if (const char* v = getenv("D2T_CLUSTER_STEP")) e->use_cluster_step = atoi(v) != 0;
   if (cudaMallocHost(&e->h_counters, 4 * D2T_MAX_GROUPS * sizeof(int)) != cudaSuccess) {
     g_create_error = "cudaMallocHost failed";
     delete e;
@@ -699,6 +708,7 @@ int d2t_finalize_weights(d2t_engine* e) {
         if ((rc = prep(e->dev[p + "linear2.weight"], D, c.dec_ff))) return rc;
       }
       if ((rc = prep(e->dev[PRED + "proj.weight"], c.vocab, D))) return rc;
+      if ((rc = prepare_cluster_step(e))) return rc;
     } else if (c.head == D2T_HEAD_ATTNV2) {
       const int Hs = c.attn_hidden;
       const std::string a = PRED + "attention_cell.attn.";
@@ -737,6 +747,8 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
   } else if (k == "decode_groups") {
     if (value < 0 || value > D2T_MAX_GROUPS) return e->fail(D2T_ERR_INVALID, "decode_groups must be in [0, %d]", D2T_MAX_GROUPS);
     e->decode_groups = value;
+  } else if (k == "cluster_step") {
+    e->use_cluster_step = value != 0;
   } else if (k == "pdl") {
     e->use_pdl = value != 0;
   } else if (k == "tc2") {
