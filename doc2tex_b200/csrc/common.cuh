@@ -37,6 +37,12 @@ struct ConvGemm {
   const float* ln_w;
   const float* ln_b;
   float ln_eps;
+  // optional split-K (TMA-fed-A tensor-core path): the K range is cut into k_splits slices, slice s is computed by its own
+  // CTA and stored (without activation; bias / residual only in slice 0) at out + s * split_stride; the consumer (the
+  // LayerNorm kernel) adds the slices.  A tcgen05.mma retires every ~90 ns whatever its N, so a K=1024 bf16x3 projection
+  // is 192 serial MMAs = 17 us on one CTA; eight slices take 2 us each.
+  int k_splits;            // 0 / 1 = no split
+  long long split_stride;  // elements between partial outputs
   // optional bf16 hi/lo NHWC planes of the INPUT activation (cp.async-fed A operand of conv_gemm_tc3_kernel)
   const __nv_bfloat16* x_hi;
   const __nv_bfloat16* x_lo;

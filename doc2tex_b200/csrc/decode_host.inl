@@ -18,7 +18,9 @@ struct TfmBuffers {
   long long* ids = nullptr;
   // bf16 hi/lo operand planes of the decoder activations + their TMA maps (tensor-core precisions only)
   long long* dbg = nullptr;   // D2T_DBG_DECODE=1: phase timestamps of one decode-step GEMM
+  long long* timeline = nullptr;   // D2T_DBG_TIMELINE=1: per-launch timestamps of a step
   bool planes = false;
+  int x2_parts = 1;   // x2 holds up to this many split-K partial outputs [parts][R][D]
   __nv_bfloat16 *x_hi = nullptr, *x_lo = nullptr, *att_hi = nullptr, *att_lo = nullptr, *ffn_hi = nullptr, *ffn_lo = nullptr;
   CUtensorMap map_x_hi, map_x_lo, map_att_hi, map_att_lo, map_ffn_hi, map_ffn_lo;
 };
@@ -47,8 +49,12 @@ int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long 
                       float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int R, cudaStream_t s) {
   const int heads = e->cfg.dec_heads, D = e->cfg.hidden;
   if (heads > 8) return e->fail(D2T_ERR_UNSUPPORTED, "decode attention supports at most 8 heads per row block");
-  CUDA_TRY(e, launch_kernel(decode_attention_kernel<32>, dim3(R), dim3(heads * 32), 0, s, q, D, kv, row_stride, 2 * D, anc,
-                            anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
+  static const int split_env = getenv("D2T_ATTN_SPLIT") ? atoi(getenv("D2T_ATTN_SPLIT")) : 0;
+  // few rows: the loads in flight per SM, not the bandwidth, bound the kernel -> two warps per (row, head)
+  const int split = split_env > 0 ? split_env : (R <= 4 * e->num_sms && heads == 8 ? 2 : 1);
+  auto kern = split >= 2 && heads == 8 ? decode_attention_kernel<32, 2> : decode_attention_kernel<32, 1>;
+  CUDA_TRY(e, launch_kernel(kern, dim3(R), dim3(heads * 32 * (split >= 2 && heads == 8 ? 2 : 1)), 0, s, q, D, kv, row_stride, 2 * D,
+                            anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
   e->launches += 1;
   return 0;
 }
@@ -66,8 +72,16 @@ int linear_ln(d2t_engine* e, ConvGemm g, const TfmBuffers& b, const float* lw, c
     g.out = b.x; g.out_hi = b.x_hi; g.out_lo = b.x_lo;
     return dec_linear(e, g, s);
   }
+  // split-K over extra CTAs: the serial tcgen05.mma chain of one tile (K/16 x passes instructions, ~90 ns each) is the
+  // critical path of these projections; the LayerNorm kernel adds the slices
+  int parts = 1;
+  if (tc && b.planes && e->split_k > 0 && g.a_map_hi != nullptr && e->tcw.count(g.w) && b.x2_parts > 1) {
+    const int nkb = g.K / 64, tiles = ((R + TC_BM - 1) / TC_BM) * ((g.N + 63) / 64);
+    while (parts * 2 <= b.x2_parts && nkb % (parts * 2) == 0 && tiles * parts * 2 <= e->active_sms) parts *= 2;
+  }
+  if (parts > 1) { g.k_splits = parts; g.split_stride = (long long)R * D; }
   if (int rc = dec_linear(e, g, s)) return rc;
-  return layernorm(e, b.x2, lw, lb, b.x, R, D, 1e-5f, s, b.x_hi, b.x_lo);
+  return layernorm(e, b.x2, lw, lb, b.x, R, D, 1e-5f, s, b.x_hi, b.x_lo, parts, (long long)R * D);
 }
 
 // Tensor maps and occupancy of the cluster-resident decode step (decode_cluster.cuh).  The kernel is specialised for the
@@ -176,6 +190,25 @@ int enqueue_cluster_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int n
   return 0;
 }
 
+// D2T_DBG_TIMELINE=1: a one-thread kernel between the launches of a step records globaltimer, so the last step's
+// per-launch durations (each inflated by one extra launch gap) can be printed.  Debug only.
+__global__ void timeline_stamp_kernel(long long* buf, int idx) {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  buf[idx] = t;
+}
+std::vector<const char*> g_tl_names;
+const char* timeline_name(int i) { return i < (int)g_tl_names.size() ? g_tl_names[i] : "?"; }
+struct Timeline {
+  long long* buf = nullptr; int n = 0; cudaStream_t s = nullptr; std::vector<const char*>* names = nullptr;
+  void mark(const char* what) {
+    if (!buf || n >= 63) return;
+    timeline_stamp_kernel<<<1, 1, 0, s>>>(buf, n);
+    if (names && (int)names->size() <= n) names->push_back(what);
+    ++n;
+  }
+};
+
 struct PdlScope {   // kernels enqueued inside the scope are chained with programmatic dependent launch
   bool prev;
   explicit PdlScope(bool on) : prev(pdl_enabled()) { pdl_enabled() = on; }
@@ -193,6 +226,8 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
   auto from_x = [&](ConvGemm& g) { if (b.planes) { g.a_map_hi = &b.map_x_hi; g.a_map_lo = b.x_lo ? &b.map_x_lo : nullptr; } };
   auto from_att = [&](ConvGemm& g) { if (b.planes) { g.a_map_hi = &b.map_att_hi; g.a_map_lo = b.att_lo ? &b.map_att_lo : nullptr; } };
   auto from_ffn = [&](ConvGemm& g) { if (b.planes) { g.a_map_hi = &b.map_ffn_hi; g.a_map_lo = b.ffn_lo ? &b.map_ffn_lo : nullptr; } };
+  Timeline tl; tl.buf = b.timeline; tl.s = s; tl.names = &g_tl_names;
+  tl.mark("start");
   const bool cluster = cluster_step_active(e) && b.crosskv_tmp != nullptr;
   if (cluster) {
     if ((rc = enqueue_cluster_step(e, b, R, B, ntok, beam, T, s))) return rc;
@@ -201,6 +236,7 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
                             e->dev[PRED + "word_embed.weight"], e->dev[PRED + "pos_enc.pe"], b.x, R, D, sqrtf((float)D),
                             b.x_hi, b.x_lo));
   e->launches += 1;
+  tl.mark("embed");
   for (int l = 0; l < c.dec_layers; ++l) {
     const std::string p = PRED + "model.layers." + std::to_string(l) + ".";
     float* selfkv = b.selfkv + (size_t)l * R * T * 2 * D;
@@ -213,26 +249,32 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
       if (l == 1) g.dbg = b.dbg;
       if ((rc = dec_linear(e, g, s))) return rc;
     }
+    if (l == 1) tl.mark("qkv");
     if ((rc = enqueue_attention(e, b.q, selfkv, (long long)T * 2 * D, beam > 0 ? b.anc : nullptr, par, L,
                                 beam > 0 ? beam : 1, step, 0, b.att, b.att_hi, b.att_lo, R, s))) return rc;
+    if (l == 1) tl.mark("self-attn");
     {
       ConvGemm g = linear_params(b.att, e->dev[p + "self_attn.out_proj.weight"], e->dev[p + "self_attn.out_proj.bias"], b.x2, R, D, D);
       g.res = b.x; g.ldr = D; from_att(g);
       if ((rc = linear_ln(e, g, b, e->dev[p + "norm1.weight"], e->dev[p + "norm1.bias"], R, D, s))) return rc;
     }
+    if (l == 1) tl.mark("o1+LN1");
     // cross-attention over the encoder memory (K/V projected once per image, shared by its beams), norm2
     {
       ConvGemm g = linear_params(b.x, e->dev[p + "multihead_attn.in_proj_weight"], e->dev[p + "multihead_attn.in_proj_bias"], b.q, R, D, D);
       from_x(g);
       if ((rc = dec_linear(e, g, s))) return rc;
     }
+    if (l == 1) tl.mark("q2");
     if ((rc = enqueue_attention(e, b.q, crosskv, (long long)ntok * 2 * D, nullptr, 0, 0, beam > 0 ? beam : 1, nullptr,
                                 ntok, b.att, b.att_hi, b.att_lo, R, s))) return rc;
+    if (l == 1) tl.mark("cross-attn");
     {
       ConvGemm g = linear_params(b.att, e->dev[p + "multihead_attn.out_proj.weight"], e->dev[p + "multihead_attn.out_proj.bias"], b.x2, R, D, D);
       g.res = b.x; g.ldr = D; from_att(g);
       if ((rc = linear_ln(e, g, b, e->dev[p + "norm2.weight"], e->dev[p + "norm2.bias"], R, D, s))) return rc;
     }
+    if (l == 1) tl.mark("o2+LN2");
     // feed-forward, norm3
     {
       ConvGemm g = linear_params(b.x, e->dev[p + "linear1.weight"], e->dev[p + "linear1.bias"], b.ffn, R, F, D);
@@ -240,17 +282,21 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
       g.out_hi = b.ffn_hi; g.out_lo = b.ffn_lo;
       if ((rc = dec_linear(e, g, s))) return rc;
     }
+    if (l == 1) tl.mark("lin1");
     {
       ConvGemm g = linear_params(b.ffn, e->dev[p + "linear2.weight"], e->dev[p + "linear2.bias"], b.x2, R, D, F);
       g.res = b.x; g.ldr = D; from_ffn(g);
       if ((rc = linear_ln(e, g, b, e->dev[p + "norm3.weight"], e->dev[p + "norm3.bias"], R, D, s))) return rc;
     }
+    if (l == 1) tl.mark("lin2+LN3");
+    if (l != 1) tl.mark("layer");
   }
   {
     ConvGemm g = linear_params(b.x, e->dev[PRED + "proj.weight"], e->dev[PRED + "proj.bias"], b.logits, R, V, D);
     from_x(g);
     if ((rc = dec_linear(e, g, s))) return rc;
   }
+  tl.mark("vocab");
   }  // launch-per-sublayer chain
   if (beam > 0) {
     BeamState st{};
@@ -264,8 +310,11 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
                               want_logits ? b.logits_out : nullptr, b.ended, b.counters + 1, b.counters + 2, R, TFM_END));
   }
   e->launches += 1;
+  tl.mark("pick");
   CUDA_TRY(e, launch_kernel(advance_step_kernel, dim3(1), dim3(1), 0, s, step));
   e->launches += 1;
+  tl.mark("advance");
+  tl.mark("(stamp only)");
   return 0;
 }
 
@@ -289,7 +338,8 @@ int alloc_group(d2t_engine* e, TfmGroup& grp, int ntok, int beam, int T, bool wa
   if ((rc = pool_get(e, &b.selfkv, (size_t)nl * R * T * 2 * D))) return rc;
   if (cluster_step_active(e) && (rc = pool_get(e, &b.crosskv_tmp, (size_t)B * ntok * 2 * D))) return rc;
   if ((rc = pool_get(e, &b.x, (size_t)R * D))) return rc;
-  if ((rc = pool_get(e, &b.x2, (size_t)R * D))) return rc;
+  b.x2_parts = 8;
+  if ((rc = pool_get(e, &b.x2, (size_t)b.x2_parts * R * D))) return rc;
   if ((rc = pool_get(e, &b.q, (size_t)R * D))) return rc;
   if ((rc = pool_get(e, &b.att, (size_t)R * D))) return rc;
   if ((rc = pool_get(e, &b.ffn, (size_t)R * F))) return rc;
@@ -298,6 +348,10 @@ int alloc_group(d2t_engine* e, TfmGroup& grp, int ntok, int beam, int T, bool wa
   if (getenv("D2T_DBG_DECODE") && grp.B0 == 0) {
     if ((rc = pool_get(e, &b.dbg, 64))) return rc;
     CUDA_TRY(e, cudaMemsetAsync(b.dbg, 0, 64 * sizeof(long long), s));
+  }
+  if (getenv("D2T_DBG_TIMELINE") && grp.B0 == 0) {
+    if ((rc = pool_get(e, &b.timeline, 64))) return rc;
+    CUDA_TRY(e, cudaMemsetAsync(b.timeline, 0, 64 * sizeof(long long), s));
   }
   b.planes = c.precision == D2T_PREC_BF16X3 || c.precision == D2T_PREC_BF16;
   if (b.planes) {
@@ -512,6 +566,13 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     fprintf(stderr, "[decode gemm dbg R=%d] prologue %lld ns, first full +%lld, last full +%lld, last commit +%lld, "
                     "epi start +%lld, epi done +%lld, exit +%lld\n", groups[0].Rg, h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0],
             h[5] - h[0], h[6] - h[0], h[7] - h[0]);
+  }
+  if (groups[0].b.timeline) {
+    long long h[64];
+    cudaMemcpy(h, groups[0].b.timeline, sizeof h, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[step timeline R=%d, last step; each interval includes one stamp launch]", groups[0].Rg);
+    for (int i = 1; i < 64 && h[i] != 0; ++i) fprintf(stderr, " %s %.1f", timeline_name(i), (h[i] - h[i - 1]) * 1e-3);
+    fprintf(stderr, "\n");
   }
   *steps_out = (stop_early && done_step >= 0) ? done_step : executed;
   return 0;

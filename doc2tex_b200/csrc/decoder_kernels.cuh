@@ -59,8 +59,11 @@ __global__ void embed_tokens_kernel(const int* __restrict__ tokens, int tok_ld, 
 // online-softmax state each (running max, sum, 4 output channels per lane), two keys in flight per quarter warp,
 // and are merged with shuffles at the end.  Optional bf16 hi/lo planes of the output feed the tensor-core
 // out-projection.
-template <int HD>
-__global__ void __launch_bounds__(256)
+// SPLIT > 1: the keys of a (row, head) are dealt to SPLIT warps of the block (8-key groups, round robin) and their
+// online-softmax states are merged through shared memory.  At small batch the kernel is bound by the loads each SM
+// has in flight, not by bandwidth: twice the warps per row = twice the bytes in flight.
+template <int HD, int SPLIT = 1>
+__global__ void __launch_bounds__(256 * SPLIT)
 decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kv,
                         long long row_stride, int pos_stride, const int* __restrict__ anc,
                         long long anc_parity_stride, int anc_ld, int rows_per_src,
@@ -70,7 +73,9 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __res
   pdl_wait();      // PDL: everything above overlapped the predecessor
   pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
   const int r = blockIdx.x;
-  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nheads = SPLIT == 1 ? 0 : blockDim.x / (32 * SPLIT);
+  const int h = SPLIT == 1 ? wid : wid % nheads, sp = SPLIT == 1 ? 0 : wid / nheads;
   const int g = lane >> 3, c = (lane & 7) * 4;
   const int t = step ? *step : 0;
   const int n_keys = n_fixed > 0 ? n_fixed : t + 1;
@@ -84,7 +89,7 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __res
   float mx = -INFINITY, sum = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const unsigned gmask = 0xFFu << (g * 8);   // quarter warps run different trip counts: group-local shuffles
-  for (int j0 = g; j0 < n_keys; j0 += 8) {
+  for (int j0 = g + 8 * sp; j0 < n_keys; j0 += 8 * SPLIT) {
     const int j1 = j0 + 4;
     const bool has1 = j1 < n_keys;
     const int s0 = anc_r ? src_base + anc_r[j0] : src_base;
@@ -126,6 +131,29 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __res
     acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
     acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
     acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
+  }
+  if constexpr (SPLIT > 1) {
+    __shared__ float s_part[8 * (SPLIT - 1) * 36];   // [head][split - 1][max, sum, pad, pad, acc[32]]
+    if (sp > 0) {
+      float* pp = s_part + (h * (SPLIT - 1) + sp - 1) * 36;
+      if (g == 0) *reinterpret_cast<float4*>(pp + 4 + c) = acc;
+      if (lane == 0) { pp[0] = gm; pp[1] = sum; }
+    }
+    __syncthreads();
+    if (sp > 0) return;
+    float M = gm;
+#pragma unroll
+    for (int q = 0; q < SPLIT - 1; ++q) M = fmaxf(M, s_part[(h * (SPLIT - 1) + q) * 36]);
+    const float w0 = (gm == -INFINITY) ? 0.f : expf(gm - M);
+    sum *= w0; acc.x *= w0; acc.y *= w0; acc.z *= w0; acc.w *= w0;
+#pragma unroll
+    for (int q = 0; q < SPLIT - 1; ++q) {
+      const float* pp = s_part + (h * (SPLIT - 1) + q) * 36;
+      const float wq = (pp[0] == -INFINITY) ? 0.f : expf(pp[0] - M);
+      const float4 a = *reinterpret_cast<const float4*>(pp + 4 + c);
+      sum = fmaf(wq, pp[1], sum);
+      acc.x = fmaf(wq, a.x, acc.x); acc.y = fmaf(wq, a.y, acc.y); acc.z = fmaf(wq, a.z, acc.z); acc.w = fmaf(wq, a.w, acc.w);
+    }
   }
   if (g == 0) {
     const float inv = 1.0f / sum;

@@ -126,7 +126,8 @@ __global__ void assemble_tokens_kernel(const float* __restrict__ tok, const floa
 template <int NV4>
 __global__ void layernorm_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
                                  float* __restrict__ y, int rows, float eps,
-                                 __nv_bfloat16* __restrict__ y_hi = nullptr, __nv_bfloat16* __restrict__ y_lo = nullptr) {
+                                 __nv_bfloat16* __restrict__ y_hi = nullptr, __nv_bfloat16* __restrict__ y_lo = nullptr,
+                                 int nparts = 1, long long part_stride = 0) {
   pdl_wait();      // PDL: everything above overlapped the predecessor
   pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
   constexpr int D = 128 * NV4;
@@ -139,6 +140,10 @@ __global__ void layernorm_kernel(const float* __restrict__ x, const float* __res
 #pragma unroll
   for (int i = 0; i < NV4; ++i) {
     v[i] = *reinterpret_cast<const float4*>(xr + (i * 32 + lane) * 4);
+    for (int pt = 1; pt < nparts; ++pt) {   // split-K partial sums of the producing GEMM, added in slice order
+      const float4 u = *reinterpret_cast<const float4*>(xr + (size_t)pt * part_stride + (i * 32 + lane) * 4);
+      v[i].x += u.x; v[i].y += u.y; v[i].z += u.z; v[i].w += u.w;
+    }
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
   const float mean = warp_sum(s) * (1.0f / D);

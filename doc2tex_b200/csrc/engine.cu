@@ -109,6 +109,10 @@ struct d2t_engine {
   bool use_tc3 = true;   // D2T_TC3=0 / option "tc3": stem convolutions fed from bf16 activation planes by cp.async
   bool use_tc4 = false;  // D2T_TC4=1 / option "tc4": CTA-pair + cp.async planes kernel for the 256-wide stem convolutions
   bool use_tc2 = false;  // D2T_TC2=1 / option "tc2": CTA-pair (cta_group::2) kernel for the large stem convolutions
+  bool time_conv = false;   // option "time_conv": bracket layer3.1.conv1 with events (d2t_debug_conv_time)
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
+  double conv_flops = 0.0;
+  int split_k = 1;       // D2T_SPLIT_K / option "split_k": 0 = never, 1 = auto split-K of the LayerNorm-fed decode projections
   bool fuse_ln = false;  // D2T_FUSE_LN=1: cluster-fused residual+LayerNorm epilogue (measured slower than the stand-alone
                          // LayerNorm kernel on B200: cluster launch + DSMEM exchange cost more than the saved launch)
   std::map<std::string, Tap> taps;
@@ -344,6 +348,17 @@ int conv_layer(d2t_engine* e, const std::string& name, const Fmap& x, Fmap* y, i
   p.ldc = c.cout; p.ldc2 = 0; p.ldr = c.cout; p.n_split = c.cout;
   p.B = x.B; p.H = x.H; p.W = x.W; p.C = x.C; p.KH = c.kh; p.KW = c.kw; p.SH = sh; p.SW = sw; p.PH = ph; p.PW = pw;
   p.OH = OH; p.OW = OW; p.M = x.B * OH * OW; p.N = c.cout; p.K = c.kh * c.kw * c.cin; p.act = act;
+  if (e->time_conv && name == "layer3.1.conv1" && e->conv_events.size() < 4096) {
+    cudaEvent_t a, b;
+    CUDA_TRY(e, cudaEventCreate(&a));
+    CUDA_TRY(e, cudaEventCreate(&b));
+    CUDA_TRY(e, cudaEventRecord(a, s));
+    const int rc = run_contraction(e, p, nullptr, e->cfg.precision, s);
+    CUDA_TRY(e, cudaEventRecord(b, s));
+    e->conv_events.emplace_back(a, b);
+    e->conv_flops = 2.0 * p.M * p.N * p.K;
+    return rc;
+  }
   return run_contraction(e, p, nullptr, e->cfg.precision, s);
 }
 
@@ -380,15 +395,16 @@ int basic_block(d2t_engine* e, const std::string& name, Fmap& x, cudaStream_t s)
 }
 
 int layernorm(d2t_engine* e, const float* x, const float* w, const float* b, float* y, int rows, int D, float eps,
-              cudaStream_t s, __nv_bfloat16* y_hi = nullptr, __nv_bfloat16* y_lo = nullptr) {
+              cudaStream_t s, __nv_bfloat16* y_hi = nullptr, __nv_bfloat16* y_lo = nullptr, int nparts = 1,
+              long long part_stride = 0) {
   const int threads = 256, wpb = threads / 32;
   const int grid = (rows + wpb - 1) / wpb;
   cudaError_t st;
   switch (D / 128) {
-    case 1: st = launch_kernel(layernorm_kernel<1>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo); break;
-    case 2: st = launch_kernel(layernorm_kernel<2>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo); break;
-    case 4: st = launch_kernel(layernorm_kernel<4>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo); break;
-    case 8: st = launch_kernel(layernorm_kernel<8>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo); break;
+    case 1: st = launch_kernel(layernorm_kernel<1>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo, nparts, part_stride); break;
+    case 2: st = launch_kernel(layernorm_kernel<2>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo, nparts, part_stride); break;
+    case 4: st = launch_kernel(layernorm_kernel<4>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo, nparts, part_stride); break;
+    case 8: st = launch_kernel(layernorm_kernel<8>, dim3(grid), dim3(threads), 0, s, x, w, b, y, rows, eps, y_hi, y_lo, nparts, part_stride); break;
     default: return e->fail(D2T_ERR_UNSUPPORTED, "LayerNorm width %d unsupported (need 128/256/512/1024)", D);
   }
   if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "layernorm launch: %s", cudaGetErrorString(st));
@@ -469,6 +485,7 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   if (const char* v = getenv("D2T_TC3_MT2")) tc3_two_mtiles() = atoi(v) != 0;
   cudaSetDevice(device);
   if (const char* v = getenv("D2T_DECODE_GROUPS")) e->decode_groups = atoi(v);
+  if (const char* v = getenv("D2T_SPLIT_K")) e->split_k = atoi(v);
   if (const char* v = getenv("D2T_CLUSTER_STEP")) e->use_cluster_step = atoi(v) != 0;
   if (cudaMallocHost(&e->h_counters, 4 * D2T_MAX_GROUPS * sizeof(int)) != cudaSuccess) {
     g_create_error = "cudaMallocHost failed";
@@ -747,6 +764,10 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
   } else if (k == "decode_groups") {
     if (value < 0 || value > D2T_MAX_GROUPS) return e->fail(D2T_ERR_INVALID, "decode_groups must be in [0, %d]", D2T_MAX_GROUPS);
     e->decode_groups = value;
+  } else if (k == "time_conv") {
+    e->time_conv = value != 0;
+  } else if (k == "split_k") {
+    e->split_k = value;
   } else if (k == "cluster_step") {
     e->use_cluster_step = value != 0;
   } else if (k == "pdl") {
@@ -760,6 +781,24 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
   } else {
     return e->fail(D2T_ERR_INVALID, "unknown option '%s'", key);
   }
+  return D2T_OK;
+}
+
+int d2t_debug_conv_time(d2t_engine* e, double* total_ms, int64_t* launches, double* flops_per_launch) {
+  if (!e || !total_ms || !launches || !flops_per_launch) return D2T_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  double tot = 0.0;
+  for (auto& ev : e->conv_events) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.first, ev.second) == cudaSuccess) tot += ms;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  *total_ms = tot;
+  *launches = (int64_t)e->conv_events.size();
+  *flops_per_launch = e->conv_flops;
+  e->conv_events.clear();
   return D2T_OK;
 }
 

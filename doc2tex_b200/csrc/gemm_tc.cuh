@@ -222,8 +222,11 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
   float* const ln_part_gen = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + TC_EPI_STAGE_BYTES + 256);
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
   if (dbg && threadIdx.x == 0) p.dbg[0] = tc::gtime();
-  const int num_tiles = tiles_m * tiles_n;
-  const int nkb = (p.K + Cfg::KB_ELEMS - 1) / Cfg::KB_ELEMS;
+  const int KS = (A_TMA && p.k_splits > 1) ? p.k_splits : 1;   // split-K slices (TMA-fed-A variant only)
+  const int tiles_mn = tiles_m * tiles_n;
+  const int num_tiles = tiles_mn * KS;
+  const int nkb_total = (p.K + Cfg::KB_ELEMS - 1) / Cfg::KB_ELEMS;
+  const int nkb = nkb_total / KS;   // host guarantees divisibility
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -266,9 +269,6 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
     const int sub_r = lane >> 3, c4 = (lane & 7) * 4;
     const int M = p.M, N = p.N, ldc = p.ldc, ldr = p.ldr, ldc2 = p.ldc2, n_split = p.n_split, act = p.act & 15;
     const float* const scale = p.scale;
-    const float* const shift = p.shift;
-    const float* const res = p.res;
-    float* const out = p.out;
     float* out2 = nullptr;   // columns >= n_split (KV-cache slot of the current decode step)
     if (p.out2) out2 = p.out2 + (p.dyn ? (long long)(*p.dyn) * p.dyn_mul2 : 0) - n_split;
     __nv_bfloat16* const out_hi = p.out_hi;
@@ -301,8 +301,13 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
     } while (0)
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+      const int ks = tile / tiles_mn, tmn = tile - ks * tiles_mn;
+      const int tm = tmn / tiles_n, tn = tmn - tm * tiles_n;
       const int acc = it & 1;
+      // split-K: slice ks > 0 stores the bare partial sum at its own offset
+      const float* const shift = ks == 0 ? p.shift : nullptr;
+      const float* const res = ks == 0 ? p.res : nullptr;
+      float* const out = p.out + (size_t)ks * p.split_stride;
       if (slot < BN / 32) TC_EPI_PREFETCH(tm, tn, slot);
       tc::mbar_wait(tfull_bar(acc), (it >> 1) & 1);
       tc::tcgen05_after_sync();
@@ -519,19 +524,21 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
     if (lane == 0) {
       int kit = 0;
       for (int tile = blockIdx.x; tile < num_tiles && !(p.act & 64); tile += gridDim.x) {
-        const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+        const int ks = tile / tiles_mn, tmn = tile - ks * tiles_mn;
+        const int tm = tmn / tiles_n, tn = tmn - tm * tiles_n;
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
           const int s = kit % STAGES;
+          const int kcoord = (ks * nkb + kb) * Cfg::KB_ELEMS;
           tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
           tc::mbar_arrive_expect_tx(full_bar(s), PLANES * (Cfg::B_BYTES + (A_TMA ? Cfg::A_BYTES : 0)));
           if constexpr (A_TMA) {
             const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
-            tc::tma_load_2d(a_hi, &map_a_hi, full_bar(s), kb * Cfg::KB_ELEMS, tm * TC_BM);
-            if (PLANES == 2) tc::tma_load_2d(a_hi + Cfg::A_BYTES, &map_a_lo, full_bar(s), kb * Cfg::KB_ELEMS, tm * TC_BM);
+            tc::tma_load_2d(a_hi, &map_a_hi, full_bar(s), kcoord, tm * TC_BM);
+            if (PLANES == 2) tc::tma_load_2d(a_hi + Cfg::A_BYTES, &map_a_lo, full_bar(s), kcoord, tm * TC_BM);
           }
           const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES;
-          tc::tma_load_2d(b_hi, &map_hi, full_bar(s), kb * Cfg::KB_ELEMS, tn * BN);
-          if (PLANES == 2) tc::tma_load_2d(b_hi + Cfg::B_BYTES, &map_lo, full_bar(s), kb * Cfg::KB_ELEMS, tn * BN);
+          tc::tma_load_2d(b_hi, &map_hi, full_bar(s), kcoord, tn * BN);
+          if (PLANES == 2) tc::tma_load_2d(b_hi + Cfg::B_BYTES, &map_lo, full_bar(s), kcoord, tn * BN);
         }
       }
     }
@@ -698,7 +705,8 @@ inline cudaError_t tc_launch_one(const ConvGemm& p, const TcWeight& w, cudaStrea
     attr_set = true;
   }
   const int tiles_m = (p.M + TC_BM - 1) / TC_BM, tiles_n = (p.N + BN - 1) / BN;
-  const int grid = tiles_m * tiles_n < num_sms ? tiles_m * tiles_n : num_sms;
+  const int tiles = tiles_m * tiles_n * ((A_TMA && p.k_splits > 1) ? p.k_splits : 1);
+  const int grid = tiles < num_sms ? tiles : num_sms;
   constexpr int mi = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
   const CUtensorMap* ah = A_TMA ? reinterpret_cast<const CUtensorMap*>(p.a_map_hi) : &w.map_hi[mi];
   const CUtensorMap* al = (A_TMA && p.a_map_lo) ? reinterpret_cast<const CUtensorMap*>(p.a_map_lo) : ah;
@@ -723,10 +731,12 @@ inline cudaError_t tc_launch_bn(const ConvGemm& p, const TcWeight& w, cudaStream
         if (!tc_can_fuse_ln(p, num_sms)) return cudaErrorInvalidValue;
         return tc_launch_one<false, PASSES, 64, true, true>(p, w, s, num_sms);
       }
-      if (tiles_m * ((p.N + 63) / 64) <= num_sms) return tc_launch_one<false, PASSES, 64, true>(p, w, s, num_sms);
-      if (tiles_m * ((p.N + 127) / 128) <= num_sms) return tc_launch_one<false, PASSES, 128, true>(p, w, s, num_sms);
+      const int ks = p.k_splits > 1 ? p.k_splits : 1;
+      if (tiles_m * ((p.N + 63) / 64) * ks <= num_sms) return tc_launch_one<false, PASSES, 64, true>(p, w, s, num_sms);
+      if (ks == 1 && tiles_m * ((p.N + 127) / 128) <= num_sms) return tc_launch_one<false, PASSES, 128, true>(p, w, s, num_sms);
     }
   }
+  if (p.k_splits > 1) return cudaErrorInvalidValue;   // split-K exists on the TMA-fed-A path only: the caller must not ask
   switch (tc_pick_bn(p.M, p.N, num_sms)) {
     case 256: return tc_launch_one<TF32, PASSES, 256, false>(p, w, s, num_sms);
     case 128: return tc_launch_one<TF32, PASSES, 128, false>(p, w, s, num_sms);

@@ -213,5 +213,12 @@ class Engine:
                                                   self._stream()), "d2t_debug_gemm_bench")
         return ms.value * 1e3
 
+    def conv_time(self):
+        """(total ms, launches, FLOPs per launch) of the layer3 3x3 convolution launches timed since the last call
+        (enable with set_option("time_conv", 1))."""
+        ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
+        self._check(self.lib.d2t_debug_conv_time(self.h, C.byref(ms), C.byref(n), C.byref(fl)), "d2t_debug_conv_time")
+        return ms.value, n.value, fl.value
+
     def launch_count(self) -> int:
         return int(self.lib.d2t_launch_count(self.h))

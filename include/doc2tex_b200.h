@@ -140,7 +140,11 @@ int d2t_decode_attn_greedy(d2t_engine* e, const float* ctx_dev, int B, int ntok,
 /*
  * Engine knobs (no reference counterpart).  key = "encoder_sms": number of SMs the encoder's persistent
  * tensor-core kernels may occupy (default: all) — leaving a few SMs free lets the latency-bound decode of
- * batch i overlap the encode of batch i+1 on another stream (doc2tex_b200/pipeline.py); "pdl": 0/1.
+ * batch i overlap the encode of batch i+1 on another stream (doc2tex_b200/pipeline.py); "pdl": 0/1;
+ * "decode_groups": concurrent row groups of one decode call (parallel CUDA-graph branches, 0/1 = one chain);
+ * "split_k": split-K of the LayerNorm-fed decode projections (default 1); "cluster_step": 1 = the experimental
+ * cluster-resident decode step kernel (decode_cluster.cuh) instead of the launch-per-sublayer chain;
+ * "time_conv": see d2t_debug_conv_time.
  */
 int d2t_set_option(d2t_engine* e, const char* key, int value);
 
@@ -165,6 +169,12 @@ int d2t_debug_gemm(d2t_engine* e, const float* a_dev, const float* w_dev,
  * decode-step pattern); *ms_out = average milliseconds per iteration (CUDA events). */
 int d2t_debug_gemm_bench(d2t_engine* e, const float* a_dev, const float* w_dev, float* c_dev, int M, int N,
                          int K, int precision, int iters, int interleave, float* ms_out, d2t_stream stream);
+/* Live timing of the dominant kernel (bench.py's roofline): after d2t_set_option(e, "time_conv", 1) every d2t_encode
+ * brackets the launch of ONE layer3 3x3 convolution (512 -> 512 channels, the shape that carries 80 % of the encoder
+ * FLOPs) with CUDA events on the launching stream.  This call synchronises, returns the sum of the
+ * bracketed durations (ms), the number of launches timed and the algorithmic FLOPs of one launch (2*M*N*K), and
+ * clears the record. */
+int d2t_debug_conv_time(d2t_engine* e, double* total_ms, int64_t* launches, double* flops_per_launch);
 /* Number of kernel launches issued by this engine since creation (bench bookkeeping;
  * launches replayed from a CUDA graph are counted per replay). */
 int64_t d2t_launch_count(const d2t_engine* e);

@@ -122,3 +122,32 @@ def test_gather_results_gloo_world2(tmp_path):
                          capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_merged_decode_split_recovers_per_batch_steps():
+    """PipelinedRecognizer._split: a merged greedy decode runs until EVERY row of EVERY merged batch has emitted END;
+    each batch must still get the reference's own step count = first step at which all of ITS rows have ended
+    (tfm.py:138-140), or the merged count when one of its rows never ended."""
+    import torch
+    from doc2tex_b200.pipeline import PipelinedRecognizer
+
+    class FakeEngine:
+        end_id = 2
+        device = "cpu"
+
+    pipe = PipelinedRecognizer.__new__(PipelinedRecognizer)
+    pipe.eng, pipe.mode, pipe.is_test = FakeEngine(), "greedy", True
+    END = 2
+    ids = torch.full((5, 9), 7, dtype=torch.int64)
+    ids[0, 2] = END; ids[1, 4] = END            # batch 0 (rows 0-1): done after 5 steps
+    ids[2, 0] = END; ids[2, 3] = END            # batch 1 (row 2): done after 1 step (a later END does not matter)
+    ids[3, 8] = END                              # batch 2 (rows 3-4): row 4 never ends -> merged count
+    logits = torch.arange(5 * 9 * 3, dtype=torch.float32).reshape(5, 9, 3)
+    out = pipe._split({"ids": ids, "logits": logits, "steps": 9}, [2, 1, 2])
+    assert [o["steps"] for o in out] == [5, 1, 9]
+    assert torch.equal(out[0]["ids"], ids[0:2, :5]) and torch.equal(out[1]["ids"], ids[2:3, :1])
+    assert torch.equal(out[2]["ids"], ids[3:5]) and torch.equal(out[1]["logits"], logits[2:3, :1])
+    pipe.mode = "beam"
+    res = {"ids": ids, "lens": torch.arange(5), "scores": torch.arange(5.0), "steps": 9}
+    outb = pipe._split(res, [2, 1, 2])
+    assert torch.equal(outb[1]["lens"], torch.tensor([2])) and torch.equal(outb[2]["ids"], ids[3:5])
