@@ -61,8 +61,6 @@ def parse():
         a.decode_merge = 4   # measured: profiles/r01_pipeline_sweep.txt (decode of 4 encoded batches costs ~1.6x one)
     if a.encoder_sms <= 0:
         a.encoder_sms = 132  # measured sweet spot with merged decode (112 / 88 without)
-    if a.head == "Attnv2" and a.mode != "greedy":
-        ap.error("the Attnv2 head is accelerated for greedy decode only (beam is a 'next' row, SURVEY 8f1)")
     return a
 
 

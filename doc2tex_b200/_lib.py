@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libd2t_b200.so")
 SYMBOLS = [
     "d2t_create", "d2t_destroy", "d2t_last_error", "d2t_version", "d2t_load_tensor",
     "d2t_finalize_weights", "d2t_encode", "d2t_encoder_geometry", "d2t_decode_greedy",
-    "d2t_decode_beam", "d2t_decode_attn_greedy", "d2t_set_option", "d2t_set_debug", "d2t_debug_tap",
+    "d2t_decode_beam", "d2t_decode_attn_greedy", "d2t_decode_attn_beam", "d2t_set_option", "d2t_set_debug", "d2t_debug_tap",
     "d2t_debug_gemm", "d2t_debug_gemm_bench", "d2t_debug_conv_time", "d2t_launch_count",
 ]
 
@@ -56,6 +56,7 @@ def load():
     lib.d2t_encoder_geometry.argtypes = [vp, i32, i32] + [C.POINTER(C.c_int)] * 5
     lib.d2t_decode_greedy.argtypes = [vp, fp, i32, i32, i32, i32, vp, fp, C.POINTER(C.c_int), vp]
     lib.d2t_decode_beam.argtypes = [vp, fp, i32, i32, i32, i32, vp, vp, fp, vp, fp, C.POINTER(C.c_int), vp]
+    lib.d2t_decode_attn_beam.argtypes = [vp, fp, i32, i32, i32, i32, vp, vp, fp, vp, fp, C.POINTER(C.c_int), vp]
     lib.d2t_decode_attn_greedy.argtypes = [vp, fp, i32, i32, i32, i32, vp, fp, C.POINTER(C.c_int), vp]
     lib.d2t_set_option.argtypes = [vp, C.c_char_p, i32]
     lib.d2t_set_debug.argtypes = [vp, i32]

@@ -29,14 +29,15 @@ lstm_attention_step_kernel(const float* __restrict__ keyproj, const float* __res
                            const float* __restrict__ qp, const float* __restrict__ locM /*[HS][taps]*/,
                            const float* __restrict__ locc /*[HS]*/, int taps, const float* __restrict__ score_w,
                            const float* __restrict__ score_b, float* __restrict__ alpha_cum /*[B][S]*/,
-                           float* __restrict__ xcat, int ld) {
+                           float* __restrict__ xcat, int ld, int rows_per_img = 1) {
   extern __shared__ float sm[];  // [S] alpha_cum copy, [S] scores
   const int S = ntok - 1;
   float* s_ac = sm;
   float* s_e = sm + S;
   __shared__ float red[8];
   __shared__ float s_bc[2];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x;               // decoder row (hypothesis slot)
+  const int img = b / rows_per_img;       // the beams of an image share its encoder memory
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   constexpr int PER = HS / 32;
   for (int i = threadIdx.x; i < S; i += blockDim.x) s_ac[i] = alpha_cum[(size_t)b * S + i];
@@ -51,7 +52,7 @@ lstm_attention_step_kernel(const float* __restrict__ keyproj, const float* __res
   const int pad = taps / 2;
   const float sb = score_b[0];
   for (int s = wid; s < S; s += nw) {
-    const float* kr = keyproj + ((size_t)b * ntok + 1 + s) * HS;
+    const float* kr = keyproj + ((size_t)img * ntok + 1 + s) * HS;
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
@@ -95,7 +96,7 @@ lstm_attention_step_kernel(const float* __restrict__ keyproj, const float* __res
   __syncthreads();
   // context = alpha^T H, one thread per channel (HS == input channels == 256 here)
   for (int d = threadIdx.x; d < HS; d += blockDim.x) {
-    const float* hp = ctx + ((size_t)b * ntok + 1) * HS + d;
+    const float* hp = ctx + ((size_t)img * ntok + 1) * HS + d;
     float a0 = 0.f, a1 = 0.f;
     int s = 0;
     for (; s + 2 <= S; s += 2) {
@@ -162,6 +163,217 @@ __global__ void lstm_pick_kernel(const float* __restrict__ logits, int V, const 
       if (n == B) *done_step = t + 1;
     }
   }
+}
+
+// xcat[r, off : off+D] = E[targets[r]]  (beam rows carry their current token instead of a history lookup)
+__global__ void lstm_embed_cur_kernel(const int* __restrict__ targets, const float* __restrict__ emb,
+                                      float* __restrict__ xcat, int ld, int off, int R, int D) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int d4n = D / 4;
+  if (idx >= R * d4n) return;
+  const int r = idx / d4n, d = (idx % d4n) * 4;
+  *reinterpret_cast<float4*>(xcat + (size_t)r * ld + off + d) =
+      *reinterpret_cast<const float4*>(emb + (size_t)targets[r] * D + d);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Beam step of AttentionV2.forward_beam (seq2seq_v2.py:82-150), one CTA per image, batched over images (the
+// reference asserts batch 1, :18-19).  Reproduces its quirks:
+//   * step 0 ranks the candidates of row 0 only (:98-99); later steps rank rows < n_live flattened row-major, k = n_live;
+//   * candidates are processed in top-k order; word == END -> completed list (ascending top-k position, :115), else
+//     the next live set in that order;
+//   * hidden (h, c) and the token history follow the PARENT, the coverage memory alpha_cum (already += alpha by the
+//     attention kernel) is re-indexed by top-k POSITION (:137-147);
+//   * n_complete of the LAST executed step decides the final pick (:152-168, attn_beam_finalize_kernel).
+// State is permuted in place: every source row is staged in shared memory before anything is written.
+// ---------------------------------------------------------------------------------------------
+constexpr int ATTN_BEAM_MAX = 16;
+
+struct AttnBeamState {
+  float* scores;        // [R] cumulative log-prob of the live hypotheses
+  int* targets;         // [R] current token
+  int* seqs;            // [R][L] token history incl. GO at 0
+  float* h; float* c;   // [R][HS]
+  float* xcat; int ld, hoff;   // LSTM input rows: the h part lives at xcat[r*ld + hoff]
+  float* alpha_cum;     // [R][S]
+  int* n_live;          // [B]
+  int* n_done;          // [B]
+  int* last_complete;   // [B] completions of the last executed step
+  int* finished;        // [B]
+  int* done_seq;        // [R][L] completed hypotheses (GO ... END)
+  int* done_len;        // [R]   length incl. GO and END
+  float* done_score;    // [R]
+  int* counters;        // step, -, done_step, n_finished
+  int* trace;           // optional [B][max_steps][beam][2]
+  float* trace_score;   // optional [B][max_steps][beam]
+  int L, beam, B, V, S, HS, end_id, max_steps;
+};
+
+__global__ void __launch_bounds__(256)
+attn_beam_step_kernel(const float* __restrict__ logits, AttnBeamState st) {
+  extern __shared__ float s_dyn[];   // candidates [n][V]; later the staging area of the in-place permutation
+  __shared__ float s_rowmax[ATTN_BEAM_MAX], s_rowlse[ATTN_BEAM_MAX];
+  __shared__ float red_v[8];
+  __shared__ int red_i[8];
+  __shared__ float top_v[ATTN_BEAM_MAX];
+  __shared__ int top_i[ATTN_BEAM_MAX];
+  __shared__ int inc_pos[ATTN_BEAM_MAX], inc_parent[ATTN_BEAM_MAX], inc_word[ATTN_BEAM_MAX];
+  __shared__ int cmp_parent[ATTN_BEAM_MAX];
+  __shared__ float inc_score[ATTN_BEAM_MAX], cmp_score[ATTN_BEAM_MAX];
+  __shared__ int s_ninc, s_ncmp;
+  const int img = blockIdx.x;
+  if (st.finished[img]) return;
+  const int t = st.counters[0];
+  const int V = st.V, beam = st.beam, L = st.L, S = st.S, HS = st.HS;
+  const int n = st.n_live[img];
+  const int n_eff = t == 0 ? 1 : n;   // step 0: scores[0].topk (all rows are identical)
+  const int k = n;
+  const int row0 = img * beam;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+
+  for (int s = wid; s < n_eff; s += nw) {   // log-softmax per live row
+    const float* x = logits + (size_t)(row0 + s) * V;
+    float mx = -INFINITY;
+    for (int i = lane; i < V; i += 32) mx = fmaxf(mx, x[i]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int i = lane; i < V; i += 32) sum += expf(x[i] - mx);
+    sum = warp_sum(sum);
+    if (lane == 0) { s_rowmax[s] = mx; s_rowlse[s] = logf(sum); }
+  }
+  __syncthreads();
+  const int ncand = n_eff * V;
+  for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
+    const int s = i / V, v = i - s * V;
+    const float lp = (logits[(size_t)(row0 + s) * V + v] - s_rowmax[s]) - s_rowlse[s];
+    s_dyn[i] = st.scores[row0 + s] + lp;
+  }
+  __syncthreads();
+  for (int round = 0; round < k; ++round) {   // k rounds of block-wide argmax (value desc, index asc)
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
+      const float v = s_dyn[i];
+      if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < nw; ++i)
+        if (red_v[i] > bv || (red_v[i] == bv && red_i[i] < bi)) { bv = red_v[i]; bi = red_i[i]; }
+      top_v[round] = bv; top_i[round] = bi;
+      if (bi != 0x7fffffff) s_dyn[bi] = -INFINITY;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    int ninc = 0, ncmp = 0;
+    for (int i = 0; i < k; ++i) {
+      const int parent = top_i[i] / V, word = top_i[i] - parent * V;
+      if (st.trace) {
+        int* tr = st.trace + (((size_t)img * st.max_steps + t) * beam + i) * 2;
+        tr[0] = parent; tr[1] = word;
+        if (st.trace_score) st.trace_score[((size_t)img * st.max_steps + t) * beam + i] = top_v[i];
+      }
+      if (word != st.end_id) { inc_pos[ninc] = i; inc_parent[ninc] = parent; inc_word[ninc] = word; inc_score[ninc] = top_v[i]; ++ninc; }
+      else { cmp_parent[ncmp] = parent; cmp_score[ncmp] = top_v[i]; ++ncmp; }
+    }
+    s_ninc = ninc; s_ncmp = ncmp;
+  }
+  __syncthreads();
+  const int ninc = s_ninc, ncmp = s_ncmp;
+  const int ndone0 = st.n_done[img];
+  // completed hypotheses: history of the parent (t + 1 tokens incl. GO) + END
+  for (int j = 0; j < ncmp; ++j) {
+    const int* src = st.seqs + (size_t)(row0 + cmp_parent[j]) * L;
+    int* dst = st.done_seq + (size_t)(row0 + ndone0 + j) * L;
+    for (int i = threadIdx.x; i <= t; i += blockDim.x) dst[i] = src[i];
+    if (threadIdx.x == 0) {
+      dst[t + 1] = st.end_id;
+      st.done_len[row0 + ndone0 + j] = t + 2;
+      st.done_score[row0 + ndone0 + j] = cmp_score[j];
+    }
+  }
+  // stage the sources of the in-place permutation: [n][HS] h, [n][HS] c, [k][S] alpha_cum, [n][t+1] tokens
+  float* s_h = s_dyn;
+  float* s_c = s_h + (size_t)n * HS;
+  float* s_a = s_c + (size_t)n * HS;
+  int* s_q = reinterpret_cast<int*>(s_a + (size_t)n * S);
+  for (int i = threadIdx.x; i < n * HS; i += blockDim.x) {
+    s_h[i] = st.h[(size_t)row0 * HS + i];
+    s_c[i] = st.c[(size_t)row0 * HS + i];
+  }
+  for (int i = threadIdx.x; i < n * S; i += blockDim.x) s_a[i] = st.alpha_cum[(size_t)row0 * S + i];
+  for (int i = threadIdx.x; i < n * (t + 1); i += blockDim.x) {
+    const int r = i / (t + 1), p = i - r * (t + 1);
+    s_q[i] = st.seqs[(size_t)(row0 + r) * L + p];
+  }
+  __syncthreads();
+  for (int j = 0; j < ninc; ++j) {
+    const int par = inc_parent[j], pos = inc_pos[j];
+    const size_t r = (size_t)(row0 + j);
+    for (int i = threadIdx.x; i < HS; i += blockDim.x) {
+      const float hv = s_h[par * HS + i];
+      st.h[r * HS + i] = hv;
+      st.c[r * HS + i] = s_c[par * HS + i];
+      st.xcat[r * st.ld + st.hoff + i] = hv;
+    }
+    for (int i = threadIdx.x; i < S; i += blockDim.x) st.alpha_cum[r * S + i] = s_a[pos * S + i];   // by position (Q10)
+    for (int i = threadIdx.x; i <= t; i += blockDim.x) st.seqs[r * L + i] = s_q[par * (t + 1) + i];
+    if (threadIdx.x == 0) {
+      if (t + 1 < L) st.seqs[r * L + t + 1] = inc_word[j];
+      st.scores[row0 + j] = inc_score[j];
+      st.targets[row0 + j] = inc_word[j];
+    }
+  }
+  if (threadIdx.x == 0) {
+    st.n_live[img] = ninc;
+    st.n_done[img] = ndone0 + ncmp;
+    st.last_complete[img] = ncmp;
+    if (ninc == 0) {
+      st.finished[img] = 1;
+      const int nf = atomicAdd(&st.counters[3], 1) + 1;
+      if (nf == st.B) st.counters[2] = t + 1;
+    }
+  }
+}
+
+// Final pick (seq2seq_v2.py:152-174): the last executed step completed nothing -> live beam 0 (tokens after GO,
+// its running score); else the first maximum of fp32 score / len(seq incl. GO and END) over the completion order,
+// returned with the MAXIMUM completed score.
+__global__ void attn_beam_finalize_kernel(AttnBeamState st, int steps, long long* __restrict__ best_ids, int ids_ld,
+                                          int* __restrict__ best_len, float* __restrict__ best_score) {
+  const int img = blockIdx.x;
+  const int beam = st.beam, L = st.L;
+  const int row0 = img * beam;
+  __shared__ int s_best;
+  __shared__ float s_score;
+  if (threadIdx.x == 0) {
+    int best = -1;
+    float bv = 0.f, mxs = -INFINITY;
+    if (st.last_complete[img] > 0) {
+      const int nd = st.n_done[img];
+      for (int c = 0; c < nd; ++c) {
+        const float sc = st.done_score[row0 + c];
+        const float v = sc / (float)st.done_len[row0 + c];
+        if (best < 0 || v > bv) { best = c; bv = v; }
+        mxs = fmaxf(mxs, sc);
+      }
+    }
+    s_best = best;
+    s_score = best < 0 ? st.scores[row0] : mxs;
+  }
+  __syncthreads();
+  const int best = s_best;
+  const int* src = best < 0 ? st.seqs + (size_t)row0 * L + 1 : st.done_seq + (size_t)(row0 + best) * L + 1;
+  const int len = best < 0 ? steps : st.done_len[row0 + best] - 1;
+  for (int i = threadIdx.x; i < ids_ld; i += blockDim.x) best_ids[(size_t)img * ids_ld + i] = i < len ? src[i] : 0;
+  if (threadIdx.x == 0) { best_len[img] = len; best_score[img] = s_score; }
 }
 
 }  // namespace d2t

@@ -151,7 +151,7 @@ class Engine:
         return ids, logits, steps.value
 
     def decode_beam(self, ctx: torch.Tensor, beam: int, max_steps: Optional[int] = None, trace: bool = False):
-        """Batched TransformerPrediction.forward_beam: per image best ids (padded), length, score."""
+        """Batched TransformerPrediction.forward_beam / AttentionV2.forward_beam: per image best ids (padded), length, score."""
         ctx = self._dev(ctx, torch.float32)
         B, ntok, _ = ctx.shape
         T = self.cfg.max_seq_len + 1 if max_steps is None else max_steps
@@ -161,9 +161,10 @@ class Engine:
         tr = torch.empty(B, T, beam, 2, device=self.device, dtype=torch.int32) if trace else None
         trs = torch.empty(B, T, beam, device=self.device, dtype=torch.float32) if trace else None
         steps = C.c_int()
-        self._check(self.lib.d2t_decode_beam(self.h, ctx.data_ptr(), B, ntok, beam, T, ids.data_ptr(), lens.data_ptr(),
-                                             score.data_ptr(), tr.data_ptr() if trace else None,
-                                             trs.data_ptr() if trace else None, C.byref(steps), self._stream()),
+        fn = self.lib.d2t_decode_beam if self.cfg.head == _lib.HEAD["TFM"] else self.lib.d2t_decode_attn_beam
+        self._check(fn(self.h, ctx.data_ptr(), B, ntok, beam, T, ids.data_ptr(), lens.data_ptr(),
+                       score.data_ptr(), tr.data_ptr() if trace else None,
+                       trs.data_ptr() if trace else None, C.byref(steps), self._stream()),
                     "d2t_decode_beam")
         return ids, lens, score, steps.value, tr, trs
 

@@ -14,8 +14,9 @@ Differences, all on purpose:
   * inference only — ``is_train=True`` raises (the reference trains through the same class);
   * the arithmetic runs in hand-written sm_100a kernels behind the C ABI; there is no PyTorch
     or CPU fallback (a missing library / non-CUDA device raises);
-  * TFM beam search accepts B > 1 (the reference asserts B == 1, tfm.py:146-148) and gives every
-    image a fresh beam (the reference never resets it — SURVEY quirk Q6);
+  * beam search accepts B > 1 for both heads (the reference asserts B == 1, tfm.py:146-148 and
+    seq2seq_v2.py:18-19) and gives every image a fresh beam (the reference never resets the TFM one —
+    SURVEY quirk Q6);
   * optional ``opt["engine"] = {"precision": "fp32"|"tf32x3"|"bf16x3"|"bf16", "use_graphs": bool}``.
 """
 from __future__ import annotations
@@ -124,9 +125,16 @@ class Model(nn.Module):
                 return ids[:, : int(lens.max())], score.tolist(), None, addition_outputs
             ids, logits, steps = eng.decode_greedy(ctx, is_test=is_test)
             return ids[:, :steps], logits[:, :steps], None, addition_outputs
-        if beam_size > 1:
-            raise EngineError("Attnv2 beam search is not on the accelerated path yet (SURVEY §8 f1)")
         steps_total = int(self.opt["batch_max_length"]) + 1
+        if beam_size > 1:
+            # AttentionV2.forward_beam (seq2seq_v2.py:152-174): (LongTensor (1, len) on CPU, score tensor, alphas or None);
+            # batched here (the reference asserts batch 1): ids padded to the longest result, per-image lengths on the side
+            ids, lens, score, steps, _, _ = eng.decode_beam(ctx, beam_size, max_steps=steps_total)
+            ids, lens, score = ids.cpu(), lens.cpu(), score.cpu()
+            if ctx.shape[0] == 1:
+                return ids[:, : int(lens[0])], score[0], None, addition_outputs
+            addition_outputs["lengths"] = lens
+            return ids[:, : int(lens.max())], score, None, addition_outputs
         ids, logits, steps = eng.decode_greedy(ctx, max_steps=steps_total, is_test=is_test)
         return ids, logits, None, addition_outputs
 

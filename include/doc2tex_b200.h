@@ -138,6 +138,17 @@ int d2t_decode_attn_greedy(d2t_engine* e, const float* ctx_dev, int B, int ntok,
                            float* logits_dev, int* steps_out, d2t_stream stream);
 
 /*
+ * Replaces AttentionV2.forward_beam (seq2seq_v2.py:12-174), batched over B images (the reference asserts batch 1, :18-19).
+ * Same outputs as d2t_decode_beam.  Reproduces the reference's rules: step 0 ranks row 0 only; hidden state follows the
+ * parent while the coverage memory is re-indexed by top-k position; when the last executed step completed nothing the
+ * live beam 0 wins, else the first maximum of fp32 score / len(seq incl. GO and END), returned with the maximum
+ * completed score.
+ */
+int d2t_decode_attn_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, int beam, int max_steps,
+                         int64_t* best_ids_dev, int32_t* best_len_dev, float* best_score_dev, int32_t* trace_dev,
+                         float* trace_score_dev, int* steps_out, d2t_stream stream);
+
+/*
  * Engine knobs (no reference counterpart).  key = "encoder_sms": number of SMs the encoder's persistent
  * tensor-core kernels may occupy (default: all) — leaving a few SMs free lets the latency-bound decode of
  * batch i overlap the encode of batch i+1 on another stream (doc2tex_b200/pipeline.py); "pdl": 0/1;

@@ -149,6 +149,53 @@ def attn_case(name, H, W, B, end_bias):
                         margin=margins(probs_ref).numpy())
 
 
+def attn_beam_case(name, H, W, B, end_bias, beam=5):
+    """AttentionV2.forward_beam of the live reference, one image at a time (it asserts batch 1, seq2seq_v2.py:18-19)."""
+    cfg = synth.make_config("Attnv2")
+    sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias)
+    img = synth.make_images(B, H, W, seed=2024)
+    m = ref_model(cfg, sd)
+    head_ref = m.predicter.Prediction
+    head_or = om.AttnV2Head(sd)
+    seqs, scores, traces = [], [], []
+    with torch.no_grad():
+        ctx_ref, _, _ = m.forward_encoder(img)
+        ctx_or, _, _ = om.encoder_forward(sd, img)
+        for i in range(B):
+            seq_ref, sc_ref, _ = head_ref.forward_beam(ctx_ref[i:i + 1], batch_max_length=150, beam_size=beam)
+            s_ref = seq_ref[0].tolist()
+            tr = []
+            s_or, sc_or = head_or.beam(ctx_or[i:i + 1], beam, 150, trace=tr)
+            assert s_ref == s_or, f"attn beam seq differs for image {i}: {s_ref[:12]} vs {s_or[:12]}"
+            assert abs(float(sc_ref) - sc_or) <= 1e-3 * max(1.0, abs(float(sc_ref))), (float(sc_ref), sc_or)
+            live = [len(t[0]) for t in tr]
+            print(f"[{name}] attn beam img {i}: len {len(s_ref)} score {float(sc_ref):.4f} steps {len(tr)} "
+                  f"live rows per step (first 12) {live[:12]} ... last {live[-1]}")
+            seqs.append(s_ref); scores.append(float(sc_ref)); traces.append(tr)
+    L = max(len(s) for s in seqs)
+    T = max(len(t) for t in traces)
+    par = np.full((B, T, beam), -1, dtype=np.int64)
+    wrd = np.full((B, T, beam), -1, dtype=np.int64)
+    sco = np.zeros((B, T, beam), dtype=np.float32)
+    for i, t in enumerate(traces):
+        for st, (p_, w_, sc_) in enumerate(t):
+            par[i, st, :len(p_)] = p_; wrd[i, st, :len(w_)] = w_; sco[i, st, :len(sc_)] = sc_
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"),
+                        end_bias=np.array(np.nan if end_bias is None else end_bias),
+                        beam_seq=np.array([s_ + [-1] * (L - len(s_)) for s_ in seqs]),
+                        beam_len=np.array([len(s_) for s_ in seqs]), beam_score=np.array(scores, dtype=np.float64),
+                        beam_steps=np.array([len(t) for t in traces]),
+                        beam_parents=par, beam_words=wrd, beam_scores=sco)
+
+
+def attn_beam_cases():
+    attn_beam_case("attnv2_beam_64x256_full", 64, 256, 2, -1e4)    # nothing completes: live beam 0 after 151 steps
+    attn_beam_case("attnv2_beam_64x256_end04", 64, 256, 3, 0.4)    # the beam shrinks at steps 1..124, the last step completes
+                                                                   # nothing -> live beam 0 beats the completed ones (Q11)
+    attn_beam_case("attnv2_beam_64x256_end05", 64, 256, 3, 0.5)    # all five complete by step 10: best = fp32 score / len
+    attn_beam_case("attnv2_beam_64x256_end30", 64, 256, 2, 3.0)    # everything completes within the first two steps
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
@@ -161,3 +208,4 @@ if __name__ == "__main__":
     attn_case("attnv2_64x256_natural", 64, 256, 2, None)
     attn_case("attnv2_64x256_full", 64, 256, 2, -1e4)
     attn_case("attnv2_64x256_end", 64, 256, 2, 3.0)
+    attn_beam_cases()

@@ -294,6 +294,82 @@ class AttnV2Head:
             return probs.max(2)[1], probs
 
 
+    def _cell(self, h, c, H, emb, mem):
+        """LocationAwareAttentionCell.forward (attention1D.py:223-242) for n rows; mem = coverage memory or None."""
+        sd, P = self.sd, PRED
+        a = P + "attention_cell.attn."
+        n = h.shape[0]
+        pad = sd[a + "loc_conv.weight"].shape[2] // 2
+        kp = F.linear(H, sd[a + "key_proj.weight"], sd[a + "key_proj.bias"])
+        qp = F.linear(h, sd[a + "query_proj.weight"], sd[a + "query_proj.bias"]).unsqueeze(1)
+        last = mem if mem is not None else h.new_zeros(n, H.shape[1], 1)
+        loc = F.conv1d(last.permute(0, 2, 1), sd[a + "loc_conv.weight"], sd[a + "loc_conv.bias"], padding=pad)
+        loc = F.linear(loc.transpose(1, 2), sd[a + "loc_proj.weight"], sd[a + "loc_proj.bias"])
+        e = F.linear(torch.tanh(kp + qp + loc), sd[a + "score.weight"], sd[a + "score.bias"])
+        alpha = F.softmax(e / 1.0, dim=1)
+        context = torch.bmm(alpha.permute(0, 2, 1), H).squeeze(1)
+        h, c = self.rnn(torch.cat([context, emb], 1), (h, c))
+        out = F.linear(h, sd[P + "attention_cell.generator.weight"], sd[P + "attention_cell.generator.bias"])
+        return out, h, c, alpha
+
+    def beam(self, ctx1: torch.Tensor, beam_size: int = 5, batch_max_length: int = 150, trace: Optional[list] = None):
+        """AttentionV2.forward_beam (seq2seq_v2.py:12-174), batch 1, with its quirks:
+        step 0 ranks row 0 only (:98-99); hidden follows the parent but the coverage memory is re-indexed by top-k
+        POSITION (:137-147); if the LAST executed step completed nothing, live beam 0 wins over earlier completions
+        (:152-160); else first max of fp32 score / len(seq incl. GO and END), returned score = max score (:162-168).
+        Returns (token list without GO, score float)."""
+        sd, P = self.sd, PRED
+        with torch.no_grad():
+            assert ctx1.shape[0] == 1
+            num_steps = batch_max_length + 1
+            bH = ctx1[0][None].expand(beam_size, -1, -1)
+            H = bH[:, 1:, :]
+            init = bH[:, 0, :]
+            h = F.linear(init, sd[P + "proj_init_h.weight"], sd[P + "proj_init_h.bias"])
+            c = F.linear(init, sd[P + "proj_init_c.weight"], sd[P + "proj_init_c.bias"])
+            alpha_cum = torch.zeros(beam_size, H.shape[1], 1)
+            mem = None
+            seqs = torch.full((beam_size, 1), self.GO, dtype=torch.long)
+            targets = seqs.squeeze(-1)
+            top_k_scores = torch.zeros(beam_size, 1)
+            complete_seqs, complete_scores = [], []
+            complete_inds = []
+            for step in range(num_steps):
+                emb = self.embedding[targets]
+                out, h, c, alpha = self._cell(h, c, H, emb, mem)
+                V = out.shape[1]
+                scores = top_k_scores.expand_as(out) + F.log_softmax(out, dim=-1)
+                if step == 0:
+                    top_k_scores, top_k_words = scores[0].topk(beam_size, 0, True, True)
+                else:
+                    top_k_scores, top_k_words = scores.view(-1).topk(beam_size, 0, True, True)
+                prev = top_k_words // V
+                nxt = top_k_words % V
+                if trace is not None:
+                    trace.append((prev.tolist(), nxt.tolist(), top_k_scores.tolist()))
+                seqs = torch.cat([seqs[prev], nxt.unsqueeze(1)], dim=1)
+                incomplete_inds = [i for i, w in enumerate(nxt.tolist()) if w != self.END]
+                complete_inds = list(set(range(len(nxt))) - set(incomplete_inds))
+                if complete_inds:
+                    complete_seqs.extend(seqs[complete_inds].tolist())
+                    complete_scores.extend(top_k_scores[complete_inds])
+                beam_size -= len(complete_inds)
+                if beam_size == 0:
+                    break
+                seqs = seqs[incomplete_inds]
+                h, c = h[prev[incomplete_inds]], c[prev[incomplete_inds]]
+                H = H[prev[incomplete_inds]]
+                top_k_scores = top_k_scores[incomplete_inds].unsqueeze(1)
+                targets = nxt[incomplete_inds]
+                alpha_cum = (alpha_cum + alpha)[incomplete_inds]   # by position, not by parent (quirk Q10)
+                mem = alpha_cum
+            if len(complete_inds) == 0:
+                return seqs[0][1:].tolist(), float(top_k_scores[0])
+            combine = tuple(zip(complete_seqs, complete_scores))
+            best = combine.index(max(combine, key=lambda x: x[1] / len(x[0])))
+            return complete_seqs[best][1:], float(max(complete_scores))
+
+
 # --------------------------------------------------------------------------------------
 # whole-path helpers (what bench.py's reference arm times)
 # --------------------------------------------------------------------------------------

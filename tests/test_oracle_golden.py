@@ -73,6 +73,27 @@ def test_attnv2_greedy_matches_reference_golden(threads, case):
         assert (probs[:, s] - ref[:, j]).abs().max().item() <= 1e-4
 
 
+@pytest.mark.parametrize("case,img", [("attnv2_beam_64x256_end04", 1), ("attnv2_beam_64x256_end05", 0),
+                                      ("attnv2_beam_64x256_end30", 1)])
+def test_attnv2_beam_matches_reference_golden(threads, case, img):
+    """AttentionV2.forward_beam restatement (seq2seq_v2.py:12-174) against the live reference's outputs: a beam that
+    shrinks over 124 steps and ends on the live hypothesis (Q11), one that completes everything by step 10, one that
+    ends after two steps; top-k (parent, word) per step included."""
+    g = load_golden(case)
+    cfg, sd = state_dict_for("Attnv2", end_bias_of(g))
+    x = synth.make_images(int(g["beam_len"].shape[0]), 64, 256, seed=2024)
+    ctx, _, _ = om.encoder_forward(sd, x)
+    tr = []
+    seq, score = om.AttnV2Head(sd).beam(ctx[img:img + 1], 5, 150, trace=tr)
+    n = int(g["beam_len"][img])
+    assert seq == g["beam_seq"][img, :n].tolist()
+    assert abs(score - float(g["beam_score"][img])) <= 1e-3 * max(1.0, abs(score))
+    assert len(tr) == int(g["beam_steps"][img])
+    for t, (p, w, _) in enumerate(tr):
+        k = len(p)
+        assert p == g["beam_parents"][img, t, :k].tolist() and w == g["beam_words"][img, t, :k].tolist()
+
+
 def test_oracle_edge_cases():
     """Quirks the engine must share: causal mask values, prefix pos-embed slice, -inf pooling pad, tie rule."""
     m = om.TFMHead.causal_mask(4)
