@@ -9,6 +9,7 @@
 // stages.  Stages are half as deep (64-byte rows, 64B swizzle, 32 bf16 per k-block) so that twice as many fit:
 // 4 x 48 KB for the 3-pass 256-wide tile.
 #pragma once
+#include <cstdlib>
 #include "gemm_tc.cuh"
 
 namespace d2t {
@@ -352,7 +353,12 @@ inline bool& tc3_two_mtiles() {
 inline cudaError_t launch_conv_gemm_tc3(const ConvGemm& p, const Tc3Maps& m, int precision, cudaStream_t s, int num_sms) {
   const int bn = tc_pick_bn(p.M, p.N, num_sms);
   // two m-tiles per CTA when the 256-row x 256-column tiles still give every SM at least two tiles
-  const bool mt2 = tc3_two_mtiles() && bn == 256 && (long long)((p.M + 255) / 256) * (p.N / 256) >= 2LL * num_sms;
+  // Single-pass bf16 on the 512-channel 3x3 convolutions is the one place where it pays (measured: 0.828 -> 0.734 ms per
+  // launch, 0.54 -> 0.61 of the sustained bf16 peak): there the weight stage is re-read for half as many MMAs.  On the
+  // narrower / shallower convolutions and in the 3-pass mode it loses (encoder 24.4 -> 27.4 ms when applied everywhere).
+  static const bool auto_off = getenv("D2T_TC3_MT2_AUTO") && atoi(getenv("D2T_TC3_MT2_AUTO")) == 0;
+  const bool want = tc3_two_mtiles() || (!auto_off && precision == 3 && p.N >= 512 && p.K >= 4608 && p.res == nullptr);
+  const bool mt2 = want && bn == 256 && (long long)((p.M + 255) / 256) * (p.N / 256) >= 2LL * num_sms;
   if (mt2) return precision == 2 ? tc3_launch_one<3, 256, 2>(p, m, s, num_sms) : tc3_launch_one<1, 256, 2>(p, m, s, num_sms);
   if (precision == 2) {
     switch (bn) {
