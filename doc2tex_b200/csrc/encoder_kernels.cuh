@@ -121,6 +121,47 @@ __global__ void assemble_tokens_kernel(const float* __restrict__ tok, const floa
   }
 }
 
+// ViTEncoder.interpolating_pos_embedding (vit_encoder.py:58-95): out[0] = pos[0] (cls), out[1 + y*gw + x] = bicubic
+// resample of the [EH, EW, D] patch table at output cell (y, x).  torch upsample_bicubic2d, align_corners=False with an
+// explicit scale_factor: src = (dst + 0.5) / scale - 0.5 (not clamped), A = -0.75, taps clamped to the border.
+__device__ __forceinline__ void bicubic_coeffs(float t, float (&c)[4]) {
+  const float A = -0.75f;
+  const float x0 = t + 1.0f, x1 = t, x2 = 1.0f - t, x3 = 2.0f - t;
+  c[0] = ((A * x0 - 5.0f * A) * x0 + 8.0f * A) * x0 - 4.0f * A;
+  c[1] = ((A + 2.0f) * x1 - (A + 3.0f)) * x1 * x1 + 1.0f;
+  c[2] = ((A + 2.0f) * x2 - (A + 3.0f)) * x2 * x2 + 1.0f;
+  c[3] = ((A * x3 - 5.0f * A) * x3 + 8.0f * A) * x3 - 4.0f * A;
+}
+__global__ void pos_embed_bicubic_kernel(const float* __restrict__ pos, int EH, int EW, float* __restrict__ out, int gh,
+                                         int gw, float inv_scale_h, float inv_scale_w, int D) {
+  const long long total = (long long)(1 + gh * gw) * D;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(idx % D);
+    const int t = (int)(idx / D);
+    if (t == 0) { out[idx] = pos[d]; continue; }
+    const int oy = (t - 1) / gw, ox = (t - 1) % gw;
+    const float sy = inv_scale_h * (oy + 0.5f) - 0.5f, sx = inv_scale_w * (ox + 0.5f) - 0.5f;
+    const int iy = (int)floorf(sy), ix = (int)floorf(sx);
+    float cy[4], cx[4];
+    bicubic_coeffs(sy - iy, cy);
+    bicubic_coeffs(sx - ix, cx);
+    float acc = 0.f;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const int yy = min(max(iy - 1 + a, 0), EH - 1);
+      float row = 0.f;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int xx = min(max(ix - 1 + b, 0), EW - 1);
+        row += cx[b] * pos[(size_t)(1 + yy * EW + xx) * D + d];
+      }
+      acc += cy[a] * row;
+    }
+    out[idx] = acc;
+  }
+}
+
 // LayerNorm over the last dim, one warp per row, values kept in registers (D = 128 * NV4).
 // Two-pass mean / biased variance in fp32, y = (x - mean) / sqrt(var + eps) * w + b (torch semantics).
 template <int NV4>

@@ -109,6 +109,11 @@ struct d2t_engine {
   bool use_tc3 = true;   // D2T_TC3=0 / option "tc3": stem convolutions fed from bf16 activation planes by cp.async
   bool use_tc4 = false;  // D2T_TC4=1 / option "tc4": CTA-pair + cp.async planes kernel for the 256-wide stem convolutions
   bool use_tc2 = false;  // D2T_TC2=1 / option "tc2": CTA-pair (cta_group::2) kernel for the large stem convolutions
+  // ViTEncoder (fix_embed: False, interpolate_embed: True): pos_embed is resampled bicubically to the grid of each image
+  // size (vit_encoder.py:58-95) — options "pos_interpolate", "pos_grid_h", "pos_grid_w"; tables cached per grid
+  bool pos_interpolate = false;
+  int pos_grid_h = 0, pos_grid_w = 0;
+  std::map<std::pair<int, int>, float*> pos_tables;
   bool time_conv = false;   // option "time_conv": bracket layer3.1.conv1 with events (d2t_debug_conv_time)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
   double conv_flops = 0.0;
@@ -764,6 +769,12 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
   } else if (k == "decode_groups") {
     if (value < 0 || value > D2T_MAX_GROUPS) return e->fail(D2T_ERR_INVALID, "decode_groups must be in [0, %d]", D2T_MAX_GROUPS);
     e->decode_groups = value;
+  } else if (k == "pos_interpolate") {
+    e->pos_interpolate = value != 0;
+  } else if (k == "pos_grid_h") {
+    e->pos_grid_h = value;
+  } else if (k == "pos_grid_w") {
+    e->pos_grid_w = value;
   } else if (k == "time_conv") {
     e->time_conv = value != 0;
   } else if (k == "split_k") {
@@ -880,8 +891,27 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
   if ((rc = alloc_act(e, e->enc_pool, &qkv, B, 1, T, 3 * D))) return rc;
   if ((rc = alloc_act(e, e->enc_pool, &att, B, 1, T, D))) return rc;
   if ((rc = alloc_act(e, e->enc_pool, &ff, B, 1, T, 4 * D))) return rc;
+  const float* pos = e->dev[SEQ + "pos_embed"];
+  if (e->pos_interpolate && (gh != e->pos_grid_h || gw != e->pos_grid_w)) {
+    if (e->pos_grid_h <= 0 || e->pos_grid_w <= 0 || 1 + e->pos_grid_h * e->pos_grid_w != c.max_tokens)
+      return e->fail(D2T_ERR_STATE, "pos_interpolate needs pos_grid_h x pos_grid_w = the rows of pos_embed - 1");
+    auto it = e->pos_tables.find({gh, gw});
+    if (it == e->pos_tables.end()) {
+      float* tbl = nullptr;
+      CUDA_TRY(e, cudaMalloc(&tbl, (size_t)T * D * sizeof(float)));
+      e->owned.push_back(tbl);
+      // torch: scale_factor = (h0 + 0.1) / emb_height with h0 = grid rows; source index uses 1 / scale_factor
+      const float sfh = (float)((gh + 0.1) / e->pos_grid_h), sfw = (float)((gw + 0.1) / e->pos_grid_w);
+      pos_embed_bicubic_kernel<<<grid_for((long long)T * D, 256, e->num_sms), 256, 0, s>>>(
+          pos, e->pos_grid_h, e->pos_grid_w, tbl, gh, gw, 1.0f / sfh, 1.0f / sfw, D);
+      e->launches += 1;
+      CUDA_TRY(e, cudaGetLastError());
+      it = e->pos_tables.emplace(std::make_pair(gh, gw), tbl).first;
+    }
+    pos = it->second;
+  }
   assemble_tokens_kernel<<<grid_for((long long)rows * D / 4, 256, e->active_sms), 256, 0, s>>>(
-      tok.p, e->dev[SEQ + "cls_token"], e->dev[SEQ + "pos_embed"], xs.p, B, N, D);
+      tok.p, e->dev[SEQ + "cls_token"], pos, xs.p, B, N, D);
   e->launches += 1;
   CUDA_TRY(e, cudaGetLastError());
   free_act(e, e->enc_pool, tok);

@@ -21,8 +21,8 @@ def config_from_opt(opt: dict, precision: str = "fp32", use_graphs: bool = True)
     sp = opt["SequenceModeling"]["params"]
     if opt["FeatureExtraction"]["name"] != "None" or opt["SequenceModeling"]["name"] != "ViT":
         raise EngineError("only the HybridViT stack (FeatureExtraction None + SequenceModeling ViT) is accelerated")
-    if sp.get("patching_style", "2d") != "2d" or not sp.get("fix_embed", False):
-        raise EngineError("only patching_style '2d' with fix_embed: True (ViTEncoderV3) is supported")
+    if sp.get("patching_style", "2d") != "2d":
+        raise EngineError("only patching_style '2d' (ViTEncoder / ViTEncoderV2 / ViTEncoderV3) is supported")
     if sp["backbone"]["name"] != "resnet" or sp["backbone"].get("gcb", False):
         raise EngineError("only the resnet backbone without GlobalContext is supported")
     if list(sp["patch_size"]) != [2, 2]:
@@ -78,6 +78,15 @@ class Engine:
             raise EngineError(f"d2t_create failed ({rc}): {self.lib.d2t_last_error(None).decode()}")
         self.h = h
         self.loaded = False
+        sp = opt["SequenceModeling"]["params"]
+        # encoder variant (vit_encoder.py:301-309): fix_embed -> V3 (sin-cos table, prefix slice); else interpolate_embed
+        # (default True) -> ViTEncoder (bicubic resample of the learnable table per image size), False -> V2 (prefix slice)
+        if not sp.get("fix_embed", False) and sp.get("interpolate_embed", True):
+            max_h, max_w = (opt["imgH"], opt["max_dimension"][1]) if opt.get("imgH") else opt["max_dimension"]
+            fh, fw = max_h // 16 - 1, max_w // 4 + 1
+            self.set_option("pos_interpolate", 1)
+            self.set_option("pos_grid_h", (fh + 1) // 2)
+            self.set_option("pos_grid_w", (fw + 1) // 2)
 
     # ------------------------------------------------------------------
     def _check(self, rc: int, what: str):

@@ -203,7 +203,10 @@ def make_state_dict(cfg: dict, seed: int = 1111, suppress_end: bool = False,
     gh, gw = grid_hw(max_h, max_w)
 
     sd[SEQ + "cls_token"] = rng.trunc_normal((1, 1, D), 0.02)
-    sd[SEQ + "pos_embed"] = sincos_pos_embed(D, gh, gw)
+    if cfg["SequenceModeling"]["params"].get("fix_embed", False):
+        sd[SEQ + "pos_embed"] = sincos_pos_embed(D, gh, gw)                 # ViTEncoderV3 (vit_encoder.py:229-247)
+    else:
+        sd[SEQ + "pos_embed"] = rng.trunc_normal((1, gh * gw + 1, D), 0.02)  # ViTEncoder / V2: learnable (:43-49)
     for i in range(depth):
         p = f"{SEQ}blocks.{i}."
         sd[p + "norm1.weight"] = rng.normal((D,), 0.1, 1.0)

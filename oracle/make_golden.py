@@ -43,7 +43,10 @@ def ref_model(cfg, sd):
     for k, v in ref_sd.items():
         assert tuple(v.shape) == tuple(sd[k].shape) and v.dtype == sd[k].dtype, k
     # fixed buffers must be reproduced exactly by the synth restatement
-    for k in (synth.SEQ + "pos_embed", synth.PRED + "pos_enc.pe"):
+    fixed = [synth.PRED + "pos_enc.pe"]
+    if cfg["SequenceModeling"]["params"].get("fix_embed", False):
+        fixed.append(synth.SEQ + "pos_embed")   # sin-cos table of ViTEncoderV3; a learnable parameter in the other variants
+    for k in fixed:
         if k in ref_sd:
             assert torch.equal(ref_sd[k], sd[k]), k
     m.load_state_dict(sd, strict=True)
@@ -188,6 +191,36 @@ def attn_beam_case(name, H, W, B, end_bias, beam=5):
                         beam_parents=par, beam_words=wrd, beam_scores=sco)
 
 
+def encoder_variant_case(name, fix_embed, interpolate_embed, sizes):
+    """ViTEncoder (bicubic-interpolated learnable pos_embed) / ViTEncoderV2 (learnable, prefix slice), SURVEY 8 f4:
+    ctx of the live reference for several image sizes, incl. the max grid (no interpolation)."""
+    cfg = synth.make_config("TFM")
+    sp = cfg["SequenceModeling"]["params"]
+    sp["fix_embed"] = fix_embed
+    sp["interpolate_embed"] = interpolate_embed
+    sd = synth.make_state_dict(cfg, seed=1111, end_bias=None)
+    m = ref_model(cfg, sd)
+    assert type(m.seqmodeler.SequenceModeling).__name__ == ("ViTEncoder" if interpolate_embed else "ViTEncoderV2")
+    max_grid = synth.grid_hw(*cfg["max_dimension"])
+    out = {"fix_embed": np.array(fix_embed), "interpolate_embed": np.array(interpolate_embed)}
+    for (H, W) in sizes:
+        img = synth.make_images(1, H, W, seed=2024)
+        with torch.no_grad():
+            ctx_ref, shape, pad = m.forward_encoder(img)
+        ctx_or, grid, pad_o = om.encoder_forward(sd, img, pos_mode="interpolate" if interpolate_embed else "prefix",
+                                                 max_grid=max_grid)
+        d = (ctx_ref - ctx_or).abs().max().item()
+        print(f"[{name}] {H}x{W}: grid {grid} ctx ref-vs-oracle max abs diff {d:.3e}")
+        assert d <= 1e-5 and tuple(shape) == tuple(grid) and tuple(pad) == tuple(pad_o)
+        out[f"ctx_{H}x{W}"] = ctx_ref.numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+
+
+def encoder_variant_cases():
+    encoder_variant_case("vit_interp_posembed", False, True, [(64, 256), (96, 384), (192, 896)])
+    encoder_variant_case("vit_v2_posembed", False, False, [(64, 256), (96, 384)])
+
+
 def attn_beam_cases():
     attn_beam_case("attnv2_beam_64x256_full", 64, 256, 2, -1e4)    # nothing completes: live beam 0 after 151 steps
     attn_beam_case("attnv2_beam_64x256_end04", 64, 256, 3, 0.4)    # the beam shrinks at steps 1..124, the last step completes
@@ -209,3 +242,4 @@ if __name__ == "__main__":
     attn_case("attnv2_64x256_full", 64, 256, 2, -1e4)
     attn_case("attnv2_64x256_end", 64, 256, 2, 3.0)
     attn_beam_cases()
+    encoder_variant_cases()

@@ -114,9 +114,24 @@ def vit_block(sd: SD, x: torch.Tensor, i: int, heads: int) -> torch.Tensor:
     return x + F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])
 
 
-def encoder_forward(sd: SD, img: torch.Tensor, heads: int = 8, taps: Optional[dict] = None):
-    """Model.forward_encoder for Seq='ViT' + fix_embed (build_model.py:36-43,
-    build_seq.py:59-66, vit_encoder.py:249-268).  Returns (ctx, (gh,gw), (pad_W,pad_H))."""
+def interpolated_pos_embed(pos: torch.Tensor, max_grid: Tuple[int, int], height: int, width: int, patch: int = 2):
+    """ViTEncoder.interpolating_pos_embedding (vit_encoder.py:58-95): bicubic resize of the max-grid table to the
+    grid of this image; height/width = padded feature map size, scale factors (h0 + 0.1) / emb_height."""
+    eh, ew = max_grid
+    dim = pos.shape[-1]
+    h0, w0 = height // patch + 0.1, width // patch + 0.1
+    pp = F.interpolate(pos[:, 1:].reshape(1, eh, ew, dim).permute(0, 3, 1, 2), scale_factor=(h0 / eh, w0 / ew),
+                       mode="bicubic", align_corners=False)
+    assert int(h0) == pp.shape[-2] and int(w0) == pp.shape[-1]
+    return torch.cat((pos[:, 0].unsqueeze(0), pp.permute(0, 2, 3, 1).reshape(1, -1, dim)), dim=1)
+
+
+def encoder_forward(sd: SD, img: torch.Tensor, heads: int = 8, taps: Optional[dict] = None,
+                    pos_mode: str = "prefix", max_grid: Optional[Tuple[int, int]] = None):
+    """Model.forward_encoder for Seq='ViT' (build_model.py:36-43, build_seq.py:59-66).  pos_mode 'prefix' =
+    ViTEncoderV3 / ViTEncoderV2 (vit_encoder.py:205-268: first N+1 rows of the table); 'interpolate' = ViTEncoder
+    (:96-118: bicubic resize of the max-grid table unless the image has the max grid).
+    Returns (ctx, (gh,gw), (pad_W,pad_H))."""
     with torch.no_grad():
         feat = resnet_stem(sd, img, taps)
         tok, grid, pad = patch_embed(sd, feat)
@@ -124,7 +139,11 @@ def encoder_forward(sd: SD, img: torch.Tensor, heads: int = 8, taps: Optional[di
             taps["patch_embed"] = tok
         B, N, C = tok.shape
         x = torch.cat((sd[SEQ + "cls_token"].expand(B, -1, -1), tok), dim=1)
-        x = x + sd[SEQ + "pos_embed"][:, : N + 1]          # PREFIX slice (quirk Q3)
+        pos = sd[SEQ + "pos_embed"]
+        if pos_mode == "interpolate" and tuple(grid) != tuple(max_grid):
+            x = x + interpolated_pos_embed(pos, max_grid, 2 * grid[0], 2 * grid[1])
+        else:
+            x = x + pos[:, : N + 1]                          # PREFIX slice (quirk Q3); the full table at the max grid
         depth = 1 + max(int(k.split(".")[3]) for k in sd if k.startswith(SEQ + "blocks."))
         for i in range(depth):
             x = vit_block(sd, x, i, heads)

@@ -229,6 +229,25 @@ def test_attnv2_beam_batch_equals_per_image_and_model_surface(built_lib):
     assert abs(float(sc) - float(g["beam_score"][0])) <= 1e-3 * abs(float(g["beam_score"][0]))
 
 
+@pytest.mark.parametrize("case,interp,sizes", [("vit_interp_posembed", True, [(64, 256), (96, 384), (192, 896)]),
+                                               ("vit_v2_posembed", False, [(64, 256), (96, 384)])])
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_encoder_variants_match_golden(built_lib, case, interp, sizes, precision):
+    """fix_embed: False encoders: ViTEncoder resamples the learnable pos_embed bicubically per image size
+    (pos_embed_bicubic_kernel), ViTEncoderV2 takes the prefix slice; ctx against the live reference."""
+    from doc2tex_b200.engine import Engine
+    g = load_golden(case)
+    cfg = synth.make_config("TFM")
+    cfg["SequenceModeling"]["params"].update(fix_embed=False, interpolate_embed=interp)
+    sd = synth.make_state_dict(cfg, seed=1111, end_bias=None)
+    e = Engine(cfg, "cuda:0", precision=precision)
+    e.load_state_dict(sd)
+    for (H, W) in sizes:
+        ctx, _, _ = e.encode(synth.make_images(1, H, W, seed=2024).cuda())
+        assert rel_err(ctx.cpu(), torch.from_numpy(g[f"ctx_{H}x{W}"])) < REL_TOL_FP32, (H, W)
+    e.close()
+
+
 def test_model_dropin_surface(built_lib):
     """Same call surface as doc2tex.modules.build_model.Model (build_model.py:36-79, infer.py:149-161)."""
     from doc2tex_b200.modules.build_model import Model

@@ -94,6 +94,21 @@ def test_attnv2_beam_matches_reference_golden(threads, case, img):
         assert p == g["beam_parents"][img, t, :k].tolist() and w == g["beam_words"][img, t, :k].tolist()
 
 
+@pytest.mark.parametrize("case,interp", [("vit_interp_posembed", True), ("vit_v2_posembed", False)])
+def test_encoder_variants_match_reference_golden(threads, case, interp):
+    """ViTEncoder (bicubic-interpolated learnable pos_embed, vit_encoder.py:58-118) and ViTEncoderV2 (prefix slice,
+    :205-226) against the live reference's ctx."""
+    g = load_golden(case)
+    cfg = synth.make_config("TFM")
+    cfg["SequenceModeling"]["params"].update(fix_embed=False, interpolate_embed=interp)
+    sd = synth.make_state_dict(cfg, seed=1111, end_bias=None)
+    max_grid = synth.grid_hw(*cfg["max_dimension"])
+    for (H, W) in [(64, 256), (96, 384)]:
+        ctx, _, _ = om.encoder_forward(sd, synth.make_images(1, H, W, seed=2024),
+                                       pos_mode="interpolate" if interp else "prefix", max_grid=max_grid)
+        assert (ctx - torch.from_numpy(g[f"ctx_{H}x{W}"])).abs().max().item() <= 1e-5
+
+
 def test_oracle_edge_cases():
     """Quirks the engine must share: causal mask values, prefix pos-embed slice, -inf pooling pad, tie rule."""
     m = om.TFMHead.causal_mask(4)
