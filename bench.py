@@ -55,6 +55,11 @@ def parse():
                     help="concurrent row groups of a decode call (0 = engine default)")
     ap.add_argument("--decode-merge", type=int, default=0,
                     help="encoded batches handed to one decode call by the pipelined schedule (0 = default for the mode)")
+    ap.add_argument("--natural", action="store_true",
+                    help="natural decode regime: unmodified END logit, early exit as in the reference (tfm.py:138-140) "
+                         "instead of the deterministic full-length regime (SURVEY 8d)")
+    ap.add_argument("--no-overlap", action="store_true",
+                    help="encode decode_merge batches back to back on all SMs, then decode them in one call (no stage overlap)")
     ap.add_argument("--sequential", action="store_true", help="no encode/decode overlap across batches")
     a = ap.parse_args()
     if a.decode_merge <= 0:
@@ -123,7 +128,7 @@ def run_reference(args):
         return
     torch.set_num_threads(os.cpu_count())
     cfg = synth.make_config(args.head)
-    sd = synth.make_state_dict(cfg, seed=1111, suppress_end=True)
+    sd = synth.make_state_dict(cfg, seed=1111, suppress_end=not args.natural)
     n = args.ref_batch if args.mode == "greedy" else max(1, args.ref_batch // 4)
     img = synth.make_images(n, args.height, args.width, seed=2024)
     for _ in range(min(args.warmup, 1)):
@@ -153,7 +158,8 @@ def workload_config(args, batch):
     return {
         "workload": f"HybridViT (ResNet stem + 6-block ViT + "
                     f"{'4-layer TFM decoder' if args.head == 'TFM' else 'Attnv2 LSTM coverage-attention decoder'}) {dec} decode, batch {batch} per GPU, "
-                    f"{args.height}x{args.width} grayscale, max_len 150 (151 full-length steps, END suppressed), "
+                    f"{args.height}x{args.width} grayscale, max_len 150 "
+                    f"({'natural regime: early exit when every row has emitted END' if args.natural else '151 full-length steps, END suppressed'}), "
                     f"{args.precision} mode",
         "batch_per_gpu": batch, "image": [args.height, args.width], "decode": dec, "decode_steps": 151,
         "precision": args.precision, "vocab": 504 if args.head == "TFM" else 503, "head": args.head,
@@ -175,7 +181,7 @@ def run_engine(args):
 
     cfg = synth.make_config(args.head, beam_size=(args.beam if args.mode == "beam" else 1))
     cfg["engine"] = {"precision": args.precision, "use_graphs": not args.no_graphs}
-    sd = synth.make_state_dict(cfg, seed=1111, suppress_end=True)
+    sd = synth.make_state_dict(cfg, seed=1111, suppress_end=not args.natural)
     model = Model(cfg)
     model.load_state_dict(sd, strict=True)
     model = model.to(dev)
@@ -192,7 +198,9 @@ def run_engine(args):
 
     from doc2tex_b200.pipeline import PipelinedRecognizer
     pipe = PipelinedRecognizer(eng, args.mode, args.beam, T, encoder_sms=None if args.sequential else args.encoder_sms,
-                               decode_merge=1 if args.sequential else args.decode_merge)
+                               decode_merge=1 if args.sequential else args.decode_merge, overlap=not args.no_overlap)
+    if args.no_overlap and not args.sequential:
+        eng.set_option("encoder_sms", torch.cuda.get_device_properties(dev).multi_processor_count)
 
     def gather(res):
         return d2dist.gather_results(res["ids"], res.get("lens"), res.get("scores"), n_total=B * world)
@@ -266,7 +274,7 @@ def run_engine(args):
     enc_ms /= args.steps
     dec_ms /= args.steps
     seq_ms = enc_ms + dec_ms
-    if not args.sequential:
+    if not args.sequential and not args.no_overlap:
         eng.set_option("encoder_sms", args.encoder_sms)
     # end to end through the public API with host buffers
     run_steps(pipe.decode_merge, True)
@@ -319,6 +327,8 @@ def run_engine(args):
         "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16x3": "bf16x3", "bf16": "bf16"}[args.precision],
         "data": "synthetic", "config": dict(workload_config(args, B), schedule=(
             "sequential" if args.sequential else
+            (f"grouped: {args.decode_merge} batches encoded back to back on all SMs, then decoded in one call; one batch "
+             f"alone takes {seq_ms:.1f} ms") if args.no_overlap else
             f"pipelined: encode on {args.encoder_sms} SMs overlaps the decode of the previous batches, {args.decode_merge} encoded "
             f"batch(es) per decode call; one batch alone takes {seq_ms:.1f} ms")),
         "clocks": clocks,

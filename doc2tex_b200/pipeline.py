@@ -24,9 +24,13 @@ from .engine import Engine
 class PipelinedRecognizer:
     def __init__(self, engine: Engine, mode: str = "greedy", beam: int = 5, max_steps: Optional[int] = None,
                  encoder_sms: Optional[int] = None, is_test: bool = True, return_logits: bool = False,
-                 decode_merge: int = 1):
+                 decode_merge: int = 1, overlap: bool = True):
         self.eng, self.mode, self.beam, self.max_steps = engine, mode, beam, max_steps
         self.decode_merge = max(1, int(decode_merge))
+        # overlap=False: encode the batches of a group back to back on all SMs, then decode them in one call — no
+        # concurrency between the stages (they slow each other down by about what the overlap saves), only the
+        # amortisation of the decode chain over more rows
+        self.overlap = overlap
         self.is_test, self.return_logits = is_test, return_logits
         self.enc_stream = torch.cuda.Stream(device=engine.device)
         self.timing = None   # set to [] to collect (encode_ms, decode_ms) per batch (CUDA events; adds two syncs per batch)
@@ -47,6 +51,19 @@ class PipelinedRecognizer:
         main = torch.cuda.current_stream(self.eng.device)
         M = self.decode_merge
         queue = []   # encoded (or being encoded) batches not yet decoded
+        if not self.overlap:
+            for img in batches:
+                x = img.to(self.eng.device, non_blocking=True)
+                ctx, _, _ = self.eng.encode(x)
+                done = torch.cuda.Event()
+                done.record(main)
+                queue.append((ctx, done, None))
+                if len(queue) >= M:
+                    yield from self._finish(queue[:M], main)
+                    del queue[:M]
+            if queue:
+                yield from self._finish(queue, main)
+            return
         for img in batches:
             self.enc_stream.wait_stream(main)
             with torch.cuda.stream(self.enc_stream):
