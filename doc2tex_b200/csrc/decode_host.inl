@@ -52,9 +52,15 @@ int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long 
   static const int split_env = getenv("D2T_ATTN_SPLIT") ? atoi(getenv("D2T_ATTN_SPLIT")) : 0;
   // few rows: the loads in flight per SM, not the bandwidth, bound the kernel -> two warps per (row, head)
   const int split = split_env > 0 ? split_env : (R <= 4 * e->num_sms && heads == 8 ? 2 : 1);
-  auto kern = split >= 2 && heads == 8 ? decode_attention_kernel<32, 2> : decode_attention_kernel<32, 1>;
-  CUDA_TRY(e, launch_kernel(kern, dim3(R), dim3(heads * 32 * (split >= 2 && heads == 8 ? 2 : 1)), 0, s, q, D, kv, row_stride, 2 * D,
-                            anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
+  static const int hb_env = getenv("D2T_ATTN_HB") ? atoi(getenv("D2T_ATTN_HB")) : 2;
+  if (split >= 2 && heads == 8 && hb_env >= 2) {
+    CUDA_TRY(e, launch_kernel(decode_attention_kernel<32, 2, 2>, dim3(R * 2), dim3(256), 0, s, q, D, kv, row_stride, 2 * D,
+                              anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
+  } else {
+    auto kern = split >= 2 && heads == 8 ? decode_attention_kernel<32, 2> : decode_attention_kernel<32, 1>;
+    CUDA_TRY(e, launch_kernel(kern, dim3(R), dim3(heads * 32 * (split >= 2 && heads == 8 ? 2 : 1)), 0, s, q, D, kv, row_stride, 2 * D,
+                              anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
+  }
   e->launches += 1;
   return 0;
 }

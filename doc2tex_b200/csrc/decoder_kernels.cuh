@@ -62,8 +62,10 @@ __global__ void embed_tokens_kernel(const int* __restrict__ tokens, int tok_ld, 
 // SPLIT > 1: the keys of a (row, head) are dealt to SPLIT warps of the block (8-key groups, round robin) and their
 // online-softmax states are merged through shared memory.  At small batch the kernel is bound by the loads each SM
 // has in flight, not by bandwidth: twice the warps per row = twice the bytes in flight.
-template <int HD, int SPLIT = 1>
-__global__ void __launch_bounds__(256 * SPLIT)
+// HB > 1: the heads of a row are spread over HB blocks (grid = rows x HB, 8 / HB heads each): 512 quarter-size blocks
+// balance over 148 SMs better than 256 full ones.
+template <int HD, int SPLIT = 1, int HB = 1>
+__global__ void __launch_bounds__(256 * SPLIT / HB)
 decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kv,
                         long long row_stride, int pos_stride, const int* __restrict__ anc,
                         long long anc_parity_stride, int anc_ld, int rows_per_src,
@@ -72,10 +74,11 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __res
   static_assert(HD == 32, "8 lanes x float4 per head slice");
   pdl_wait();      // PDL: everything above overlapped the predecessor
   pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
-  const int r = blockIdx.x;
+  const int r = HB == 1 ? blockIdx.x : blockIdx.x / HB;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nheads = SPLIT == 1 ? 0 : blockDim.x / (32 * SPLIT);
-  const int h = SPLIT == 1 ? wid : wid % nheads, sp = SPLIT == 1 ? 0 : wid / nheads;
+  const int nheads = blockDim.x / (32 * SPLIT);                       // heads of this block
+  const int hl = SPLIT == 1 ? wid : wid % nheads, sp = SPLIT == 1 ? 0 : wid / nheads;
+  const int h = HB == 1 ? hl : (blockIdx.x % HB) * nheads + hl;
   const int g = lane >> 3, c = (lane & 7) * 4;
   const int t = step ? *step : 0;
   const int n_keys = n_fixed > 0 ? n_fixed : t + 1;
@@ -135,7 +138,7 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __res
   if constexpr (SPLIT > 1) {
     __shared__ float s_part[8 * (SPLIT - 1) * 36];   // [head][split - 1][max, sum, pad, pad, acc[32]]
     if (sp > 0) {
-      float* pp = s_part + (h * (SPLIT - 1) + sp - 1) * 36;
+      float* pp = s_part + (hl * (SPLIT - 1) + sp - 1) * 36;
       if (g == 0) *reinterpret_cast<float4*>(pp + 4 + c) = acc;
       if (lane == 0) { pp[0] = gm; pp[1] = sum; }
     }
@@ -143,12 +146,12 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __res
     if (sp > 0) return;
     float M = gm;
 #pragma unroll
-    for (int q = 0; q < SPLIT - 1; ++q) M = fmaxf(M, s_part[(h * (SPLIT - 1) + q) * 36]);
+    for (int q = 0; q < SPLIT - 1; ++q) M = fmaxf(M, s_part[(hl * (SPLIT - 1) + q) * 36]);
     const float w0 = (gm == -INFINITY) ? 0.f : expf(gm - M);
     sum *= w0; acc.x *= w0; acc.y *= w0; acc.z *= w0; acc.w *= w0;
 #pragma unroll
     for (int q = 0; q < SPLIT - 1; ++q) {
-      const float* pp = s_part + (h * (SPLIT - 1) + q) * 36;
+      const float* pp = s_part + (hl * (SPLIT - 1) + q) * 36;
       const float wq = (pp[0] == -INFINITY) ? 0.f : expf(pp[0] - M);
       const float4 a = *reinterpret_cast<const float4*>(pp + 4 + c);
       sum = fmaf(wq, pp[1], sum);
