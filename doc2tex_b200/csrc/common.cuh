@@ -41,6 +41,7 @@ struct ConvGemm {
   // CTA and stored (without activation; bias / residual only in slice 0) at out + s * split_stride; the consumer (the
   // LayerNorm kernel) adds the slices.  A tcgen05.mma retires every ~90 ns whatever its N, so a K=1024 bf16x3 projection
   // is 192 serial MMAs = 17 us on one CTA; eight slices take 2 us each.
+  int out2_bf16;           // out2 (the KV-cache slot) holds bf16 elements (single-pass bf16 mode): same element offsets
   int k_splits;            // 0 / 1 = no split
   long long split_stride;  // elements between partial outputs
   // optional bf16 hi/lo NHWC planes of the INPUT activation (cp.async-fed A operand of conv_gemm_tc3_kernel)

@@ -11,6 +11,7 @@ constexpr int POLL_EVERY = 8;
 
 struct TfmBuffers {
   float *crosskv = nullptr, *selfkv = nullptr, *crosskv_tmp = nullptr;
+  float* crosskv_f32 = nullptr;   // bf16 KV mode: fp32 staging of one layer's cross K/V projection
   float *x = nullptr, *x2 = nullptr, *q = nullptr, *att = nullptr, *ffn = nullptr, *logits = nullptr;
   int *tokens = nullptr, *anc = nullptr, *n_live = nullptr, *n_done = nullptr, *finished = nullptr;
   int *done_seq = nullptr, *done_len = nullptr, *ended = nullptr, *counters = nullptr, *trace = nullptr;
@@ -44,6 +45,13 @@ int pool_get(d2t_engine* e, T** out, size_t n) {
 
 int dec_linear(d2t_engine* e, ConvGemm p, cudaStream_t s) { return run_contraction(e, p, nullptr, e->cfg.precision, s); }
 
+// KV caches are fp32 except in the single-pass bf16 mode, where K/V are stored as bf16 (half the attention traffic;
+// the operands of every projection are bf16 there anyway).  Buffers keep their float* type; element offsets are equal.
+bool kv_is_bf16(const d2t_engine* e) {
+  static const bool off = getenv("D2T_KV_BF16") && atoi(getenv("D2T_KV_BF16")) == 0;
+  return e->cfg.precision == D2T_PREC_BF16 && !off;
+}
+
 int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long row_stride, const int* anc,
                       long long anc_parity, int anc_ld, int rows_per_src, const int* step, int n_fixed,
                       float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int R, cudaStream_t s) {
@@ -53,7 +61,16 @@ int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long 
   // few rows: the loads in flight per SM, not the bandwidth, bound the kernel -> two warps per (row, head)
   const int split = split_env > 0 ? split_env : (R <= 4 * e->num_sms && heads == 8 ? 2 : 1);
   static const int hb_env = getenv("D2T_ATTN_HB") ? atoi(getenv("D2T_ATTN_HB")) : 2;
-  if (split >= 2 && heads == 8 && hb_env >= 2) {
+  if (kv_is_bf16(e)) {
+    const __nv_bfloat16* kv16 = reinterpret_cast<const __nv_bfloat16*>(kv);
+    if (split >= 2 && heads == 8) {
+      CUDA_TRY(e, launch_kernel(decode_attention_kernel<32, 2, 2, __nv_bfloat16>, dim3(R * 2), dim3(256), 0, s, q, D, kv16, row_stride,
+                                2 * D, anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
+    } else {
+      CUDA_TRY(e, launch_kernel(decode_attention_kernel<32, 1, 1, __nv_bfloat16>, dim3(R), dim3(heads * 32), 0, s, q, D, kv16,
+                                row_stride, 2 * D, anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
+    }
+  } else if (split >= 2 && heads == 8 && hb_env >= 2) {
     CUDA_TRY(e, launch_kernel(decode_attention_kernel<32, 2, 2>, dim3(R * 2), dim3(256), 0, s, q, D, kv, row_stride, 2 * D,
                               anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
   } else {
@@ -245,12 +262,15 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
   tl.mark("embed");
   for (int l = 0; l < c.dec_layers; ++l) {
     const std::string p = PRED + "model.layers." + std::to_string(l) + ".";
-    float* selfkv = b.selfkv + (size_t)l * R * T * 2 * D;
-    const float* crosskv = b.crosskv + (size_t)l * B * ntok * 2 * D;
+    // element offset of layer l; a bf16 cache addresses 2-byte elements from the same base
+    const size_t kvdiv = kv_is_bf16(e) && !cluster ? 2 : 1;
+    float* selfkv = b.selfkv + (size_t)l * R * T * 2 * D / kvdiv;
+    const float* crosskv = b.crosskv + (size_t)l * B * ntok * 2 * D / kvdiv;
     // self-attention: in_proj (q -> b.q, k|v -> cache slot t), attention over the prefix, out_proj + residual, norm1
     {
       ConvGemm g = linear_params(b.x, e->dev[p + "self_attn.in_proj_weight"], e->dev[p + "self_attn.in_proj_bias"], b.q, R, 3 * D, D);
       g.ldc = D; g.n_split = D; g.out2 = selfkv; g.ldc2 = T * 2 * D; g.dyn = step; g.dyn_mul2 = 2 * D;
+      g.out2_bf16 = kv_is_bf16(e) ? 1 : 0;
       from_x(g);
       if (l == 1) g.dbg = b.dbg;
       if ((rc = dec_linear(e, g, s))) return rc;
@@ -343,6 +363,7 @@ int alloc_group(d2t_engine* e, TfmGroup& grp, int ntok, int beam, int T, bool wa
   if ((rc = pool_get(e, &b.crosskv, (size_t)nl * B * ntok * 2 * D))) return rc;
   if ((rc = pool_get(e, &b.selfkv, (size_t)nl * R * T * 2 * D))) return rc;
   if (cluster_step_active(e) && (rc = pool_get(e, &b.crosskv_tmp, (size_t)B * ntok * 2 * D))) return rc;
+  if (!cluster_step_active(e) && kv_is_bf16(e) && (rc = pool_get(e, &b.crosskv_f32, (size_t)B * ntok * 2 * D))) return rc;
   if ((rc = pool_get(e, &b.x, (size_t)R * D))) return rc;
   b.x2_parts = 8;
   if ((rc = pool_get(e, &b.x2, (size_t)b.x2_parts * R * D))) return rc;
@@ -464,11 +485,18 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
   rc = for_each_group_parallel(e, groups, s, [&](TfmGroup& grp, cudaStream_t gs) -> int {
     for (int l = 0; l < nl; ++l) {
       const std::string p = PRED + "model.layers." + std::to_string(l) + ".multihead_attn.";
-      float* dst = grp.b.crosskv + (size_t)l * grp.Bg * ntok * 2 * D;
+      float* dst = grp.b.crosskv + (size_t)l * grp.Bg * ntok * 2 * D / (grp.b.crosskv_f32 ? 2 : 1);
       ConvGemm g = linear_params(ctx + (size_t)grp.B0 * ntok * D, e->dev[p + "in_proj_weight"] + (size_t)D * D,
-                                 e->dev[p + "in_proj_bias"] + D, grp.b.crosskv_tmp ? grp.b.crosskv_tmp : dst,
+                                 e->dev[p + "in_proj_bias"] + D,
+                                 grp.b.crosskv_tmp ? grp.b.crosskv_tmp : (grp.b.crosskv_f32 ? grp.b.crosskv_f32 : dst),
                                  grp.Bg * ntok, 2 * D, D);
       if (int r = dec_linear(e, g, gs)) return r;
+      if (grp.b.crosskv_f32) {   // bf16 KV cache
+        const long long n = (long long)grp.Bg * ntok * 2 * D;
+        f32_to_bf16_kernel<<<grid_for(n, 256, e->num_sms), 256, 0, gs>>>(grp.b.crosskv_f32, reinterpret_cast<__nv_bfloat16*>(dst), n);
+        e->launches += 1;
+        CUDA_TRY(e, cudaGetLastError());
+      }
       if (grp.b.crosskv_tmp) {   // cluster step: head-major [image][head][tok][K|V]
         const long long total4 = (long long)grp.Bg * ntok * 128;
         repack_cross_kv_kernel<<<grid_for(total4, 256, e->num_sms), 256, 0, gs>>>(grp.b.crosskv_tmp, dst, grp.Bg, ntok);
@@ -495,7 +523,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
       const void* ptrs[] = {b.crosskv, b.selfkv, b.x, b.x2, b.q, b.att, b.ffn, b.logits, b.counters, b.tokens, b.anc,
                             b.scores, b.n_live, b.n_done, b.finished, b.done_seq, b.done_len, b.done_score, b.trace,
                             b.trace_score, b.ended, b.ids, b.logits_out, b.dbg, b.x_hi, b.x_lo, b.att_hi, b.att_lo, b.ffn_hi, b.ffn_lo,
-                            b.crosskv_tmp};
+                            b.crosskv_tmp, b.crosskv_f32};
       for (const void* q : ptrs) key.push_back((long long)(uintptr_t)q);
     }
     for (auto& g : e->graphs) if (g.key == key) { exec = g.exec; nodes = g.nodes; }

@@ -62,11 +62,20 @@ __global__ void embed_tokens_kernel(const int* __restrict__ tokens, int tok_ld, 
 // SPLIT > 1: the keys of a (row, head) are dealt to SPLIT warps of the block (8-key groups, round robin) and their
 // online-softmax states are merged through shared memory.  At small batch the kernel is bound by the loads each SM
 // has in flight, not by bandwidth: twice the warps per row = twice the bytes in flight.
+// four consecutive K / V channels of one lane: fp32 cache (16-byte load) or bf16 cache (8-byte load, single-pass bf16 mode)
+__device__ __forceinline__ float4 kv_load4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 kv_load4(const __nv_bfloat16* p) {
+  const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(&u.x), b = *reinterpret_cast<const __nv_bfloat162*>(&u.y);
+  const float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+  return make_float4(fa.x, fa.y, fb.x, fb.y);
+}
+
 // HB > 1: the heads of a row are spread over HB blocks (grid = rows x HB, 8 / HB heads each): 512 quarter-size blocks
 // balance over 148 SMs better than 256 full ones.
-template <int HD, int SPLIT = 1, int HB = 1>
+template <int HD, int SPLIT = 1, int HB = 1, typename KV = float>
 __global__ void __launch_bounds__(256 * SPLIT / HB)
-decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ kv,
+decode_attention_kernel(const float* __restrict__ q, int ldq, const KV* __restrict__ kv,
                         long long row_stride, int pos_stride, const int* __restrict__ anc,
                         long long anc_parity_stride, int anc_ld, int rows_per_src,
                         const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
@@ -87,7 +96,7 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __res
   const float scale = rsqrtf((float)HD);
   float4 q4 = *reinterpret_cast<const float4*>(q + (size_t)r * ldq + h * HD + c);
   q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
-  const float* kbase = kv + h * HD + c;
+  const KV* kbase = kv + h * HD + c;
 
   float mx = -INFINITY, sum = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -97,12 +106,12 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __res
     const bool has1 = j1 < n_keys;
     const int s0 = anc_r ? src_base + anc_r[j0] : src_base;
     const int s1 = has1 ? (anc_r ? src_base + anc_r[j1] : src_base) : s0;
-    const float* p0 = kbase + (size_t)s0 * row_stride + (size_t)j0 * pos_stride;
-    const float* p1 = kbase + (size_t)s1 * row_stride + (size_t)(has1 ? j1 : j0) * pos_stride;
-    const float4 k0 = __ldg(reinterpret_cast<const float4*>(p0));
-    const float4 k1 = __ldg(reinterpret_cast<const float4*>(p1));
-    const float4 v0 = __ldg(reinterpret_cast<const float4*>(p0 + D));
-    const float4 v1 = __ldg(reinterpret_cast<const float4*>(p1 + D));
+    const KV* p0 = kbase + (size_t)s0 * row_stride + (size_t)j0 * pos_stride;
+    const KV* p1 = kbase + (size_t)s1 * row_stride + (size_t)(has1 ? j1 : j0) * pos_stride;
+    const float4 k0 = kv_load4(p0);
+    const float4 k1 = kv_load4(p1);
+    const float4 v0 = kv_load4(p0 + D);
+    const float4 v1 = kv_load4(p1 + D);
     float d0 = fmaf(q4.x, k0.x, fmaf(q4.y, k0.y, fmaf(q4.z, k0.z, q4.w * k0.w)));
     float d1 = fmaf(q4.x, k1.x, fmaf(q4.y, k1.y, fmaf(q4.z, k1.z, q4.w * k1.w)));
 #pragma unroll
@@ -174,6 +183,11 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const float* __res
       }
     }
   }
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
 }
 
 // Greedy pick: next = argmax(softmax(logits[r])) with the lowest index on ties (tfm.py:134-135, quirk Q7).

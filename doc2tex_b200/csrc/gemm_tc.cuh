@@ -386,9 +386,23 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
               v[i].z = (v[i].z - mean) * rstd * lw.z + lb.z; v[i].w = (v[i].w - mean) * rstd * lw.w + lb.w;
             }
           }
+          if (second && p.out2_bf16) {   // bf16 KV cache: same element offsets, 2-byte elements
+            __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(p.out2) + (dst - p.out2);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (m_first + 4 * i < M) {
+                const __nv_bfloat162 lo2 = __floats2bfloat162_rn(v[i].x, v[i].y), hi2 = __floats2bfloat162_rn(v[i].z, v[i].w);
+                uint2 pk;
+                pk.x = *reinterpret_cast<const uint32_t*>(&lo2);
+                pk.y = *reinterpret_cast<const uint32_t*>(&hi2);
+                *reinterpret_cast<uint2*>(dst16 + i * dst_step) = pk;
+              }
+            }
+          } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             if (m_first + 4 * i < M) *reinterpret_cast<float4*>(dst + i * dst_step) = v[i];
+          }
           if (planes) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
