@@ -61,6 +61,25 @@ int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long 
   // few rows: the loads in flight per SM, not the bandwidth, bound the kernel -> two warps per (row, head)
   const int split = split_env > 0 ? split_env : (R <= 4 * e->num_sms && heads == 8 ? 2 : 1);
   static const int hb_env = getenv("D2T_ATTN_HB") ? atoi(getenv("D2T_ATTN_HB")) : 2;
+  // beam search: the hypotheses of an image share the encoder memory and most of their prefixes.  The grouped kernel fetches
+  // every shared record once — and is measured 2x SLOWER than the per-row kernel (self 68 vs 36 us, cross 47 vs 24 us at
+  // 1 280 rows): this attention is bound by issue / latency per warp (125 registers -> 16 warps per SM, five dependent
+  // online-softmax updates per key), not by the L2-served traffic it saves.  Off by default (option "attn_group").
+  if (e->attn_group && rows_per_src == 5 && heads == 8 && R % 5 == 0 && anc_ld <= BEAM_ATT_ANC_LD && n_fixed < 1024) {
+    const int B = R / 5;
+    const int src_mul = anc ? 5 : 1;
+    cudaError_t st;
+    if (kv_is_bf16(e))
+      st = launch_kernel(decode_attention_beam_kernel<32, 5, __nv_bfloat16>, dim3(B * 4), dim3(256), 0, s, q, D,
+                         reinterpret_cast<const __nv_bfloat16*>(kv), row_stride, 2 * D, anc, anc_parity, anc_ld, src_mul, step,
+                         n_fixed, out, D, out_hi, out_lo);
+    else
+      st = launch_kernel(decode_attention_beam_kernel<32, 5, float>, dim3(B * 4), dim3(256), 0, s, q, D, kv, row_stride, 2 * D,
+                         anc, anc_parity, anc_ld, src_mul, step, n_fixed, out, D, out_hi, out_lo);
+    CUDA_TRY(e, st);
+    e->launches += 1;
+    return 0;
+  }
   if (kv_is_bf16(e)) {
     const __nv_bfloat16* kv16 = reinterpret_cast<const __nv_bfloat16*>(kv);
     if (split >= 2 && heads == 8) {

@@ -185,6 +185,157 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const KV* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Beam-grouped single-query attention: the NB hypotheses of one image are processed TOGETHER, so a key/value record
+// that several of them share is fetched once.  Cross-attention: all NB beams read the same encoder memory (1 fetch
+// instead of NB).  Self-attention: position j of beam b lives in physical slot anc[b][j]; beams with a common prefix
+// name the same slot, the first of them ("leader") fetches it and every beam naming that slot is updated from the
+// registers.  The per-row kernel above gets the same sharing only through L2 (NB fetches per record).
+//   grid = images x 4 (two heads per block), block = 2 heads x 4 key splits; a quarter warp owns one key per iteration
+//   (keys j = g + 4*split mod 16), one online-softmax state per beam; splits are merged through shared memory.
+// ---------------------------------------------------------------------------------------------
+constexpr int BEAM_ATT_ANC_LD = 160;
+
+template <int HD, int NB, typename KV>
+__global__ void __launch_bounds__(256)
+decode_attention_beam_kernel(const float* __restrict__ q, int ldq, const KV* __restrict__ kv, long long row_stride,
+                             int pos_stride, const int* __restrict__ anc, long long anc_parity_stride, int anc_ld,
+                             int src_mul /* NB: self (slot = img*NB + anc), 1: cross (slot = img) */,
+                             const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
+                             __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  static_assert(HD == 32, "8 lanes x float4 per head slice");
+  constexpr int SPLIT = 4, HPB = 2;
+  pdl_wait();
+  pdl_trigger();
+  __shared__ int s_anc[NB * BEAM_ATT_ANC_LD];
+  __shared__ float s_part[HPB * (SPLIT - 1) * NB * 36];
+  const int img = blockIdx.x >> 2;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int hl = wid & (HPB - 1), sp = wid >> 1;
+  const int h = (blockIdx.x & 3) * HPB + hl;
+  const int g = lane >> 3, c = (lane & 7) * 4;
+  const int t = step ? *step : 0;
+  const int n_keys = n_fixed > 0 ? n_fixed : t + 1;
+  const int r0 = img * NB;
+  if (anc) {
+    const int* a0 = anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)r0 * anc_ld;
+    for (int i = threadIdx.x; i < NB * n_keys; i += blockDim.x) {
+      const int b = i / n_keys, j = i - b * n_keys;
+      s_anc[b * BEAM_ATT_ANC_LD + j] = a0[(size_t)b * anc_ld + j];
+    }
+    __syncthreads();
+  }
+  const float scale = rsqrtf((float)HD);
+  float4 q4[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    q4[b] = *reinterpret_cast<const float4*>(q + (size_t)(r0 + b) * ldq + h * HD + c);
+    q4[b].x *= scale; q4[b].y *= scale; q4[b].z *= scale; q4[b].w *= scale;
+  }
+  const KV* kbase = kv + (size_t)img * src_mul * row_stride + h * HD + c;
+  float mx[NB], sum[NB];
+  float4 acc[NB];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) { mx[b] = -INFINITY; sum[b] = 0.f; acc[b] = make_float4(0.f, 0.f, 0.f, 0.f); }
+  const unsigned gmask = 0xFFu << (g * 8);
+  for (int j = g + 4 * sp; j < n_keys; j += 4 * SPLIT) {
+    int slot[NB];
+    bool lead[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      slot[b] = anc ? s_anc[b * BEAM_ATT_ANC_LD + j] : 0;
+      lead[b] = true;
+#pragma unroll
+      for (int e = 0; e < b; ++e) lead[b] = lead[b] && (slot[e] != slot[b]);
+    }
+    float4 kk[NB], vv[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (lead[b]) {
+        const KV* ptr = kbase + (size_t)slot[b] * row_stride + (size_t)j * pos_stride;
+        kk[b] = kv_load4(ptr);
+        vv[b] = kv_load4(ptr + D);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+      if (!lead[b]) continue;
+#pragma unroll
+      for (int v = b; v < NB; ++v) {
+        if (slot[v] != slot[b]) continue;
+        float d = fmaf(q4[v].x, kk[b].x, fmaf(q4[v].y, kk[b].y, fmaf(q4[v].z, kk[b].z, q4[v].w * kk[b].w)));
+        d += __shfl_xor_sync(gmask, d, 1);
+        d += __shfl_xor_sync(gmask, d, 2);
+        d += __shfl_xor_sync(gmask, d, 4);
+        const float nm = fmaxf(mx[v], d);
+        const float corr = expf(mx[v] - nm), e0 = expf(d - nm);   // corr = 0 on the first key of this state
+        sum[v] = sum[v] * corr + e0;
+        acc[v].x = fmaf(e0, vv[b].x, acc[v].x * corr); acc[v].y = fmaf(e0, vv[b].y, acc[v].y * corr);
+        acc[v].z = fmaf(e0, vv[b].z, acc[v].z * corr); acc[v].w = fmaf(e0, vv[b].w, acc[v].w * corr);
+        mx[v] = nm;
+      }
+    }
+  }
+  __syncwarp();
+  // merge the four quarter-warp states of every beam, then the key splits through shared memory
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    float gm = fmaxf(mx[b], __shfl_xor_sync(0xffffffffu, mx[b], 8));
+    gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 16));
+    const float sc = (mx[b] == -INFINITY) ? 0.f : expf(mx[b] - gm);
+    sum[b] *= sc; acc[b].x *= sc; acc[b].y *= sc; acc[b].z *= sc; acc[b].w *= sc;
+#pragma unroll
+    for (int o = 8; o < 32; o <<= 1) {
+      sum[b] += __shfl_xor_sync(0xffffffffu, sum[b], o);
+      acc[b].x += __shfl_xor_sync(0xffffffffu, acc[b].x, o);
+      acc[b].y += __shfl_xor_sync(0xffffffffu, acc[b].y, o);
+      acc[b].z += __shfl_xor_sync(0xffffffffu, acc[b].z, o);
+      acc[b].w += __shfl_xor_sync(0xffffffffu, acc[b].w, o);
+    }
+    mx[b] = gm;
+    if (sp > 0) {
+      float* pp = s_part + (((hl * (SPLIT - 1) + sp - 1) * NB) + b) * 36;
+      if (g == 0) *reinterpret_cast<float4*>(pp + 4 + c) = acc[b];
+      if (lane == 0) { pp[0] = gm; pp[1] = sum[b]; }
+    }
+  }
+  __syncthreads();
+  if (sp > 0) return;
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    float M = mx[b];
+#pragma unroll
+    for (int qd = 0; qd < SPLIT - 1; ++qd) M = fmaxf(M, s_part[(((hl * (SPLIT - 1) + qd) * NB) + b) * 36]);
+    const float w0 = (mx[b] == -INFINITY) ? 0.f : expf(mx[b] - M);
+    float sm = sum[b] * w0;
+    float4 a = make_float4(acc[b].x * w0, acc[b].y * w0, acc[b].z * w0, acc[b].w * w0);
+#pragma unroll
+    for (int qd = 0; qd < SPLIT - 1; ++qd) {
+      const float* pp = s_part + (((hl * (SPLIT - 1) + qd) * NB) + b) * 36;
+      const float wq = (pp[0] == -INFINITY) ? 0.f : expf(pp[0] - M);
+      const float4 pa = *reinterpret_cast<const float4*>(pp + 4 + c);
+      sm = fmaf(wq, pp[1], sm);
+      a.x = fmaf(wq, pa.x, a.x); a.y = fmaf(wq, pa.y, a.y); a.z = fmaf(wq, pa.z, a.z); a.w = fmaf(wq, pa.w, a.w);
+    }
+    if (g == 0) {
+      const float inv = 1.0f / sm;
+      const float4 o4 = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
+      const size_t off = (size_t)(r0 + b) * D + h * HD + c;
+      *reinterpret_cast<float4*>(out + off) = o4;
+      if (out_hi) {
+        const float f[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          __nv_bfloat16 hi, lo;
+          split_bf16(f[u], hi, lo);
+          out_hi[off + u] = hi;
+          if (out_lo) out_lo[off + u] = lo;
+        }
+      }
+    }
+  }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);

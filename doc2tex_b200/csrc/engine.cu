@@ -117,6 +117,7 @@ struct d2t_engine {
   bool time_conv = false;   // option "time_conv": bracket layer3.1.conv1 with events (d2t_debug_conv_time)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
   double conv_flops = 0.0;
+  bool attn_group = false;  // D2T_ATTN_GROUP=1 / option "attn_group": beam-grouped decode attention (measured slower, off)
   int split_k = 1;       // D2T_SPLIT_K / option "split_k": 0 = never, 1 = auto split-K of the LayerNorm-fed decode projections
   bool fuse_ln = false;  // D2T_FUSE_LN=1: cluster-fused residual+LayerNorm epilogue (measured slower than the stand-alone
                          // LayerNorm kernel on B200: cluster launch + DSMEM exchange cost more than the saved launch)
@@ -491,6 +492,7 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   cudaSetDevice(device);
   if (const char* v = getenv("D2T_DECODE_GROUPS")) e->decode_groups = atoi(v);
   if (const char* v = getenv("D2T_SPLIT_K")) e->split_k = atoi(v);
+  if (const char* v = getenv("D2T_ATTN_GROUP")) e->attn_group = atoi(v) != 0;
   if (const char* v = getenv("D2T_CLUSTER_STEP")) e->use_cluster_step = atoi(v) != 0;
   if (cudaMallocHost(&e->h_counters, 4 * D2T_MAX_GROUPS * sizeof(int)) != cudaSuccess) {
     g_create_error = "cudaMallocHost failed";
@@ -777,6 +779,8 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
     e->pos_grid_w = value;
   } else if (k == "time_conv") {
     e->time_conv = value != 0;
+  } else if (k == "attn_group") {
+    e->attn_group = value != 0;
   } else if (k == "split_k") {
     e->split_k = value;
   } else if (k == "cluster_step") {

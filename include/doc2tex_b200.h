@@ -155,7 +155,7 @@ int d2t_decode_attn_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, i
  * "decode_groups": concurrent row groups of one decode call (parallel CUDA-graph branches, 0/1 = one chain);
  * "split_k": split-K of the LayerNorm-fed decode projections (default 1); "cluster_step": 1 = the experimental
  * cluster-resident decode step kernel (decode_cluster.cuh) instead of the launch-per-sublayer chain;
- * "time_conv": see d2t_debug_conv_time.
+ * "attn_group": 1 = beam-grouped decode attention (experimental, measured slower); "time_conv": see d2t_debug_conv_time.
  */
 int d2t_set_option(d2t_engine* e, const char* key, int value);
 

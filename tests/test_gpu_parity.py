@@ -321,6 +321,22 @@ def test_merged_decode_schedule_equals_sequential(built_lib, merge):
     e.set_option("encoder_sms", 148)
 
 
+def test_grouped_beam_attention_equals_per_row_kernel(built_lib):
+    """Option attn_group: the five hypotheses of an image attend together (shared records fetched once).  Same beams,
+    lengths and traces as the per-row kernel; scores within fp32 rounding (different merge order)."""
+    e = engine_for("TFM", 1.5, "bf16x3")
+    ctx, _, _ = e.encode(synth.make_images(6, 64, 256, seed=55).cuda())
+    b0 = e.decode_beam(ctx, 5, trace=True)
+    e.set_option("attn_group", 1)
+    try:
+        b1 = e.decode_beam(ctx, 5, trace=True)
+    finally:
+        e.set_option("attn_group", 0)
+    assert b0[3] == b1[3] and torch.equal(b0[0], b1[0]) and torch.equal(b0[1], b1[1])
+    assert torch.equal(b0[4][:, :b0[3]], b1[4][:, :b1[3]])
+    assert float((b0[2] - b1[2]).abs().max()) <= 1e-4 * float(b0[2].abs().max())
+
+
 @pytest.mark.parametrize("groups", [2, 3, 8])
 def test_decode_row_groups_equal_single_chain(built_lib, groups):
     """decode_groups cuts one decode call into concurrent image slices (side streams, one graph with parallel
