@@ -528,6 +528,7 @@ int d2t_destroy(d2t_engine* e) {
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
   for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (auto& ev : e->conv_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   for (void* p : e->owned) cudaFree(p);
   e->enc_pool.destroy();
   e->dec_pool.destroy();
@@ -570,6 +571,7 @@ int d2t_finalize_weights(d2t_engine* e) {
   for (void* p : e->owned) cudaFree(p);
   e->owned.clear(); e->conv.clear(); e->dev.clear(); e->tcw.clear(); e->tc3.clear();
   for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (auto& ev : e->conv_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
   e->graphs.clear();
   const d2t_config& c = e->cfg;
   const int C = c.stem_channels, D = c.hidden;
