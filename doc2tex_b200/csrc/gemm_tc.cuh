@@ -252,7 +252,25 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
   __syncthreads();
   tc::tcgen05_after_sync();
   const uint32_t tmem_base = *tmem_slot_gen;
-  pdl_wait();      // everything above (barrier init, TMEM alloc, descriptor prefetch) overlapped the previous kernel
+  // TMA-fed-A variant (one tile per CTA): the weight tiles do not depend on the previous kernel, so their loads for the
+  // first stages are issued BEFORE the dependency wait and overlap the predecessor's tail; the activation tiles follow.
+  int w_prefetched = 0;
+  if constexpr (A_TMA) {
+    w_prefetched = nkb < STAGES ? nkb : STAGES;
+    if (warp == TMA_WARP && lane == 0 && !(p.act & 64) && (int)blockIdx.x < num_tiles) {
+      const int tile = blockIdx.x;
+      const int ks = tile / tiles_mn, tmn = tile - ks * tiles_mn;
+      const int tn = tmn % tiles_n;
+      for (int kb = 0; kb < w_prefetched; ++kb) {
+        const int kcoord = (ks * nkb + kb) * Cfg::KB_ELEMS;
+        tc::mbar_arrive_expect_tx(full_bar(kb), PLANES * (Cfg::B_BYTES + Cfg::A_BYTES));
+        const uint32_t b_hi = smem_base + kb * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES;
+        tc::tma_load_2d(b_hi, &map_hi, full_bar(kb), kcoord, tn * BN);
+        if (PLANES == 2) tc::tma_load_2d(b_hi + Cfg::B_BYTES, &map_lo, full_bar(kb), kcoord, tn * BN);
+      }
+    }
+  }
+  pdl_wait();      // everything above (barrier init, TMEM alloc, descriptor prefetch, weight tiles) overlapped the previous kernel
   pdl_trigger();   // now let ONE successor pre-launch (pre-launched CTAs pin 200 KB of smem each while they wait)
   if (dbg && threadIdx.x == 0) p.dbg[1] = tc::gtime();
 
@@ -543,13 +561,17 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
           const int s = kit % STAGES;
           const int kcoord = (ks * nkb + kb) * Cfg::KB_ELEMS;
-          tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
-          tc::mbar_arrive_expect_tx(full_bar(s), PLANES * (Cfg::B_BYTES + (A_TMA ? Cfg::A_BYTES : 0)));
+          const bool pre = A_TMA && kit < w_prefetched;   // barrier armed and weight tile already in flight
+          if (!pre) {
+            tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
+            tc::mbar_arrive_expect_tx(full_bar(s), PLANES * (Cfg::B_BYTES + (A_TMA ? Cfg::A_BYTES : 0)));
+          }
           if constexpr (A_TMA) {
             const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
             tc::tma_load_2d(a_hi, &map_a_hi, full_bar(s), kcoord, tm * TC_BM);
             if (PLANES == 2) tc::tma_load_2d(a_hi + Cfg::A_BYTES, &map_a_lo, full_bar(s), kcoord, tm * TC_BM);
           }
+          if (pre) continue;
           const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES;
           tc::tma_load_2d(b_hi, &map_hi, full_bar(s), kcoord, tn * BN);
           if (PLANES == 2) tc::tma_load_2d(b_hi + Cfg::B_BYTES, &map_lo, full_bar(s), kcoord, tn * BN);
