@@ -65,7 +65,7 @@ __global__ void conv0_direct_kernel(const float* __restrict__ x, const float* __
     o.y = fmaxf(a1 * ssc[c4 + 1] + ssh[c4 + 1], 0.f);
     o.z = fmaxf(a2 * ssc[c4 + 2] + ssh[c4 + 2], 0.f);
     o.w = fmaxf(a3 * ssc[c4 + 3] + ssh[c4 + 3], 0.f);
-    *reinterpret_cast<float4*>(out + pix * Cout + c4) = o;
+    if (out) *reinterpret_cast<float4*>(out + pix * Cout + c4) = o;   // fp32 copy only when a consumer reads it
     if (out_hi) store_planes4(o, out_hi, out_lo, (size_t)(pix * Cout + c4));
   }
 }

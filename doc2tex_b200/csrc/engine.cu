@@ -117,6 +117,7 @@ struct d2t_engine {
   bool time_conv = false;   // option "time_conv": bracket layer3.1.conv1 with events (d2t_debug_conv_time)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
   double conv_flops = 0.0;
+  bool lean_acts = true;    // D2T_LEAN_ACTS=0: every stem layer writes fp32 AND operand planes, read or not
   bool attn_group = false;  // D2T_ATTN_GROUP=1 / option "attn_group": beam-grouped decode attention (measured slower, off)
   int split_k = 1;       // D2T_SPLIT_K / option "split_k": 0 = never, 1 = auto split-K of the LayerNorm-fed decode projections
   bool fuse_ln = false;  // D2T_FUSE_LN=1: cluster-fused residual+LayerNorm epilogue (measured slower than the stand-alone
@@ -312,12 +313,15 @@ ConvGemm linear_params(const float* x, const float* w, const float* bias, float*
   return p;
 }
 
-int alloc_act(d2t_engine* e, SlotPool& pool, Fmap* a, int B, int H, int W, int C, bool planes = false) {
+int alloc_act(d2t_engine* e, SlotPool& pool, Fmap* a, int B, int H, int W, int C, bool planes = false, bool f32 = true) {
   cudaError_t st = cudaSuccess;
   a->B = B; a->H = H; a->W = W; a->C = C;
   a->hi = a->lo = nullptr;
-  a->p = (float*)pool.get(a->numel() * sizeof(float), &st);
-  if (!a->p) return e->fail(D2T_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", a->numel() * 4, cudaGetErrorString(st));
+  a->p = nullptr;
+  if (f32) {
+    a->p = (float*)pool.get(a->numel() * sizeof(float), &st);
+    if (!a->p) return e->fail(D2T_ERR_CUDA, "cudaMalloc of %zu bytes failed: %s", a->numel() * 4, cudaGetErrorString(st));
+  }
   if (planes) {
     a->hi = (__nv_bfloat16*)pool.get(a->numel() * 2, &st);
     if (a->hi && e->cfg.precision == D2T_PREC_BF16X3) a->lo = (__nv_bfloat16*)pool.get(a->numel() * 2, &st);
@@ -339,21 +343,42 @@ inline bool stem_planes(const d2t_engine* e) {
   return e->use_tc3 && (e->cfg.precision == D2T_PREC_BF16X3 || e->cfg.precision == D2T_PREC_BF16);
 }
 
+// Which representations of a layer's output its consumers read: the fp32 tensor (residual adds, max-pools, taps) and /
+// or the bf16 operand planes (the next tensor-core convolution).  The early stem layers are bound by activation traffic
+// (ncu: conv0_2 moves 2.6 GB in 1.12 ms at 19 % tensor-pipe activity), so a representation nobody reads is not written.
+enum OutNeed { NEED_F32 = 1, NEED_PLANES = 2, NEED_BOTH = 3 };
+
+// true when run_contraction will route this problem to the cp.async-fed kernel, whose epilogue accepts out == nullptr
+bool routes_to_tc3(d2t_engine* e, const ConvGemm& p) {
+  const int prec = e->cfg.precision;
+  if (prec != D2T_PREC_BF16X3 && prec != D2T_PREC_BF16) return false;
+  if (!e->use_tc3 || e->use_tc4 || !tc3_supported(p, prec) || !tc_supported(p)) return false;
+  auto w = e->tcw.find(p.w);
+  auto m = e->tc3.find(p.w);
+  return w != e->tcw.end() && w->second.ready && w->second.N == p.N && w->second.K == p.K && m != e->tc3.end() && m->second.ready;
+}
+
 int conv_layer(d2t_engine* e, const std::string& name, const Fmap& x, Fmap* y, int sh, int sw, int ph, int pw,
-               const Fmap* res, int act, cudaStream_t s, int oh_override = -1, int ow_override = -1) {
+               const Fmap* res, int act, cudaStream_t s, int oh_override = -1, int ow_override = -1, int need = NEED_BOTH) {
   auto it = e->conv.find(name);
   if (it == e->conv.end()) return e->fail(D2T_ERR_STATE, "conv '%s' not finalized", name.c_str());
   const ConvW& c = it->second;
   const int OH = oh_override > 0 ? oh_override : (x.H + 2 * ph - c.kh) / sh + 1;
   const int OW = ow_override > 0 ? ow_override : (x.W + 2 * pw - c.kw) / sw + 1;
-  if (int rc = alloc_act(e, e->enc_pool, y, x.B, OH, OW, c.cout, stem_planes(e) && name != "patch_embed.proj")) return rc;
+  const bool planes_mode = stem_planes(e) && name != "patch_embed.proj";
+  const bool want_planes = planes_mode && ((need & NEED_PLANES) || !e->lean_acts);
   ConvGemm p{};
-  p.x = x.p; p.x_hi = x.hi; p.x_lo = x.lo; p.out_hi = y->hi; p.out_lo = y->lo;
+  p.x = x.p; p.x_hi = x.hi; p.x_lo = x.lo;
   p.w = c.w; p.scale = c.scale; p.shift = c.shift; p.res = res ? res->p : nullptr;
-  p.out = y->p; p.out2 = nullptr; p.dyn = nullptr; p.dyn_mul2 = 0;
+  p.out2 = nullptr; p.dyn = nullptr; p.dyn_mul2 = 0;
   p.ldc = c.cout; p.ldc2 = 0; p.ldr = c.cout; p.n_split = c.cout;
   p.B = x.B; p.H = x.H; p.W = x.W; p.C = x.C; p.KH = c.kh; p.KW = c.kw; p.SH = sh; p.SW = sw; p.PH = ph; p.PW = pw;
   p.OH = OH; p.OW = OW; p.M = x.B * OH * OW; p.N = c.cout; p.K = c.kh * c.kw * c.cin; p.act = act;
+  // the fp32 copy is dropped only when nobody reads it AND the kernel that will run tolerates its absence
+  const bool want_f32 = (need & NEED_F32) || e->keep_taps || !want_planes || !e->lean_acts || !routes_to_tc3(e, p);
+  if (int rc = alloc_act(e, e->enc_pool, y, x.B, OH, OW, c.cout, want_planes, want_f32)) return rc;
+  p.out_hi = y->hi; p.out_lo = y->lo;
+  p.out = y->p;
   if (e->time_conv && name == "layer3.1.conv1" && e->conv_events.size() < 4096) {
     cudaEvent_t a, b;
     CUDA_TRY(e, cudaEventCreate(&a));
@@ -386,15 +411,16 @@ void tap(d2t_engine* e, const std::string& name, const Fmap& a, bool tokens = fa
 int basic_block(d2t_engine* e, const std::string& name, Fmap& x, cudaStream_t s) {
   // BasicBlock.forward (resnet.py:32-48): conv-bn-relu, conv-bn, (+1x1 conv-bn downsample), add, relu
   Fmap t, ds, o;
-  if (int rc = conv_layer(e, name + ".conv1", x, &t, 1, 1, 1, 1, nullptr, ACT_RELU, s)) return rc;
+  // t feeds conv2 only (operand planes); the downsample branch is read only as the fp32 residual
+  if (int rc = conv_layer(e, name + ".conv1", x, &t, 1, 1, 1, 1, nullptr, ACT_RELU, s, -1, -1, NEED_PLANES)) return rc;
   const Fmap* res = &x;
   if (e->conv.count(name + ".downsample.0")) {
-    if (int rc = conv_layer(e, name + ".downsample.0", x, &ds, 1, 1, 0, 0, nullptr, ACT_NONE, s)) return rc;
+    if (int rc = conv_layer(e, name + ".downsample.0", x, &ds, 1, 1, 0, 0, nullptr, ACT_NONE, s, -1, -1, NEED_F32)) return rc;
     res = &ds;
   }
   if (int rc = conv_layer(e, name + ".conv2", t, &o, 1, 1, 1, 1, res, ACT_RELU, s)) return rc;
   free_act(e, e->enc_pool, t);
-  if (ds.p) free_act(e, e->enc_pool, ds);
+  if (ds.p || ds.hi) free_act(e, e->enc_pool, ds);
   free_act(e, e->enc_pool, x);
   x = o;
   return 0;
@@ -493,6 +519,7 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   if (const char* v = getenv("D2T_DECODE_GROUPS")) e->decode_groups = atoi(v);
   if (const char* v = getenv("D2T_SPLIT_K")) e->split_k = atoi(v);
   if (const char* v = getenv("D2T_ATTN_GROUP")) e->attn_group = atoi(v) != 0;
+  if (const char* v = getenv("D2T_LEAN_ACTS")) e->lean_acts = atoi(v) != 0;
   if (const char* v = getenv("D2T_CLUSTER_STEP")) e->use_cluster_step = atoi(v) != 0;
   if (cudaMallocHost(&e->h_counters, 4 * D2T_MAX_GROUPS * sizeof(int)) != cudaSuccess) {
     g_create_error = "cudaMallocHost failed";
@@ -846,7 +873,8 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
   Fmap x, y;
   {
     const ConvW& c0 = e->conv["conv0_1"];
-    if ((rc = alloc_act(e, e->enc_pool, &x, B, H, W, c0.cout, stem_planes(e)))) return rc;
+    // conv0_1 feeds conv0_2 only: operand planes, no fp32 copy (unless taps are kept)
+    if ((rc = alloc_act(e, e->enc_pool, &x, B, H, W, c0.cout, stem_planes(e), !(stem_planes(e) && e->lean_acts) || e->keep_taps))) return rc;
     const long long total = (long long)B * H * W * (c0.cout / 4);
     const size_t smem = (size_t)11 * c0.cout * sizeof(float);
     conv0_direct_kernel<<<grid_for(total, 256, e->active_sms), 256, smem, s>>>(img, c0.w, c0.scale, c0.shift, x.p, B, H, W, c0.cout, x.hi, x.lo);
@@ -854,19 +882,19 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
     CUDA_TRY(e, cudaGetLastError());
     tap(e, "conv0_1", x);
   }
-  if ((rc = conv_layer(e, "conv0_2", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s))) return rc;
+  if ((rc = conv_layer(e, "conv0_2", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s, -1, -1, NEED_F32))) return rc;   // read by the max-pool
   free_act(e, e->enc_pool, x); tap(e, "conv0_2", y);
   if ((rc = pool_layer(e, y, &x, 2, 2, 0, 0, s))) return rc;
   free_act(e, e->enc_pool, y);
   if ((rc = basic_block(e, "layer1.0", x, s))) return rc;
   tap(e, "layer1", x);
-  if ((rc = conv_layer(e, "conv1", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s))) return rc;
+  if ((rc = conv_layer(e, "conv1", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s, -1, -1, NEED_F32))) return rc;
   free_act(e, e->enc_pool, x); tap(e, "conv1", y);
   if ((rc = pool_layer(e, y, &x, 2, 2, 0, 0, s))) return rc;
   free_act(e, e->enc_pool, y);
   for (int b = 0; b < 2; ++b) if ((rc = basic_block(e, "layer2." + std::to_string(b), x, s))) return rc;
   tap(e, "layer2", x);
-  if ((rc = conv_layer(e, "conv2", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s))) return rc;
+  if ((rc = conv_layer(e, "conv2", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s, -1, -1, NEED_F32))) return rc;
   free_act(e, e->enc_pool, x); tap(e, "conv2", y);
   if ((rc = pool_layer(e, y, &x, 2, 1, 0, 1, s))) return rc;  // maxpool3: k2 s(2,1) p(0,1), -inf padding
   free_act(e, e->enc_pool, y); tap(e, "pool3", x);

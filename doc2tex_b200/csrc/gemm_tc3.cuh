@@ -150,7 +150,7 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
                 v = tc::gelu_erf4(v);
               }
               const size_t o = (size_t)m * ldc + n;
-              *reinterpret_cast<float4*>(out + o) = v;
+              if (out) *reinterpret_cast<float4*>(out + o) = v;   // fp32 copy only when a consumer reads it
               if (out_hi) {
                 const float f[4] = {v.x, v.y, v.z, v.w};
                 uint32_t hw[2], lw[2];
@@ -376,7 +376,7 @@ conv_gemm_tc3s_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_
               if (res) v += __ldg(res + (size_t)m * ldr + n);
               v = apply_act(v, act);
               const size_t o = (size_t)m * ldc + n;
-              out[o] = v;
+              if (out) out[o] = v;
               if (out_hi) {
                 const __nv_bfloat16 h = __float2bfloat16_rn(v);
                 out_hi[o] = h;
