@@ -248,6 +248,28 @@ def test_encoder_variants_match_golden(built_lib, case, interp, sizes, precision
     e.close()
 
 
+@pytest.mark.parametrize("beam", [3, 10])
+def test_other_beam_widths_match_oracle(built_lib, beam):
+    """Beam widths other than 5 (demo/recog_cfg.yaml decodes with beam_size 10): TFM and Attnv2 heads against the CPU
+    oracle's restatement of tools/beam.py / seq2seq_v2.py on weights whose beams complete within a few steps."""
+    from oracle import oracle_model as om
+    img = synth.make_images(2, 64, 256, seed=2024)
+    for head, eb in (("TFM", 2.0), ("Attnv2", 0.5)):
+        cfg, sd = state_dict_for(head, eb)
+        e = engine_for(head, eb, "fp32")
+        ctx, _, _ = e.encode(img.cuda())
+        ids, lens, score, steps, _, _ = e.decode_beam(ctx, beam)
+        ctx_or, _, _ = om.encoder_forward(sd, img)
+        for i in range(2):
+            if head == "TFM":
+                seq, sc = om.TFMHead(sd, max_seq_len=150).beam(ctx_or[i:i + 1], beam)
+            else:
+                seq, sc = om.AttnV2Head(sd).beam(ctx_or[i:i + 1], beam, 150)
+            n = int(lens[i])
+            assert ids[i, :n].cpu().tolist() == seq, (head, beam, i)
+            assert abs(float(score[i]) - sc) <= REL_TOL_FP32 * max(1.0, abs(sc))
+
+
 def test_model_dropin_surface(built_lib):
     """Same call surface as doc2tex.modules.build_model.Model (build_model.py:36-79, infer.py:149-161)."""
     from doc2tex_b200.modules.build_model import Model
