@@ -45,7 +45,11 @@ struct Tc3Cfg {
   static constexpr int A_BYTES = MT * A_HALF_BYTES;
   static constexpr int B_BYTES = BN * 64;
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
-  static constexpr int EPI_STAGE_BYTES = 4 * 32 * TC_EPI_PITCH * 4;
+  // epilogue warps: the 64- / 128-wide tiles of the early layers are bound by their epilogue traffic (ncu), so they get
+  // two warps per TMEM lane quadrant; the 256-wide tiles hide the epilogue behind a 58 us main loop and keep the 4th stage
+  static constexpr int EPI_WARPS = (BN <= 128 && MT == 1) ? 8 : 4;
+  static constexpr int THREADS = (EPI_WARPS + 8 + 2) * 32;
+  static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * TC_EPI_PITCH * 4;
   static constexpr int STAGES_RAW = (225 * 1024 - EPI_STAGE_BYTES - 1280) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN;                 // MT=1: two buffers of one tile; MT=2: one buffer of two tiles
@@ -55,13 +59,14 @@ struct Tc3Cfg {
 };
 
 template <int PASSES, int BN, int MT>
-__global__ void __launch_bounds__(448, 1)
+__global__ void __launch_bounds__(Tc3Cfg<PASSES, BN, MT>::THREADS, 1)
 conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi,
                      const __grid_constant__ CUtensorMap map_lo, int tiles_m, int tiles_n) {
   using Cfg = Tc3Cfg<PASSES, BN, MT>;
   constexpr int ROWS = MT * TC_BM;                          // output rows per CTA tile
   constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES;
-  constexpr int EPI_WARPS = 4, TMA_WARP = 12, MMA_WARP = 13;
+  constexpr int EPI_WARPS = Cfg::EPI_WARPS, TMA_WARP = EPI_WARPS + 8, MMA_WARP = EPI_WARPS + 9;
+  constexpr int NSLOT = EPI_WARPS / 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - tc::smem_u32(smem_raw));
@@ -102,7 +107,7 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
 
   if (warp < EPI_WARPS) {
     // =========================== epilogue ===========================
-    const int quad = warp & 3;
+    const int quad = warp & 3, slot = warp >> 2;   // two warps of a quadrant alternate over the 32-column chunks
     float* const stg = reinterpret_cast<float*>(smem_gen + (size_t)STAGES * Cfg::STAGE_BYTES) + warp * (32 * TC_EPI_PITCH);
     const int sub_r = lane >> 3, c4 = (lane & 7) * 4;
     const int M = p.M, N = p.N, ldc = p.ldc, ldr = p.ldr, act = p.act & 15;
@@ -119,7 +124,7 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
       tc::mbar_wait(tfull_bar(acc), MT == 1 ? ((it >> 1) & 1) : (it & 1));
       tc::tcgen05_after_sync();
 #pragma unroll 1
-      for (int hj = 0; hj < MT * (BN / 32); ++hj) {
+      for (int hj = slot; hj < MT * (BN / 32); hj += NSLOT) {
         const int h = hj / (BN / 32), j = hj - h * (BN / 32);   // m-tile of the CTA tile, 32-column chunk
         const int m_first = tm * ROWS + h * TC_BM + quad * 32 + sub_r;
         uint32_t r[32];
@@ -134,16 +139,19 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
           float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
           if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + n));
           if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + n));
-#pragma unroll 2
+          float4 rr[8];   // residual rows of this chunk: all eight loads in flight before the first use
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = m_first + 4 * i;
+            rr[i] = (res && m < M) ? __ldg(reinterpret_cast<const float4*>(res + (size_t)m * ldr + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int m = m_first + 4 * i;
             if (m < M) {
               float4 v = *reinterpret_cast<const float4*>(stg + (sub_r + 4 * i) * TC_EPI_PITCH + c4);
-              v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
-              if (res) {
-                const float4 rr = __ldg(reinterpret_cast<const float4*>(res + (size_t)m * ldr + n));
-                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
-              }
+              v.x = fmaf(v.x, sc.x, sh.x) + rr[i].x; v.y = fmaf(v.y, sc.y, sh.y) + rr[i].y;
+              v.z = fmaf(v.z, sc.z, sh.z) + rr[i].z; v.w = fmaf(v.w, sc.w, sh.w) + rr[i].w;
               if (act == ACT_RELU) {
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
               } else if (act == ACT_GELU) {
@@ -547,7 +555,7 @@ inline cudaError_t tc3_launch_one(const ConvGemm& p, const Tc3Maps& m, cudaStrea
   const int tiles_m = (p.M + MT * TC_BM - 1) / (MT * TC_BM), tiles_n = (p.N + BN - 1) / BN;
   const int grid = tiles_m * tiles_n < num_sms ? tiles_m * tiles_n : num_sms;
   constexpr int mi = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
-  return launch_kernel(kern, dim3(grid), dim3(448), Cfg::SMEM_BYTES, s, p, m.hi[mi], m.lo[mi], tiles_m, tiles_n);
+  return launch_kernel(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, p, m.hi[mi], m.lo[mi], tiles_m, tiles_n);
 }
 
 // D2T_TC3_MT2=1: two m-tiles per CTA.  Measured SLOWER on B200 (encoder 34.7 -> 39.9 ms in bf16x3): halving the
