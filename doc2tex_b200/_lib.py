@@ -21,7 +21,7 @@ SYMBOLS = [
 ]
 
 PREC = {"fp32": 0, "tf32x3": 1, "bf16x3": 2, "bf16": 3}
-HEAD = {"None": 0, "TFM": 1, "Attnv2": 2}
+HEAD = {"None": 0, "TFM": 1, "Attnv2": 2, "Attn": 3}
 
 
 class Config(C.Structure):

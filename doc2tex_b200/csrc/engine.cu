@@ -678,7 +678,7 @@ int d2t_finalize_weights(d2t_engine* e) {
     }
     if ((rc = upload_key(e, PRED + "proj.weight", {V, D}))) return rc;
     if ((rc = upload_key(e, PRED + "proj.bias", {V}))) return rc;
-  } else if (c.head == D2T_HEAD_ATTNV2) {
+  } else if (c.head == D2T_HEAD_ATTNV2 || c.head == D2T_HEAD_ATTN) {
     const int V = c.vocab, Hs = c.attn_hidden, Kd = c.attn_kernel_dim, taps = 2 * c.attn_kernel_size + 1;
     const std::string a = PRED + "attention_cell.attn.";
     if ((rc = upload_key(e, PRED + "embedding.weight", {V, D}))) return rc;
@@ -762,7 +762,7 @@ int d2t_finalize_weights(d2t_engine* e) {
       }
       if ((rc = prep(e->dev[PRED + "proj.weight"], c.vocab, D))) return rc;
       if ((rc = prepare_cluster_step(e))) return rc;
-    } else if (c.head == D2T_HEAD_ATTNV2) {
+    } else if (c.head == D2T_HEAD_ATTNV2 || c.head == D2T_HEAD_ATTN) {
       const int Hs = c.attn_hidden;
       const std::string a = PRED + "attention_cell.attn.";
       if ((rc = prep(e->dev[a + "key_proj.weight"], Hs, D))) return rc;

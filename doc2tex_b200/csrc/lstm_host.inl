@@ -4,6 +4,10 @@ namespace {
 
 constexpr int ATTN_GO = 0, ATTN_END = 1;  // AttnLabelConverter (attn_converter.py:8)
 
+inline bool is_lstm_head(int head) { return head == D2T_HEAD_ATTNV2 || head == D2T_HEAD_ATTN; }
+// first encoder token the decoder attends to: AttentionV2 (seqmodel 'TFM') drops the cls token, Attention keeps it
+inline int attn_tok0(const d2t_config& c) { return c.head == D2T_HEAD_ATTN ? 0 : 1; }
+
 struct AttnBuffers {
   float *keyproj = nullptr, *qp = nullptr, *xcat = nullptr, *gates = nullptr, *h = nullptr, *c = nullptr;
   float *alpha_cum = nullptr, *logits = nullptr, *logits_out = nullptr;
@@ -15,7 +19,7 @@ int enqueue_attn_step(d2t_engine* e, const AttnBuffers& b, const float* ctx, int
                       cudaStream_t s) {
   const d2t_config& c = e->cfg;
   const int D = c.hidden, Hs = c.attn_hidden, V = c.vocab, L = T + 1, Kc = 2 * D + Hs;
-  const int taps = 2 * c.attn_kernel_size + 1, S = ntok - 1;
+  const int taps = 2 * c.attn_kernel_size + 1, S = ntok - attn_tok0(c);
   const std::string a = PRED + "attention_cell.attn.";
   int* step = b.counters;
   int rc;
@@ -28,7 +32,7 @@ int enqueue_attn_step(d2t_engine* e, const AttnBuffers& b, const float* ctx, int
   }
   lstm_attention_step_kernel<256><<<B, 256, (size_t)2 * S * sizeof(float), s>>>(
       b.keyproj, ctx, ntok, b.qp, e->dev["attn.locM"], e->dev["attn.locc"], taps, e->dev[a + "score.weight"],
-      e->dev[a + "score.bias"], b.alpha_cum, b.xcat, Kc);
+      e->dev[a + "score.bias"], b.alpha_cum, b.xcat, Kc, 1, attn_tok0(c));
   e->launches += 1;
   CUDA_TRY(e, cudaGetLastError());
   {  // LSTMCell gates over [context ; embedding ; h]
@@ -95,7 +99,7 @@ extern "C" int d2t_decode_attn_greedy(d2t_engine* e, const float* ctx, int B, in
                                       d2t_stream stream) {
   if (!e) return D2T_ERR_INVALID;
   const d2t_config& c = e->cfg;
-  if (c.head != D2T_HEAD_ATTNV2) return e->fail(D2T_ERR_STATE, "engine was not configured with the Attnv2 head");
+  if (!is_lstm_head(c.head)) return e->fail(D2T_ERR_STATE, "engine was not configured with the Attn / Attnv2 head");
   if (!e->finalized) return e->fail(D2T_ERR_STATE, "decode before d2t_finalize_weights");
   if (!ctx || !ids || !steps_out || B <= 0 || ntok < 2 || max_steps <= 0) return e->fail(D2T_ERR_INVALID, "bad decode arguments");
   if (c.attn_hidden != 256 || c.hidden != 256) return e->fail(D2T_ERR_UNSUPPORTED, "Attnv2 head needs hidden_size == input_size == 256");
@@ -103,7 +107,7 @@ extern "C" int d2t_decode_attn_greedy(d2t_engine* e, const float* ctx, int B, in
   WorkStream ws(e, (cudaStream_t)stream);
   cudaStream_t s = ws.get();
   e->active_sms = e->num_sms;
-  const int D = c.hidden, Hs = c.attn_hidden, V = c.vocab, T = max_steps, L = T + 1, Kc = 2 * D + Hs, S = ntok - 1;
+  const int D = c.hidden, Hs = c.attn_hidden, V = c.vocab, T = max_steps, L = T + 1, Kc = 2 * D + Hs, S = ntok - attn_tok0(c);
   const bool want_logits = logits != nullptr;
   e->dec_pool.release_all();
   AttnBuffers b;
@@ -236,7 +240,7 @@ AttnBeamState attn_beam_state(const d2t_engine* e, const AttnBeamBuffers& b, int
   st.alpha_cum = b.alpha_cum; st.n_live = b.n_live; st.n_done = b.n_done; st.last_complete = b.last_complete;
   st.finished = b.finished; st.done_seq = b.done_seq; st.done_len = b.done_len; st.done_score = b.done_score;
   st.counters = b.counters; st.trace = b.trace; st.trace_score = b.trace_score;
-  st.L = T + 1; st.beam = beam; st.B = B; st.V = c.vocab; st.S = ntok - 1; st.HS = c.attn_hidden; st.end_id = ATTN_END;
+  st.L = T + 1; st.beam = beam; st.B = B; st.V = c.vocab; st.S = ntok - attn_tok0(c); st.HS = c.attn_hidden; st.end_id = ATTN_END;
   st.max_steps = T;
   return st;
 }
@@ -245,7 +249,7 @@ int enqueue_attn_beam_step(d2t_engine* e, const AttnBeamBuffers& b, const float*
                            cudaStream_t s) {
   const d2t_config& c = e->cfg;
   const int D = c.hidden, Hs = c.attn_hidden, V = c.vocab, Kc = 2 * D + Hs, R = B * beam;
-  const int taps = 2 * c.attn_kernel_size + 1, S = ntok - 1;
+  const int taps = 2 * c.attn_kernel_size + 1, S = ntok - attn_tok0(c);
   const std::string a = PRED + "attention_cell.attn.";
   int rc;
   lstm_embed_cur_kernel<<<(R * D / 4 + 255) / 256, 256, 0, s>>>(b.targets, e->dev[PRED + "embedding.weight"], b.xcat, Kc, D, R, D);
@@ -257,7 +261,7 @@ int enqueue_attn_beam_step(d2t_engine* e, const AttnBeamBuffers& b, const float*
   }
   lstm_attention_step_kernel<256><<<R, 256, (size_t)2 * S * sizeof(float), s>>>(
       b.keyproj, ctx, ntok, b.qp, e->dev["attn.locM"], e->dev["attn.locc"], taps, e->dev[a + "score.weight"],
-      e->dev[a + "score.bias"], b.alpha_cum, b.xcat, Kc, beam);
+      e->dev[a + "score.bias"], b.alpha_cum, b.xcat, Kc, beam, attn_tok0(c));
   e->launches += 1;
   CUDA_TRY(e, cudaGetLastError());
   {
@@ -287,7 +291,7 @@ extern "C" int d2t_decode_attn_beam(d2t_engine* e, const float* ctx, int B, int 
                                     float* trace_score, int* steps_out, d2t_stream stream) {
   if (!e) return D2T_ERR_INVALID;
   const d2t_config& c = e->cfg;
-  if (c.head != D2T_HEAD_ATTNV2) return e->fail(D2T_ERR_STATE, "engine was not configured with the Attnv2 head");
+  if (!is_lstm_head(c.head)) return e->fail(D2T_ERR_STATE, "engine was not configured with the Attn / Attnv2 head");
   if (!e->finalized) return e->fail(D2T_ERR_STATE, "decode before d2t_finalize_weights");
   if (!ctx || !best_ids || !best_len || !best_score || !steps_out || B <= 0 || ntok < 2 || max_steps <= 0)
     return e->fail(D2T_ERR_INVALID, "bad decode arguments");
@@ -298,7 +302,7 @@ extern "C" int d2t_decode_attn_beam(d2t_engine* e, const float* ctx, int B, int 
   WorkStream ws(e, (cudaStream_t)stream);
   cudaStream_t s = ws.get();
   e->active_sms = e->num_sms;
-  const int D = c.hidden, Hs = c.attn_hidden, V = c.vocab, T = max_steps, L = T + 1, Kc = 2 * D + Hs, S = ntok - 1, R = B * beam;
+  const int D = c.hidden, Hs = c.attn_hidden, V = c.vocab, T = max_steps, L = T + 1, Kc = 2 * D + Hs, S = ntok - attn_tok0(c), R = B * beam;
   const size_t smem = attn_beam_smem(beam, V, Hs, S, L);
   if (smem > 200 * 1024) return e->fail(D2T_ERR_UNSUPPORTED, "beam %d x %d tokens needs %zu bytes of shared memory", beam, ntok, smem);
   CUDA_TRY(e, cudaFuncSetAttribute(attn_beam_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -29,9 +29,10 @@ lstm_attention_step_kernel(const float* __restrict__ keyproj, const float* __res
                            const float* __restrict__ qp, const float* __restrict__ locM /*[HS][taps]*/,
                            const float* __restrict__ locc /*[HS]*/, int taps, const float* __restrict__ score_w,
                            const float* __restrict__ score_b, float* __restrict__ alpha_cum /*[B][S]*/,
-                           float* __restrict__ xcat, int ld, int rows_per_img = 1) {
+                           float* __restrict__ xcat, int ld, int rows_per_img = 1,
+                           int tok0 = 1 /* first attended token: 1 skips the cls token (Attnv2), 0 keeps it (Attn) */) {
   extern __shared__ float sm[];  // [S] alpha_cum copy, [S] scores
-  const int S = ntok - 1;
+  const int S = ntok - tok0;
   float* s_ac = sm;
   float* s_e = sm + S;
   __shared__ float red[8];
@@ -52,7 +53,7 @@ lstm_attention_step_kernel(const float* __restrict__ keyproj, const float* __res
   const int pad = taps / 2;
   const float sb = score_b[0];
   for (int s = wid; s < S; s += nw) {
-    const float* kr = keyproj + ((size_t)img * ntok + 1 + s) * HS;
+    const float* kr = keyproj + ((size_t)img * ntok + tok0 + s) * HS;
     float acc = 0.f;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
@@ -96,7 +97,7 @@ lstm_attention_step_kernel(const float* __restrict__ keyproj, const float* __res
   __syncthreads();
   // context = alpha^T H, one thread per channel (HS == input channels == 256 here)
   for (int d = threadIdx.x; d < HS; d += blockDim.x) {
-    const float* hp = ctx + ((size_t)img * ntok + 1) * HS + d;
+    const float* hp = ctx + ((size_t)img * ntok + tok0) * HS + d;
     float a0 = 0.f, a1 = 0.f;
     int s = 0;
     for (; s + 2 <= S; s += 2) {

@@ -47,15 +47,20 @@ def config_from_opt(opt: dict, precision: str = "fp32", use_graphs: bool = True)
             raise EngineError("TFM d_model must equal the encoder hidden_size")
         cfg.dec_layers, cfg.dec_heads, cfg.dec_ff = pp["num_decoder_layers"], pp["nhead"], pp["dim_feedforward"]
         cfg.max_seq_len = pp["max_seq_len"]
-    elif name == "Attnv2":
+    elif name in ("Attnv2", "Attn"):
         if pp.get("attn_type", "coverage") != "coverage" or not pp.get("embed_target", False) \
-                or not pp.get("enc_init", False) or pp.get("seqmodel", "ViT") != "TFM":
-            raise EngineError("Attnv2 is supported as shipped: coverage attention, embed_target, enc_init, seqmodel TFM")
-        cfg.head = _lib.HEAD["Attnv2"]
+                or not pp.get("enc_init", False):
+            raise EngineError(f"{name} is supported as shipped: coverage attention, embed_target, enc_init")
+        if name == "Attnv2" and pp.get("seqmodel", "ViT") != "TFM":
+            raise EngineError("Attnv2 is supported with seqmodel 'TFM' (it drops the cls token, seq2seq_v2.py:27,190)")
+        if name == "Attn" and pp.get("seqmodel", "ViT") == "BiLSTM":
+            raise EngineError("Attn with seqmodel 'BiLSTM' (mean-pooled init, seq2seq.py:232-234) is not on the accelerated path")
+        # 'Attn' (seq2seq.py) attends over every encoder token incl. cls; 'Attnv2' (seq2seq_v2.py) skips the cls token
+        cfg.head = _lib.HEAD[name]
         cfg.attn_hidden, cfg.attn_kernel_dim, cfg.attn_kernel_size = pp["hidden_size"], pp["kernel_dim"], pp["kernel_size"]
         cfg.max_seq_len = int(opt["batch_max_length"])
     else:
-        raise EngineError(f"Prediction head {name!r} is not on the accelerated path (TFM, Attnv2)")
+        raise EngineError(f"Prediction head {name!r} is not on the accelerated path (TFM, Attnv2, Attn)")
     cfg.precision = _lib.PREC[precision]
     cfg.use_graphs = 1 if use_graphs else 0
     return cfg

@@ -86,11 +86,11 @@ def make_config(head: str = "TFM", **overrides) -> dict:
             },
         }
         cfg["num_class"] = N_SYMBOLS + 4
-    elif head == "Attnv2":
+    elif head in ("Attnv2", "Attn"):
         cfg["Prediction"] = {
-            "name": "Attnv2",
+            "name": head,
             "params": {
-                "seqmodel": "TFM",
+                "seqmodel": "TFM" if head == "Attnv2" else "ViT",
                 "input_size": 256,
                 "hidden_size": 256,
                 "kernel_size": 2,

@@ -35,7 +35,10 @@ enum d2t_status {
   D2T_ERR_UNSUPPORTED = 5
 };
 
-enum d2t_head { D2T_HEAD_NONE = 0, D2T_HEAD_TFM = 1, D2T_HEAD_ATTNV2 = 2 };
+/* D2T_HEAD_ATTN = Prediction.name 'Attn' (seq2seq.py:10-345): the same LSTM coverage-attention decoder as 'Attnv2', but it
+ * attends over ALL encoder tokens including the cls token (seq2seq.py:236-238), where AttentionV2 with seqmodel 'TFM'
+ * drops it (seq2seq_v2.py:27, 190). */
+enum d2t_head { D2T_HEAD_NONE = 0, D2T_HEAD_TFM = 1, D2T_HEAD_ATTNV2 = 2, D2T_HEAD_ATTN = 3 };
 
 /* Arithmetic of the dense contractions (conv stem, patch-embed, linear layers). */
 enum d2t_precision {

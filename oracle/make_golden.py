@@ -131,8 +131,8 @@ def tfm_case(name, H, W, B, end_bias, beam_imgs):
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
 
 
-def attn_case(name, H, W, B, end_bias):
-    cfg = synth.make_config("Attnv2")
+def attn_case(name, H, W, B, end_bias, head="Attnv2"):
+    cfg = synth.make_config(head)
     sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias)
     img = synth.make_images(B, H, W, seed=2024)
     m = ref_model(cfg, sd)
@@ -140,7 +140,7 @@ def attn_case(name, H, W, B, end_bias):
         text = torch.zeros(B, 151, dtype=torch.long)
         ids_ref, probs_ref, _ = m(img, text, is_train=False, is_test=True)
         ctx_or, _, _ = om.encoder_forward(sd, img)
-        ids_or, probs_or = om.AttnV2Head(sd).greedy(ctx_or, 150, True)
+        ids_or, probs_or = om.AttnV2Head(sd, include_cls=(head == "Attn")).greedy(ctx_or, 150, True)
         assert torch.equal(ids_ref, ids_or)
         d = (probs_ref - probs_or).abs().max().item()
         print(f"[{name}] attnv2 logits max abs diff {d:.3e}; nonzero steps "
@@ -152,14 +152,14 @@ def attn_case(name, H, W, B, end_bias):
                         margin=margins(probs_ref).numpy())
 
 
-def attn_beam_case(name, H, W, B, end_bias, beam=5):
+def attn_beam_case(name, H, W, B, end_bias, beam=5, head="Attnv2"):
     """AttentionV2.forward_beam of the live reference, one image at a time (it asserts batch 1, seq2seq_v2.py:18-19)."""
-    cfg = synth.make_config("Attnv2")
+    cfg = synth.make_config(head)
     sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias)
     img = synth.make_images(B, H, W, seed=2024)
     m = ref_model(cfg, sd)
     head_ref = m.predicter.Prediction
-    head_or = om.AttnV2Head(sd)
+    head_or = om.AttnV2Head(sd, include_cls=(head == "Attn"))
     seqs, scores, traces = [], [], []
     with torch.no_grad():
         ctx_ref, _, _ = m.forward_encoder(img)
@@ -216,6 +216,14 @@ def encoder_variant_case(name, fix_embed, interpolate_embed, sizes):
     np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
 
 
+def attn_base_cases():
+    """Prediction.name 'Attn' (seq2seq.py): the decoder attends over all tokens incl. cls."""
+    attn_case("attn_64x256_full", 64, 256, 2, -1e4, head="Attn")
+    attn_case("attn_64x256_end", 64, 256, 2, 3.0, head="Attn")
+    attn_beam_case("attn_beam_64x256_end04", 64, 256, 2, 0.4, head="Attn")
+    attn_beam_case("attn_beam_64x256_end05", 64, 256, 2, 0.5, head="Attn")
+
+
 def encoder_variant_cases():
     encoder_variant_case("vit_interp_posembed", False, True, [(64, 256), (96, 384), (192, 896)])
     encoder_variant_case("vit_v2_posembed", False, False, [(64, 256), (96, 384)])
@@ -242,4 +250,5 @@ if __name__ == "__main__":
     attn_case("attnv2_64x256_full", 64, 256, 2, -1e4)
     attn_case("attnv2_64x256_end", 64, 256, 2, 3.0)
     attn_beam_cases()
+    attn_base_cases()
     encoder_variant_cases()

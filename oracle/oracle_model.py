@@ -261,9 +261,12 @@ class AttnV2Head:
 
     GO, END = 0, 1
 
-    def __init__(self, sd: SD):
+    def __init__(self, sd: SD, include_cls: bool = False):
+        """include_cls=True restates the base ``Attention`` head (Prediction.name 'Attn', seq2seq.py:225-331 and :82-223):
+        identical loops, but the decoder attends over every encoder token including cls (seq2seq.py:236-238)."""
         g = lambda n: sd[PRED + n]
         self.sd = sd
+        self.tok0 = 0 if include_cls else 1
         self.embedding = g("embedding.weight")
         hs = g("proj_init_h.weight").shape[0]
         ins = g("attention_cell.rnn.weight_ih").shape[1] - self.embedding.shape[1]
@@ -278,7 +281,7 @@ class AttnV2Head:
         with torch.no_grad():
             B = ctx.shape[0]
             steps = batch_max_length + 1
-            H = ctx[:, 1:, :]
+            H = ctx[:, self.tok0:, :]
             init = ctx[:, 0, :]
             h = F.linear(init, sd[P + "proj_init_h.weight"], sd[P + "proj_init_h.bias"])
             c = F.linear(init, sd[P + "proj_init_c.weight"], sd[P + "proj_init_c.bias"])
@@ -342,7 +345,7 @@ class AttnV2Head:
             assert ctx1.shape[0] == 1
             num_steps = batch_max_length + 1
             bH = ctx1[0][None].expand(beam_size, -1, -1)
-            H = bH[:, 1:, :]
+            H = bH[:, self.tok0:, :]
             init = bH[:, 0, :]
             h = F.linear(init, sd[P + "proj_init_h.weight"], sd[P + "proj_init_h.bias"])
             c = F.linear(init, sd[P + "proj_init_c.weight"], sd[P + "proj_init_c.bias"])

@@ -248,6 +248,47 @@ def test_encoder_variants_match_golden(built_lib, case, interp, sizes, precision
     e.close()
 
 
+@pytest.mark.parametrize("precision", ["fp32", "bf16x3"])
+def test_attn_base_head_matches_golden(built_lib, precision):
+    """Prediction.name 'Attn' (seq2seq.py:10-345, the base class of Attnv2): the decoder attends over every encoder token
+    including cls.  Greedy ids / logits and beam-5 results against the live reference's outputs."""
+    from doc2tex_b200.engine import Engine
+    img = synth.make_images(2, 64, 256, seed=2024)
+    for case in ("attn_64x256_full", "attn_64x256_end"):
+        g = load_golden(case)
+        cfg = synth.make_config("Attn")
+        sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias_of(g))
+        e = Engine(cfg, "cuda:0", precision=precision)
+        e.load_state_dict(sd)
+        ctx, _, _ = e.encode(img.cuda())
+        ids, logits, steps = e.decode_greedy(ctx, max_steps=151, is_test=True)
+        assert torch.equal(ids.cpu(), torch.from_numpy(g["ids"]))
+        ref = torch.from_numpy(g["logits"])
+        for j, s_ in enumerate(g["logit_steps"].tolist()):
+            if ref[:, j].abs().max() > 0:
+                assert rel_err(logits[:, s_].cpu(), ref[:, j]) < REL_TOL_FP32, s_
+        e.close()
+    for case in ("attn_beam_64x256_end04", "attn_beam_64x256_end05"):
+        g = load_golden(case)
+        cfg = synth.make_config("Attn")
+        sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias_of(g))
+        e = Engine(cfg, "cuda:0", precision=precision)
+        e.load_state_dict(sd)
+        ctx, _, _ = e.encode(img.cuda())
+        ids, lens, score, steps, tr, trs = e.decode_beam(ctx, 5, trace=True)
+        tr, trs = tr.cpu().numpy(), trs.cpu().numpy()
+        exact = 0
+        for i in range(2):
+            T = int(g["beam_steps"][i])
+            if assert_beam_trace(tr[i, :T], trs[i, :T], g["beam_parents"][i, :T], g["beam_words"][i, :T], g["beam_scores"][i, :T]) < T:
+                continue   # a near-tie of the reference itself (checked by assert_beam_trace): hypotheses may differ after it
+            exact += 1
+            n = int(g["beam_len"][i])
+            assert int(lens[i]) == n and ids[i, :n].cpu().tolist() == g["beam_seq"][i, :n].tolist()
+        assert exact >= 1
+        e.close()
+
+
 @pytest.mark.parametrize("beam", [3, 10])
 def test_other_beam_widths_match_oracle(built_lib, beam):
     """Beam widths other than 5 (demo/recog_cfg.yaml decodes with beam_size 10): TFM and Attnv2 heads against the CPU

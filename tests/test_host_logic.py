@@ -59,6 +59,8 @@ def test_config_translation_and_rejections():
            (256, 6, 8, 679, 1, 504, 4, 1024, 2)
     c = config_from_opt(synth.make_config("Attnv2"))
     assert (c.head, c.vocab, c.attn_hidden, c.attn_kernel_dim, c.attn_kernel_size, c.max_seq_len) == (2, 503, 256, 128, 2, 150)
+    c = config_from_opt(synth.make_config("Attn"))          # base Attention head: same decoder, cls token attended
+    assert (c.head, c.vocab, c.attn_hidden) == (3, 503, 256)
     ok = synth.make_config("TFM")       # ViTEncoder / ViTEncoderV2 (learnable pos_embed) are accepted
     ok["SequenceModeling"]["params"]["fix_embed"] = False
     assert config_from_opt(ok).max_tokens == 679

@@ -109,6 +109,22 @@ def test_encoder_variants_match_reference_golden(threads, case, interp):
         assert (ctx - torch.from_numpy(g[f"ctx_{H}x{W}"])).abs().max().item() <= 1e-5
 
 
+def test_attn_base_head_matches_reference_golden(threads):
+    """Prediction.name 'Attn' (seq2seq.py): same loops as Attnv2 but the cls token is attended too."""
+    g = load_golden("attn_64x256_full")
+    cfg = synth.make_config("Attn")
+    sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias_of(g))
+    ctx, _, _ = om.encoder_forward(sd, synth.make_images(2, 64, 256, seed=2024))
+    ids, probs = om.AttnV2Head(sd, include_cls=True).greedy(ctx, 150, True)
+    assert torch.equal(ids, torch.from_numpy(g["ids"]))
+    gb = load_golden("attn_beam_64x256_end05")
+    sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias_of(gb))
+    ctx, _, _ = om.encoder_forward(sd, synth.make_images(2, 64, 256, seed=2024))
+    seq, score = om.AttnV2Head(sd, include_cls=True).beam(ctx[:1], 5, 150)
+    assert seq == gb["beam_seq"][0, : int(gb["beam_len"][0])].tolist()
+    assert abs(score - float(gb["beam_score"][0])) <= 1e-3 * abs(score)
+
+
 def test_oracle_edge_cases():
     """Quirks the engine must share: causal mask values, prefix pos-embed slice, -inf pooling pad, tie rule."""
     m = om.TFMHead.causal_mask(4)
