@@ -289,6 +289,27 @@ def test_attn_base_head_matches_golden(built_lib, precision):
         e.close()
 
 
+def test_largest_image_beam_matches_oracle(built_lib):
+    """192x896 (679 encoder tokens, the max_dimension of the shipped configs): beam-5 of both heads against the CPU
+    oracle, on weights whose beams complete within a few steps (the oracle re-runs the whole prefix every step)."""
+    from oracle import oracle_model as om
+    img = synth.make_images(1, 192, 896, seed=31)
+    for head, eb in (("TFM", 2.0), ("Attnv2", 0.5)):
+        cfg, sd = state_dict_for(head, eb)
+        e = engine_for(head, eb, "bf16x3")
+        ctx, grid, _ = e.encode(img.cuda())
+        assert tuple(grid) == (6, 113)
+        ids, lens, score, steps, _, _ = e.decode_beam(ctx, 5)
+        ctx_or, _, _ = om.encoder_forward(sd, img)
+        if head == "TFM":
+            seq, sc = om.TFMHead(sd, max_seq_len=150).beam(ctx_or, 5)
+        else:
+            seq, sc = om.AttnV2Head(sd).beam(ctx_or, 5, 150)
+        n = int(lens[0])
+        assert ids[0, :n].cpu().tolist() == seq, head
+        assert abs(float(score[0]) - sc) <= REL_TOL_FP32 * max(1.0, abs(sc))
+
+
 @pytest.mark.parametrize("beam", [3, 10])
 def test_other_beam_widths_match_oracle(built_lib, beam):
     """Beam widths other than 5 (demo/recog_cfg.yaml decodes with beam_size 10): TFM and Attnv2 heads against the CPU
