@@ -577,7 +577,13 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     }
     return last;
   };
+  // Early exit (tfm.py:138-140, :174) without draining the stream: every POLL_EVERY steps the counters are copied to
+  // pinned memory and an event is recorded, but the host only LOOKS at the copy issued one poll earlier, after it has
+  // already enqueued the next POLL_EVERY steps.  The GPU never idles on the round trip; an exit is noticed up to
+  // 2 x POLL_EVERY steps late, and the surplus steps change nothing the caller sees (done_step is latched on the device
+  // when the last row / image ends, later tokens lie beyond the returned length, finished beams are skipped).
   int executed = 0;
+  bool poll_pending = false;
   for (int t = 0; t < T; ++t) {
     if (exec) {
       CUDA_TRY(e, cudaGraphLaunch(exec, s));
@@ -587,9 +593,13 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     }
     executed = t + 1;
     if (stop_early && (executed % POLL_EVERY == 0) && executed < T) {
+      if (poll_pending) {
+        CUDA_TRY(e, cudaEventSynchronize(e->ev_poll));
+        if (all_done_step() >= 0) break;
+      }
       CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, counters_all, (size_t)4 * G * sizeof(int), cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(e, cudaStreamSynchronize(s));
-      if (all_done_step() >= 0) break;
+      CUDA_TRY(e, cudaEventRecord(e->ev_poll, s));
+      poll_pending = true;
     }
   }
   CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, counters_all, (size_t)4 * G * sizeof(int), cudaMemcpyDeviceToHost, s));

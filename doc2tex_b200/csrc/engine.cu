@@ -137,6 +137,7 @@ struct d2t_engine {
   int decode_groups = 0;      // D2T_DECODE_GROUPS / option "decode_groups": concurrent row groups of a decode call (0 = auto)
   cudaStream_t side[D2T_MAX_GROUPS] = {};   // side[g], g >= 1: stream of row group g (group 0 runs on `work`)
   cudaEvent_t ev_fork = nullptr, ev_join[D2T_MAX_GROUPS] = {};
+  cudaEvent_t ev_poll = nullptr;   // early-exit poll of the decode loop (checked one poll late, see tfm_decode)
   cudaStream_t work = nullptr;   // engine-owned stream for the decode loop (the legacy default stream cannot be captured)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 
@@ -535,7 +536,8 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
     delete e;
     return D2T_ERR_CUDA;
   }
-  bool side_ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  bool side_ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&e->ev_poll, cudaEventDisableTiming) == cudaSuccess;
   for (int g = 1; g < D2T_MAX_GROUPS && side_ok; ++g)
     side_ok = cudaStreamCreateWithPriority(&e->side[g], cudaStreamNonBlocking, prio_hi) == cudaSuccess &&
               cudaEventCreateWithFlags(&e->ev_join[g], cudaEventDisableTiming) == cudaSuccess;
@@ -564,6 +566,7 @@ int d2t_destroy(d2t_engine* e) {
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_poll) cudaEventDestroy(e->ev_poll);
   for (int g = 0; g < D2T_MAX_GROUPS; ++g) {
     if (e->side[g]) cudaStreamDestroy(e->side[g]);
     if (e->ev_join[g]) cudaEventDestroy(e->ev_join[g]);
