@@ -175,14 +175,19 @@ extern "C" int d2t_decode_attn_greedy(d2t_engine* e, const float* ctx, int B, in
     }
   }
   int executed = 0;
+  bool poll_pending = false;   // early-exit poll checked one poll late (see tfm_decode): the stream never drains
   for (int t = 0; t < T; ++t) {
     if (exec) { CUDA_TRY(e, cudaGraphLaunch(exec, s)); e->launches += nodes; }
     else if ((rc = enqueue_attn_step(e, b, ctx, B, ntok, T, want_logits, s))) return rc;
     executed = t + 1;
     if (stop_on_all_eos && (executed % POLL_EVERY == 0) && executed < T) {
+      if (poll_pending) {
+        CUDA_TRY(e, cudaEventSynchronize(e->ev_poll));
+        if (e->h_counters[2] >= 0) break;
+      }
       CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(e, cudaStreamSynchronize(s));
-      if (e->h_counters[2] >= 0) break;
+      CUDA_TRY(e, cudaEventRecord(e->ev_poll, s));
+      poll_pending = true;
     }
   }
   CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -379,14 +384,19 @@ extern "C" int d2t_decode_attn_beam(d2t_engine* e, const float* ctx, int B, int 
     }
   }
   int executed = 0;
+  bool poll_pending = false;
   for (int t = 0; t < T; ++t) {
     if (exec) { CUDA_TRY(e, cudaGraphLaunch(exec, s)); e->launches += nodes; }
     else if ((rc = enqueue_attn_beam_step(e, b, ctx, B, beam, ntok, T, s))) return rc;
     executed = t + 1;
     if ((executed % POLL_EVERY == 0) && executed < T) {   // every image has exhausted its beam (seq2seq_v2.py:124-126)
+      if (poll_pending) {
+        CUDA_TRY(e, cudaEventSynchronize(e->ev_poll));
+        if (e->h_counters[2] >= 0) break;
+      }
       CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-      CUDA_TRY(e, cudaStreamSynchronize(s));
-      if (e->h_counters[2] >= 0) break;
+      CUDA_TRY(e, cudaEventRecord(e->ev_poll, s));
+      poll_pending = true;
     }
   }
   CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, b.counters, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
