@@ -274,10 +274,14 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
   if (cluster) {
     if ((rc = enqueue_cluster_step(e, b, R, B, ntok, beam, T, s))) return rc;
   } else {
+  // greedy chain: the pick kernel of step t already wrote x of step t + 1 and advanced the counter (tfm_decode embeds GO once)
+  const bool fused_pick = beam == 0 && e->fuse_pick;
+  if (!fused_pick) {
   CUDA_TRY(e, launch_kernel(embed_tokens_kernel, dim3((R * D / 4 + 255) / 256), dim3(256), 0, s, b.tokens, L, step, par,
                             e->dev[PRED + "word_embed.weight"], e->dev[PRED + "pos_enc.pe"], b.x, R, D, sqrtf((float)D),
                             b.x_hi, b.x_lo));
   e->launches += 1;
+  }
   tl.mark("embed");
   for (int l = 0; l < c.dec_layers; ++l) {
     const std::string p = PRED + "model.layers." + std::to_string(l) + ".";
@@ -350,9 +354,18 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
     st.counters = b.counters; st.trace = b.trace; st.trace_score = b.trace_score;
     st.L = L; st.beam = beam; st.B = B; st.V = V; st.end_id = TFM_END; st.max_steps = T;
     CUDA_TRY(e, launch_kernel(beam_step_kernel, dim3(B), dim3(256), (size_t)beam * V * sizeof(float), s, b.logits, st));
+  } else if (!cluster && e->fuse_pick) {
+    CUDA_TRY(e, launch_kernel(greedy_pick_kernel, dim3(R), dim3(128), 0, s, b.logits, V, step, b.tokens, L, b.ids, T,
+                              want_logits ? b.logits_out : nullptr, b.ended, b.counters + 1, b.counters + 2, R, TFM_END,
+                              e->dev[PRED + "word_embed.weight"], e->dev[PRED + "pos_enc.pe"], b.x, b.x_hi, b.x_lo, D,
+                              sqrtf((float)D), step, b.counters + 3));
+    e->launches += 1;
+    tl.mark("pick+embed+advance");
+    return 0;
   } else {
     CUDA_TRY(e, launch_kernel(greedy_pick_kernel, dim3(R), dim3(128), 0, s, b.logits, V, step, b.tokens, L, b.ids, T,
-                              want_logits ? b.logits_out : nullptr, b.ended, b.counters + 1, b.counters + 2, R, TFM_END));
+                              want_logits ? b.logits_out : nullptr, b.ended, b.counters + 1, b.counters + 2, R, TFM_END,
+                              nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0.f, nullptr, nullptr));
   }
   e->launches += 1;
   tl.mark("pick");
@@ -526,6 +539,15 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     return 0;
   });
   if (rc) return rc;
+  if (beam == 0 && e->fuse_pick && !cluster_step_active(e)) {   // x of step 0 = embedding of GO; later steps: written by the pick kernel
+    for (TfmGroup& grp : groups) {
+      const TfmBuffers& b = grp.b;
+      CUDA_TRY(e, launch_kernel(embed_tokens_kernel, dim3((grp.Rg * D / 4 + 255) / 256), dim3(256), 0, s, b.tokens, T + 1,
+                                b.counters, 0LL, e->dev[PRED + "word_embed.weight"], e->dev[PRED + "pos_enc.pe"], b.x, grp.Rg, D,
+                                sqrtf((float)D), b.x_hi, b.x_lo));
+      e->launches += 1;
+    }
+  }
   auto enqueue_step = [&]() -> int {
     return for_each_group_parallel(e, groups, s, [&](TfmGroup& grp, cudaStream_t gs) -> int {
       return enqueue_tfm_step(e, grp.b, grp.Rg, grp.Bg, ntok, beam, T, want_logits, gs);

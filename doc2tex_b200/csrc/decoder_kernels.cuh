@@ -347,12 +347,19 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* 
 __global__ void greedy_pick_kernel(const float* __restrict__ logits, int V, const int* __restrict__ step,
                                    int* __restrict__ tokens, int tok_ld, long long* __restrict__ ids, int ids_ld,
                                    float* __restrict__ logits_out, int* __restrict__ ended, int* __restrict__ n_ended,
-                                   int* __restrict__ done_step, int R, int end_id) {
+                                   int* __restrict__ done_step, int R, int end_id,
+                                   // optional fusion of the NEXT step's token embedding and of the step counter (emb != nullptr):
+                                   // x[r] = E[picked] * mult + pe[t + 1] (+ bf16 planes); the last block to finish advances *step_rw
+                                   const float* __restrict__ emb = nullptr, const float* __restrict__ pe = nullptr,
+                                   float* __restrict__ xn = nullptr, __nv_bfloat16* __restrict__ xn_hi = nullptr,
+                                   __nv_bfloat16* __restrict__ xn_lo = nullptr, int D = 0, float mult = 0.f,
+                                   int* __restrict__ step_rw = nullptr, int* __restrict__ ticket = nullptr) {
   pdl_wait();      // PDL: everything above overlapped the predecessor
   pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
   __shared__ float red_v[32];
   __shared__ int red_i[32];
   __shared__ float s_max, s_sum;
+  __shared__ int s_tok;
   const int r = blockIdx.x;
   const int t = *step;
   const float* x = logits + (size_t)r * V;
@@ -398,6 +405,34 @@ __global__ void greedy_pick_kernel(const float* __restrict__ logits, int V, cons
       ended[r] = 1;
       const int n = atomicAdd(n_ended, 1) + 1;
       if (n == R) *done_step = t + 1;
+    }
+    s_tok = bi;
+  }
+  if (emb == nullptr) return;
+  __syncthreads();
+  const int tok = s_tok;
+  for (int i = threadIdx.x; i < D / 4; i += blockDim.x) {
+    const float4 e4 = *reinterpret_cast<const float4*>(emb + (size_t)tok * D + 4 * i);
+    const float4 p4 = *reinterpret_cast<const float4*>(pe + (size_t)(t + 1) * D + 4 * i);
+    const float4 o = make_float4(e4.x * mult + p4.x, e4.y * mult + p4.y, e4.z * mult + p4.z, e4.w * mult + p4.w);
+    *reinterpret_cast<float4*>(xn + (size_t)r * D + 4 * i) = o;
+    if (xn_hi) {
+      const float f[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        __nv_bfloat16 hi, lo;
+        split_bf16(f[u], hi, lo);
+        xn_hi[(size_t)r * D + 4 * i + u] = hi;
+        if (xn_lo) xn_lo[(size_t)r * D + 4 * i + u] = lo;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {   // every block has read *step before it takes a ticket; the last one advances the counter
+    __threadfence();
+    if (atomicAdd(ticket, 1) == (int)gridDim.x - 1) {
+      *ticket = 0;
+      *step_rw = t + 1;
     }
   }
 }

@@ -117,6 +117,7 @@ struct d2t_engine {
   bool time_conv = false;   // option "time_conv": bracket layer3.1.conv1 with events (d2t_debug_conv_time)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
   double conv_flops = 0.0;
+  bool fuse_pick = true;    // D2T_FUSE_PICK=0: separate embed / advance launches in the greedy decode step
   bool lean_acts = true;    // D2T_LEAN_ACTS=0: every stem layer writes fp32 AND operand planes, read or not
   bool attn_group = false;  // D2T_ATTN_GROUP=1 / option "attn_group": beam-grouped decode attention (measured slower, off)
   int split_k = 1;       // D2T_SPLIT_K / option "split_k": 0 = never, 1 = auto split-K of the LayerNorm-fed decode projections
@@ -521,6 +522,7 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   if (const char* v = getenv("D2T_SPLIT_K")) e->split_k = atoi(v);
   if (const char* v = getenv("D2T_ATTN_GROUP")) e->attn_group = atoi(v) != 0;
   if (const char* v = getenv("D2T_LEAN_ACTS")) e->lean_acts = atoi(v) != 0;
+  if (const char* v = getenv("D2T_FUSE_PICK")) e->fuse_pick = atoi(v) != 0;
   if (const char* v = getenv("D2T_CLUSTER_STEP")) e->use_cluster_step = atoi(v) != 0;
   if (cudaMallocHost(&e->h_counters, 4 * D2T_MAX_GROUPS * sizeof(int)) != cudaSuccess) {
     g_create_error = "cudaMallocHost failed";
