@@ -289,6 +289,27 @@ def test_attn_base_head_matches_golden(built_lib, precision):
         e.close()
 
 
+def test_eager_launches_equal_graph_replay(built_lib):
+    """use_graphs: False enqueues every decode step kernel by kernel; tokens, logits and beams must equal the CUDA-graph
+    replay (same kernels, same order), for both TFM decodes and the Attnv2 greedy."""
+    from doc2tex_b200.engine import Engine
+    for head, eb in (("TFM", 1.5), ("Attnv2", 3.0)):
+        cfg, sd = state_dict_for(head, eb)
+        img = synth.make_images(3, 64, 256, seed=5).cuda()
+        outs = []
+        for graphs in (True, False):
+            e = Engine(cfg, "cuda:0", precision="bf16x3", use_graphs=graphs)
+            e.load_state_dict(sd)
+            ctx, _, _ = e.encode(img)
+            ids, logits, steps = e.decode_greedy(ctx, is_test=True)
+            beam = e.decode_beam(ctx, 5)
+            outs.append((ids.cpu(), logits.cpu(), steps, beam[0].cpu(), beam[1].cpu(), beam[2].cpu()))
+            e.close()
+        a, b = outs
+        assert a[2] == b[2] and torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        assert torch.equal(a[3], b[3]) and torch.equal(a[4], b[4]) and torch.equal(a[5], b[5])
+
+
 def test_largest_image_beam_matches_oracle(built_lib):
     """192x896 (679 encoder tokens, the max_dimension of the shipped configs): beam-5 of both heads against the CPU
     oracle, on weights whose beams complete within a few steps (the oracle re-runs the whole prefix every step)."""
