@@ -156,3 +156,17 @@ def test_merged_decode_split_recovers_per_batch_steps():
     res = {"ids": ids, "lens": torch.arange(5), "scores": torch.arange(5.0), "steps": 9}
     outb = pipe._split(res, [2, 1, 2])
     assert torch.equal(outb[1]["lens"], torch.tensor([2])) and torch.equal(outb[2]["ids"], ids[3:5])
+
+
+def test_infer_cli_keeps_the_reference_flags():
+    """api/infer.py mirrors the reference CLI (api/infer.py:359-387 of the reference): every flag it defines must stay
+    accepted; --precision and --synthetic are this repo's additions."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "api", "infer.py")).read()
+    ours = set(re.findall(r"[\"'](--[a-z_A-Z0-9]+)[\"']", src))
+    reference = {"--amp", "--batch_size", "--config", "--console", "--csv_dir", "--data_dir", "--log_path", "--num_workers",
+                 "--resizer", "--start_idx", "--strong_log"}
+    assert reference <= ours
+    assert ours - reference == {"--precision", "--synthetic"}
