@@ -32,17 +32,13 @@ struct ConvGemm {
   const void* a_map_hi;    // optional host pointers to CUtensorMap of pre-split A planes [M, K] (TMA-fed A operand)
   const void* a_map_lo;
   long long* dbg;          // optional: CTA 0 writes phase timestamps (globaltimer ns) for latency debugging
-  // optional fused LayerNorm over the full output row (N == 256, TMA-fed-A tensor-core path only):
-  // out = LN(acc*scale + shift + res) * ln_w + ln_b   (post-norm decoder layers: norm(x + sublayer(x)))
-  const float* ln_w;
-  const float* ln_b;
-  float ln_eps;
   // optional split-K (TMA-fed-A tensor-core path): the K range is cut into k_splits slices, slice s is computed by its own
   // CTA and stored (without activation; bias / residual only in slice 0) at out + s * split_stride; the consumer (the
   // LayerNorm kernel) adds the slices.  A tcgen05.mma retires every ~90 ns whatever its N, so a K=1024 bf16x3 projection
   // is 192 serial MMAs = 17 us on one CTA; eight slices take 2 us each.
   int out2_bf16;           // out2 (the KV-cache slot) holds bf16 elements (single-pass bf16 mode): same element offsets
   int k_splits;            // 0 / 1 = no split
+  int stack;               // bf16x3, TMA-fed-A path: 1 = two MMAs per k-step against the stacked [W_hi ; W_lo] operand (see gemm_tc.cuh)
   long long split_stride;  // elements between partial outputs
   // optional bf16 hi/lo NHWC planes of the INPUT activation (cp.async-fed A operand of conv_gemm_tc3_kernel)
   const __nv_bfloat16* x_hi;

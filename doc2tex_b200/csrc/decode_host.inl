@@ -43,77 +43,89 @@ int pool_get(d2t_engine* e, T** out, size_t n) {
   return 0;
 }
 
-int dec_linear(d2t_engine* e, ConvGemm p, cudaStream_t s) { return run_contraction(e, p, nullptr, e->cfg.precision, s); }
+int dec_linear(d2t_engine* e, ConvGemm p, cudaStream_t s) {
+  p.stack = e->stack_mma ? 1 : 0;   // honoured by the TMA-fed-A bf16x3 kernel only
+  return run_contraction(e, p, nullptr, e->cfg.precision, s);
+}
 
 // KV caches are fp32 except in the single-pass bf16 mode, where K/V are stored as bf16 (half the attention traffic;
 // the operands of every projection are bf16 there anyway).  Buffers keep their float* type; element offsets are equal.
-bool kv_is_bf16(const d2t_engine* e) {
-  static const bool off = getenv("D2T_KV_BF16") && atoi(getenv("D2T_KV_BF16")) == 0;
-  return e->cfg.precision == D2T_PREC_BF16 && !off;
-}
+bool kv_is_bf16(const d2t_engine* e) { return e->cfg.precision == D2T_PREC_BF16 && e->kv_bf16; }
+
+// option "time_decode": CUDA events around one launch (eager decode only; events cannot be timed inside a captured graph)
+struct DecTimer {
+  d2t_engine* e; cudaStream_t s; bool on; d2t_engine::DecEvent ev;
+  DecTimer(d2t_engine* e_, bool want, int kind, double bytes, cudaStream_t s_) : e(e_), s(s_), on(false) {
+    if (!want || !e->time_decode || e->dec_events.size() >= 8192) return;
+    ev.kind = kind; ev.bytes = bytes;
+    if (cudaEventCreate(&ev.a) != cudaSuccess) return;
+    if (cudaEventCreate(&ev.b) != cudaSuccess) { cudaEventDestroy(ev.a); return; }
+    cudaEventRecord(ev.a, s);
+    on = true;
+  }
+  ~DecTimer() {
+    if (!on) return;
+    cudaEventRecord(ev.b, s);
+    e->dec_events.push_back(ev);
+  }
+};
 
 int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long row_stride, const int* anc,
                       long long anc_parity, int anc_ld, int rows_per_src, const int* step, int n_fixed,
                       float* out, __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, int R, cudaStream_t s) {
   const int heads = e->cfg.dec_heads, D = e->cfg.hidden;
   if (heads > 8) return e->fail(D2T_ERR_UNSUPPORTED, "decode attention supports at most 8 heads per row block");
-  static const int split_env = getenv("D2T_ATTN_SPLIT") ? atoi(getenv("D2T_ATTN_SPLIT")) : 0;
   // few rows: the loads in flight per SM, not the bandwidth, bound the kernel -> two warps per (row, head)
-  const int split = split_env > 0 ? split_env : (R <= 4 * e->num_sms && heads == 8 ? 2 : 1);
-  static const int hb_env = getenv("D2T_ATTN_HB") ? atoi(getenv("D2T_ATTN_HB")) : 2;
-  // beam search: the hypotheses of an image share the encoder memory and most of their prefixes.  The grouped kernel fetches
-  // every shared record once — and is measured 2x SLOWER than the per-row kernel (self 68 vs 36 us, cross 47 vs 24 us at
-  // 1 280 rows): this attention is bound by issue / latency per warp (125 registers -> 16 warps per SM, five dependent
-  // online-softmax updates per key), not by the L2-served traffic it saves.  Off by default (option "attn_group").
-  if (e->attn_group && rows_per_src == 5 && heads == 8 && R % 5 == 0 && anc_ld <= BEAM_ATT_ANC_LD && n_fixed < 1024) {
-    const int B = R / 5;
-    const int src_mul = anc ? 5 : 1;
-    cudaError_t st;
-    if (kv_is_bf16(e))
-      st = launch_kernel(decode_attention_beam_kernel<32, 5, __nv_bfloat16>, dim3(B * 4), dim3(256), 0, s, q, D,
-                         reinterpret_cast<const __nv_bfloat16*>(kv), row_stride, 2 * D, anc, anc_parity, anc_ld, src_mul, step,
-                         n_fixed, out, D, out_hi, out_lo);
+  const int split = e->attn_split > 0 ? e->attn_split : (R <= 4 * e->num_sms && heads == 8 ? 2 : 1);
+  const bool kv16 = kv_is_bf16(e);
+  const __nv_bfloat16* kvh = reinterpret_cast<const __nv_bfloat16*>(kv);
+  cudaError_t st;
+  // Beam search: the hypotheses of an image share the encoder memory and most of their prefixes.  One block owns ALL
+  // hypotheses of an image (for a slice of the heads), so their loads of a shared record are issued together on one SM and
+  // every fetch after the first is an L1 hit; the per-row mapping spreads them over SMs and pays L2 -> SM for each
+  // (ncu, 1 280 rows: 265 MB through L2 for 57 MB of DRAM reads, L1 hit rate 7 %).
+  if (e->attn_image_block && rows_per_src > 1 && heads == 8 && R % rows_per_src == 0 && rows_per_src <= 16) {
+    const int G = rows_per_src, B = R / G;
+    const int sp = (e->attn_split == 1 || G > 8) ? 1 : 2;
+    int nh = 8;
+    while (nh > 1 && G * nh * sp > 32) nh >>= 1;   // block = G beams x nh heads x sp key splits warps (<= 32)
+    const dim3 grid(B * (8 / nh)), block(G * nh * sp * 32);
+    const size_t smem = sp > 1 ? (size_t)G * nh * (sp - 1) * 36 * sizeof(float) : 0;
+    if (kv16)
+      st = sp == 2 ? launch_kernel(decode_attention_image_kernel<32, 2, __nv_bfloat16>, grid, block, smem, s, q, D, kvh, row_stride, 2 * D, anc, anc_parity, anc_ld, G, nh, step, n_fixed, out, D, out_hi, out_lo)
+                   : launch_kernel(decode_attention_image_kernel<32, 1, __nv_bfloat16>, grid, block, smem, s, q, D, kvh, row_stride, 2 * D, anc, anc_parity, anc_ld, G, nh, step, n_fixed, out, D, out_hi, out_lo);
     else
-      st = launch_kernel(decode_attention_beam_kernel<32, 5, float>, dim3(B * 4), dim3(256), 0, s, q, D, kv, row_stride, 2 * D,
-                         anc, anc_parity, anc_ld, src_mul, step, n_fixed, out, D, out_hi, out_lo);
+      st = sp == 2 ? launch_kernel(decode_attention_image_kernel<32, 2, float>, grid, block, smem, s, q, D, kv, row_stride, 2 * D, anc, anc_parity, anc_ld, G, nh, step, n_fixed, out, D, out_hi, out_lo)
+                   : launch_kernel(decode_attention_image_kernel<32, 1, float>, grid, block, smem, s, q, D, kv, row_stride, 2 * D, anc, anc_parity, anc_ld, G, nh, step, n_fixed, out, D, out_hi, out_lo);
     CUDA_TRY(e, st);
     e->launches += 1;
     return 0;
   }
-  if (kv_is_bf16(e)) {
-    const __nv_bfloat16* kv16 = reinterpret_cast<const __nv_bfloat16*>(kv);
-    if (split >= 2 && heads == 8) {
-      CUDA_TRY(e, launch_kernel(decode_attention_kernel<32, 2, 2, __nv_bfloat16>, dim3(R * 2), dim3(256), 0, s, q, D, kv16, row_stride,
-                                2 * D, anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
-    } else {
-      CUDA_TRY(e, launch_kernel(decode_attention_kernel<32, 1, 1, __nv_bfloat16>, dim3(R), dim3(heads * 32), 0, s, q, D, kv16,
-                                row_stride, 2 * D, anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
-    }
-  } else if (split >= 2 && heads == 8 && hb_env >= 2) {
-    CUDA_TRY(e, launch_kernel(decode_attention_kernel<32, 2, 2>, dim3(R * 2), dim3(256), 0, s, q, D, kv, row_stride, 2 * D,
-                              anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
+  if (kv16) {
+    if (split >= 2 && heads == 8)
+      st = launch_kernel(decode_attention_kernel<32, 2, 2, __nv_bfloat16>, dim3(R * 2), dim3(256), 0, s, q, D, kvh, row_stride,
+                         2 * D, anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo);
+    else
+      st = launch_kernel(decode_attention_kernel<32, 1, 1, __nv_bfloat16>, dim3(R), dim3(heads * 32), 0, s, q, D, kvh,
+                         row_stride, 2 * D, anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo);
+  } else if (split >= 2 && heads == 8) {
+    st = launch_kernel(decode_attention_kernel<32, 2, 2>, dim3(R * 2), dim3(256), 0, s, q, D, kv, row_stride, 2 * D,
+                       anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo);
   } else {
-    auto kern = split >= 2 && heads == 8 ? decode_attention_kernel<32, 2> : decode_attention_kernel<32, 1>;
-    CUDA_TRY(e, launch_kernel(kern, dim3(R), dim3(heads * 32 * (split >= 2 && heads == 8 ? 2 : 1)), 0, s, q, D, kv, row_stride, 2 * D,
-                              anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo));
+    st = launch_kernel(decode_attention_kernel<32, 1>, dim3(R), dim3(heads * 32), 0, s, q, D, kv, row_stride, 2 * D,
+                       anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo);
   }
+  CUDA_TRY(e, st);
   e->launches += 1;
   return 0;
 }
 
 // One decoder step for R rows (tfm.py:125-135 / 152-169 with a KV cache):
 // nn.TransformerDecoderLayer defaults = post-norm, ReLU, eps 1e-5.
-// x = LayerNorm(g) with g = sublayer GEMM + bias + residual (post-norm decoder layer).  On the tensor-core path the
-// LayerNorm is fused into the GEMM epilogue (4-CTA cluster per row block); the result replaces b.x in place — safe
-// because each CTA reads its residual tile (prefetched before the MMA wait) before any CTA of its cluster stores.
-// Otherwise: GEMM -> b.x2, then the stand-alone LayerNorm kernel.
+// x = LayerNorm(g) with g = sublayer GEMM + bias + residual (post-norm decoder layer): GEMM -> b.x2 (split-K partials),
+// then the LayerNorm kernel, which adds the slices.
 int linear_ln(d2t_engine* e, ConvGemm g, const TfmBuffers& b, const float* lw, const float* lb, int R, int D, cudaStream_t s) {
   const bool tc = e->cfg.precision == D2T_PREC_BF16X3 || e->cfg.precision == D2T_PREC_BF16;
-  if (tc && b.planes && e->fuse_ln && tc_can_fuse_ln(g, e->active_sms) && e->tcw.count(g.w)) {
-    g.ln_w = lw; g.ln_b = lb; g.ln_eps = 1e-5f;
-    g.out = b.x; g.out_hi = b.x_hi; g.out_lo = b.x_lo;
-    return dec_linear(e, g, s);
-  }
   // split-K over extra CTAs: the serial tcgen05.mma chain of one tile (K/16 x passes instructions, ~90 ns each) is the
   // critical path of these projections; the LayerNorm kernel adds the slices
   int parts = 1;
@@ -179,7 +191,7 @@ int prepare_cluster_step(d2t_engine* e) {
   }
   if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "cluster step kernel setup: %s", cudaGetErrorString(st));
   e->cs_plan.ready = e->cs_plan.max_clusters[0] > 0 && e->cs_plan.max_clusters[1] > 0;
-  if (getenv("D2T_DBG_DECODE"))
+  if (e->dbg_decode)
     fprintf(stderr, "[cluster step] co-resident clusters: %d (16 rows), %d (32 rows)\n", e->cs_plan.max_clusters[0], e->cs_plan.max_clusters[1]);
   return 0;
 }
@@ -299,8 +311,12 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
       if ((rc = dec_linear(e, g, s))) return rc;
     }
     if (l == 1) tl.mark("qkv");
-    if ((rc = enqueue_attention(e, b.q, selfkv, (long long)T * 2 * D, beam > 0 ? b.anc : nullptr, par, L,
-                                beam > 0 ? beam : 1, step, 0, b.att, b.att_hi, b.att_lo, R, s))) return rc;
+    {
+      // algorithmic bytes: every row reads the K and V records of its t + 1 prefix positions
+      DecTimer tm(e, l == 1, 0, (double)R * (e->cur_step + 1) * 2 * D * (kv_is_bf16(e) ? 2 : 4), s);
+      if ((rc = enqueue_attention(e, b.q, selfkv, (long long)T * 2 * D, beam > 0 ? b.anc : nullptr, par, L,
+                                  beam > 0 ? beam : 1, step, 0, b.att, b.att_hi, b.att_lo, R, s))) return rc;
+    }
     if (l == 1) tl.mark("self-attn");
     {
       ConvGemm g = linear_params(b.att, e->dev[p + "self_attn.out_proj.weight"], e->dev[p + "self_attn.out_proj.bias"], b.x2, R, D, D);
@@ -315,8 +331,12 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
       if ((rc = dec_linear(e, g, s))) return rc;
     }
     if (l == 1) tl.mark("q2");
-    if ((rc = enqueue_attention(e, b.q, crosskv, (long long)ntok * 2 * D, nullptr, 0, 0, beam > 0 ? beam : 1, nullptr,
-                                ntok, b.att, b.att_hi, b.att_lo, R, s))) return rc;
+    {
+      // algorithmic bytes: the encoder memory of an image is shared by its hypotheses -> B x ntok records
+      DecTimer tm(e, l == 1, 1, (double)B * ntok * 2 * D * (kv_is_bf16(e) ? 2 : 4), s);
+      if ((rc = enqueue_attention(e, b.q, crosskv, (long long)ntok * 2 * D, nullptr, 0, 0, beam > 0 ? beam : 1, nullptr,
+                                  ntok, b.att, b.att_hi, b.att_lo, R, s))) return rc;
+    }
     if (l == 1) tl.mark("cross-attn");
     {
       ConvGemm g = linear_params(b.att, e->dev[p + "multihead_attn.out_proj.weight"], e->dev[p + "multihead_attn.out_proj.bias"], b.x2, R, D, D);
@@ -353,8 +373,11 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
     st.finished = b.finished; st.done_seq = b.done_seq; st.done_len = b.done_len; st.done_score = b.done_score;
     st.counters = b.counters; st.trace = b.trace; st.trace_score = b.trace_score;
     st.L = L; st.beam = beam; st.B = B; st.V = V; st.end_id = TFM_END; st.max_steps = T;
+    // algorithmic bytes: the logits of every row, and the token + ancestry prefixes read from one buffer and written to the other
+    DecTimer tm(e, true, 2, (double)R * V * 4 + 4.0 * R * (e->cur_step + 1) * 4, s);
     CUDA_TRY(e, launch_kernel(beam_step_kernel, dim3(B), dim3(256), (size_t)beam * V * sizeof(float), s, b.logits, st));
   } else if (!cluster && e->fuse_pick) {
+    DecTimer tm(e, true, 3, (double)R * V * 4 * (want_logits ? 2 : 1) + (double)R * D * 4, s);
     CUDA_TRY(e, launch_kernel(greedy_pick_kernel, dim3(R), dim3(128), 0, s, b.logits, V, step, b.tokens, L, b.ids, T,
                               want_logits ? b.logits_out : nullptr, b.ended, b.counters + 1, b.counters + 2, R, TFM_END,
                               e->dev[PRED + "word_embed.weight"], e->dev[PRED + "pos_enc.pe"], b.x, b.x_hi, b.x_lo, D,
@@ -404,11 +427,11 @@ int alloc_group(d2t_engine* e, TfmGroup& grp, int ntok, int beam, int T, bool wa
   if ((rc = pool_get(e, &b.ffn, (size_t)R * F))) return rc;
   if ((rc = pool_get(e, &b.logits, (size_t)R * V))) return rc;
   b.counters = counters;
-  if (getenv("D2T_DBG_DECODE") && grp.B0 == 0) {
+  if (e->dbg_decode && grp.B0 == 0) {
     if ((rc = pool_get(e, &b.dbg, 64))) return rc;
     CUDA_TRY(e, cudaMemsetAsync(b.dbg, 0, 64 * sizeof(long long), s));
   }
-  if (getenv("D2T_DBG_TIMELINE") && grp.B0 == 0) {
+  if (e->dbg_timeline && grp.B0 == 0) {
     if ((rc = pool_get(e, &b.timeline, 64))) return rc;
     CUDA_TRY(e, cudaMemsetAsync(b.timeline, 0, 64 * sizeof(long long), s));
   }
@@ -554,11 +577,11 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     });
   };
 
-  // ---- step graph ----
-  cudaGraphExec_t exec = nullptr;
-  int nodes = 0;
-  if (c.use_graphs) {
-    std::vector<long long> key = {(long long)B, G, ntok, beam, T, want_logits ? 1 : 0};
+  // ---- step graphs: `spg` consecutive steps per graph (the step index lives on the device, so one graph serves every
+  // step), plus a one-step graph for the tail ----
+  const int spg = e->steps_per_graph < 1 ? 1 : e->steps_per_graph;
+  auto get_graph = [&](int n_steps, cudaGraphExec_t* exec_out, int* nodes_out) -> int {
+    std::vector<long long> key = {(long long)B, G, ntok, beam, T, want_logits ? 1 : 0, n_steps};
     for (const TfmGroup& grp : groups) {
       const TfmBuffers& b = grp.b;
       const void* ptrs[] = {b.crosskv, b.selfkv, b.x, b.x2, b.q, b.att, b.ffn, b.logits, b.counters, b.tokens, b.anc,
@@ -567,27 +590,35 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
                             b.crosskv_tmp, b.crosskv_f32};
       for (const void* q : ptrs) key.push_back((long long)(uintptr_t)q);
     }
-    for (auto& g : e->graphs) if (g.key == key) { exec = g.exec; nodes = g.nodes; }
-    if (!exec) {
-      cudaGraph_t graph = nullptr;
-      CUDA_TRY(e, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-      const int64_t before = e->launches;
-      rc = enqueue_step();
-      nodes = (int)(e->launches - before);
-      e->launches = before;
-      cudaError_t st = cudaStreamEndCapture(s, &graph);
-      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-      if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(st));
-      st = cudaGraphInstantiate(&exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(st));
-      if (e->graphs.size() >= 16) {  // bounded cache
-        cudaGraphExecDestroy(e->graphs.front().exec);
-        e->graphs.erase(e->graphs.begin());
-      }
-      d2t_engine::GraphEntry ge; ge.key = key; ge.exec = exec; ge.nodes = nodes;
-      e->graphs.push_back(ge);
+    for (auto& g : e->graphs) if (g.key == key) { *exec_out = g.exec; *nodes_out = g.nodes; return 0; }
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(e, cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int64_t before = e->launches;
+    int rc2 = 0;
+    for (int i = 0; i < n_steps && !rc2; ++i) rc2 = enqueue_step();
+    const int nodes = (int)(e->launches - before);
+    e->launches = before;
+    cudaError_t st = cudaStreamEndCapture(s, &graph);
+    if (rc2) { if (graph) cudaGraphDestroy(graph); return rc2; }
+    if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(st));
+    cudaGraphExec_t exec = nullptr;
+    st = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(st));
+    if (e->graphs.size() >= 16) {  // bounded cache
+      cudaGraphExecDestroy(e->graphs.front().exec);
+      e->graphs.erase(e->graphs.begin());
     }
+    d2t_engine::GraphEntry ge; ge.key = key; ge.exec = exec; ge.nodes = nodes;
+    e->graphs.push_back(ge);
+    *exec_out = exec; *nodes_out = nodes;
+    return 0;
+  };
+  cudaGraphExec_t exec_n = nullptr, exec_1 = nullptr;
+  int nodes_n = 0, nodes_1 = 0;
+  if (c.use_graphs && !e->time_decode) {
+    if (spg > 1 && T >= spg && (rc = get_graph(spg, &exec_n, &nodes_n))) return rc;
+    if ((spg == 1 || T % spg != 0 || T < spg) && (rc = get_graph(1, &exec_1, &nodes_1))) return rc;
   }
   // the reference stops when EVERY row / image of the batch is done: all groups done, at the latest group's step
   auto all_done_step = [&]() -> int {
@@ -606,15 +637,22 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
   // when the last row / image ends, later tokens lie beyond the returned length, finished beams are skipped).
   int executed = 0;
   bool poll_pending = false;
-  for (int t = 0; t < T; ++t) {
-    if (exec) {
-      CUDA_TRY(e, cudaGraphLaunch(exec, s));
-      e->launches += nodes;
-    } else if ((rc = enqueue_step())) {
-      return rc;
+  while (executed < T) {
+    int did = 1;
+    if (exec_n && T - executed >= spg) {
+      CUDA_TRY(e, cudaGraphLaunch(exec_n, s));
+      e->launches += nodes_n;
+      did = spg;
+    } else if (exec_1) {
+      CUDA_TRY(e, cudaGraphLaunch(exec_1, s));
+      e->launches += nodes_1;
+    } else {
+      e->cur_step = executed;
+      if ((rc = enqueue_step())) return rc;
     }
-    executed = t + 1;
-    if (stop_early && (executed % POLL_EVERY == 0) && executed < T) {
+    const int before = executed;
+    executed += did;
+    if (stop_early && (executed / POLL_EVERY != before / POLL_EVERY) && executed < T) {
       if (poll_pending) {
         CUDA_TRY(e, cudaEventSynchronize(e->ev_poll));
         if (all_done_step() >= 0) break;

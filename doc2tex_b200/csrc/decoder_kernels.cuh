@@ -71,33 +71,12 @@ __device__ __forceinline__ float4 kv_load4(const __nv_bfloat16* p) {
   return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
 
-// HB > 1: the heads of a row are spread over HB blocks (grid = rows x HB, 8 / HB heads each): 512 quarter-size blocks
-// balance over 148 SMs better than 256 full ones.
-template <int HD, int SPLIT = 1, int HB = 1, typename KV = float>
-__global__ void __launch_bounds__(256 * SPLIT / HB)
-decode_attention_kernel(const float* __restrict__ q, int ldq, const KV* __restrict__ kv,
-                        long long row_stride, int pos_stride, const int* __restrict__ anc,
-                        long long anc_parity_stride, int anc_ld, int rows_per_src,
-                        const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
-                        __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
-  static_assert(HD == 32, "8 lanes x float4 per head slice");
-  pdl_wait();      // PDL: everything above overlapped the predecessor
-  pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
-  const int r = HB == 1 ? blockIdx.x : blockIdx.x / HB;
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nheads = blockDim.x / (32 * SPLIT);                       // heads of this block
-  const int hl = SPLIT == 1 ? wid : wid % nheads, sp = SPLIT == 1 ? 0 : wid / nheads;
-  const int h = HB == 1 ? hl : (blockIdx.x % HB) * nheads + hl;
-  const int g = lane >> 3, c = (lane & 7) * 4;
-  const int t = step ? *step : 0;
-  const int n_keys = n_fixed > 0 ? n_fixed : t + 1;
-  const int* anc_r = anc ? anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)r * anc_ld : nullptr;
-  const int src_base = (r / rows_per_src) * (anc ? rows_per_src : 1);
-  const float scale = rsqrtf((float)HD);
-  float4 q4 = *reinterpret_cast<const float4*>(q + (size_t)r * ldq + h * HD + c);
-  q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
-  const KV* kbase = kv + h * HD + c;
-
+// The key walk of one (row, head) by one warp: returns the warp-merged online-softmax state (every lane holds gm / sum,
+// lane c holds its 4 output channels summed over the four quarter warps).  Keys j = g + 8 * sp (mod 8 * SPLIT).
+template <int SPLIT, typename KV>
+__device__ __forceinline__ void attention_walk(const float4 q4, const KV* __restrict__ kbase, long long row_stride,
+                                               int pos_stride, const int* __restrict__ anc_r, int src_base, int n_keys,
+                                               int g, int sp, int D, float& gm_out, float& sum_out, float4& acc_out) {
   float mx = -INFINITY, sum = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const unsigned gmask = 0xFFu << (g * 8);   // quarter warps run different trip counts: group-local shuffles
@@ -144,6 +123,72 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const KV* __restri
     acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
     acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
   }
+  gm_out = gm; sum_out = sum; acc_out = acc;
+}
+
+// split 0 folds the states the other key splits left in shared memory ([SPLIT - 1][max, sum, pad, pad, acc[32]]) into its own
+template <int SPLIT>
+__device__ __forceinline__ void attention_merge_splits(const float* __restrict__ parts, int c, float gm, float& sum, float4& acc) {
+  float M = gm;
+#pragma unroll
+  for (int q = 0; q < SPLIT - 1; ++q) M = fmaxf(M, parts[q * 36]);
+  const float w0 = (gm == -INFINITY) ? 0.f : expf(gm - M);
+  sum *= w0; acc.x *= w0; acc.y *= w0; acc.z *= w0; acc.w *= w0;
+#pragma unroll
+  for (int q = 0; q < SPLIT - 1; ++q) {
+    const float* pp = parts + q * 36;
+    const float wq = (pp[0] == -INFINITY) ? 0.f : expf(pp[0] - M);
+    const float4 a = *reinterpret_cast<const float4*>(pp + 4 + c);
+    sum = fmaf(wq, pp[1], sum);
+    acc.x = fmaf(wq, a.x, acc.x); acc.y = fmaf(wq, a.y, acc.y); acc.z = fmaf(wq, a.z, acc.z); acc.w = fmaf(wq, a.w, acc.w);
+  }
+}
+
+__device__ __forceinline__ void attention_store(const float4 acc, float sum, size_t off, float* __restrict__ out,
+                                                __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  const float inv = 1.0f / sum;
+  const float4 o4 = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
+  *reinterpret_cast<float4*>(out + off) = o4;
+  if (out_hi) {
+    const float f[4] = {o4.x, o4.y, o4.z, o4.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      __nv_bfloat16 hi, lo;
+      split_bf16(f[u], hi, lo);
+      out_hi[off + u] = hi;
+      if (out_lo) out_lo[off + u] = lo;
+    }
+  }
+}
+
+// HB > 1: the heads of a row are spread over HB blocks (grid = rows x HB, 8 / HB heads each): 512 quarter-size blocks
+// balance over 148 SMs better than 256 full ones.
+template <int HD, int SPLIT = 1, int HB = 1, typename KV = float>
+__global__ void __launch_bounds__(256 * SPLIT / HB)
+decode_attention_kernel(const float* __restrict__ q, int ldq, const KV* __restrict__ kv,
+                        long long row_stride, int pos_stride, const int* __restrict__ anc,
+                        long long anc_parity_stride, int anc_ld, int rows_per_src,
+                        const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
+                        __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  static_assert(HD == 32, "8 lanes x float4 per head slice");
+  pdl_wait();      // PDL: everything above overlapped the predecessor
+  pdl_trigger();   // allow exactly one successor to pre-launch (chain depth 1: pre-launched CTAs hold SM resources)
+  const int r = HB == 1 ? blockIdx.x : blockIdx.x / HB;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nheads = blockDim.x / (32 * SPLIT);                       // heads of this block
+  const int hl = SPLIT == 1 ? wid : wid % nheads, sp = SPLIT == 1 ? 0 : wid / nheads;
+  const int h = HB == 1 ? hl : (blockIdx.x % HB) * nheads + hl;
+  const int g = lane >> 3, c = (lane & 7) * 4;
+  const int t = step ? *step : 0;
+  const int n_keys = n_fixed > 0 ? n_fixed : t + 1;
+  const int* anc_r = anc ? anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)r * anc_ld : nullptr;
+  const int src_base = (r / rows_per_src) * (anc ? rows_per_src : 1);
+  const float scale = rsqrtf((float)HD);
+  float4 q4 = *reinterpret_cast<const float4*>(q + (size_t)r * ldq + h * HD + c);
+  q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
+  float gm, sum;
+  float4 acc;
+  attention_walk<SPLIT>(q4, kv + h * HD + c, row_stride, pos_stride, anc_r, src_base, n_keys, g, sp, D, gm, sum, acc);
   if constexpr (SPLIT > 1) {
     __shared__ float s_part[8 * (SPLIT - 1) * 36];   // [head][split - 1][max, sum, pad, pad, acc[32]]
     if (sp > 0) {
@@ -153,187 +198,63 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const KV* __restri
     }
     __syncthreads();
     if (sp > 0) return;
-    float M = gm;
-#pragma unroll
-    for (int q = 0; q < SPLIT - 1; ++q) M = fmaxf(M, s_part[(hl * (SPLIT - 1) + q) * 36]);
-    const float w0 = (gm == -INFINITY) ? 0.f : expf(gm - M);
-    sum *= w0; acc.x *= w0; acc.y *= w0; acc.z *= w0; acc.w *= w0;
-#pragma unroll
-    for (int q = 0; q < SPLIT - 1; ++q) {
-      const float* pp = s_part + (hl * (SPLIT - 1) + q) * 36;
-      const float wq = (pp[0] == -INFINITY) ? 0.f : expf(pp[0] - M);
-      const float4 a = *reinterpret_cast<const float4*>(pp + 4 + c);
-      sum = fmaf(wq, pp[1], sum);
-      acc.x = fmaf(wq, a.x, acc.x); acc.y = fmaf(wq, a.y, acc.y); acc.z = fmaf(wq, a.z, acc.z); acc.w = fmaf(wq, a.w, acc.w);
-    }
+    attention_merge_splits<SPLIT>(s_part + hl * (SPLIT - 1) * 36, c, gm, sum, acc);
   }
-  if (g == 0) {
-    const float inv = 1.0f / sum;
-    const float4 o4 = make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv);
-    const size_t off = (size_t)r * D + h * HD + c;
-    *reinterpret_cast<float4*>(out + off) = o4;
-    if (out_hi) {
-      const float f[4] = {o4.x, o4.y, o4.z, o4.w};
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        __nv_bfloat16 hi, lo;
-        split_bf16(f[u], hi, lo);
-        out_hi[off + u] = hi;
-        if (out_lo) out_lo[off + u] = lo;
-      }
-    }
-  }
+  if (g == 0) attention_store(acc, sum, (size_t)r * D + h * HD + c, out, out_hi, out_lo);
 }
 
 // ---------------------------------------------------------------------------------------------
-// Beam-grouped single-query attention: the NB hypotheses of one image are processed TOGETHER, so a key/value record
-// that several of them share is fetched once.  Cross-attention: all NB beams read the same encoder memory (1 fetch
-// instead of NB).  Self-attention: position j of beam b lives in physical slot anc[b][j]; beams with a common prefix
-// name the same slot, the first of them ("leader") fetches it and every beam naming that slot is updated from the
-// registers.  The per-row kernel above gets the same sharing only through L2 (NB fetches per record).
-//   grid = images x 4 (two heads per block), block = 2 heads x 4 key splits; a quarter warp owns one key per iteration
-//   (keys j = g + 4*split mod 16), one online-softmax state per beam; splits are merged through shared memory.
+// Image-block mapping of the same single-query attention for beam search.  The G hypotheses of an image read the same
+// encoder memory (cross-attention) and mostly the same ancestor slots (self-attention: anc[b][j] is the physical row that
+// holds position j of hypothesis b, and hypotheses with a common prefix name the same row).  With one block per ROW the
+// hypotheses of an image land on different SMs and every one of them pulls the shared records through L2 (ncu at 1 280
+// rows: 265 MB of L2 -> SM traffic for 57 MB of DRAM reads, L1 hit rate 7 %).  Here one block owns all G hypotheses of an
+// image for `nh` of its heads — warp = (hypothesis, head, key split) — so the G loads of a shared record are issued by
+// sibling warps of one SM within a few hundred cycles and all but the first hit in L1 (or merge with the miss in flight).
+// Arithmetic per (row, head) is exactly that of decode_attention_kernel with the same SPLIT.
+//   grid = images x (8 / nh); block = G x nh x SPLIT warps; dynamic smem = G*nh*(SPLIT-1)*36 floats
 // ---------------------------------------------------------------------------------------------
-constexpr int BEAM_ATT_ANC_LD = 160;
-
-template <int HD, int NB, typename KV>
-__global__ void __launch_bounds__(256)
-decode_attention_beam_kernel(const float* __restrict__ q, int ldq, const KV* __restrict__ kv, long long row_stride,
-                             int pos_stride, const int* __restrict__ anc, long long anc_parity_stride, int anc_ld,
-                             int src_mul /* NB: self (slot = img*NB + anc), 1: cross (slot = img) */,
-                             const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
-                             __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+template <int HD, int SPLIT, typename KV>
+__global__ void __launch_bounds__(1024)
+decode_attention_image_kernel(const float* __restrict__ q, int ldq, const KV* __restrict__ kv, long long row_stride,
+                              int pos_stride, const int* __restrict__ anc, long long anc_parity_stride, int anc_ld,
+                              int G, int nh, const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
+                              __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
   static_assert(HD == 32, "8 lanes x float4 per head slice");
-  constexpr int SPLIT = 4, HPB = 2;
+  extern __shared__ float s_part_img[];   // [G * nh][SPLIT - 1][max, sum, pad, pad, acc[32]]
   pdl_wait();
   pdl_trigger();
-  __shared__ int s_anc[NB * BEAM_ATT_ANC_LD];
-  __shared__ float s_part[HPB * (SPLIT - 1) * NB * 36];
-  const int img = blockIdx.x >> 2;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hl = wid & (HPB - 1), sp = wid >> 1;
-  const int h = (blockIdx.x & 3) * HPB + hl;
+  const int hb = 8 / nh;                       // blocks per image
+  const int img = blockIdx.x / hb;
+  // warp order: key split slowest, then head, hypothesis fastest — the sibling hypotheses of one head sit in adjacent warps
+  const int sp = wid / (G * nh);
+  const int pair = wid - sp * (G * nh);        // (hypothesis, head) of this block
+  const int hl = pair / G, beam = pair - hl * G;
+  const int h = (blockIdx.x - img * hb) * nh + hl;
+  const int r = img * G + beam;
   const int g = lane >> 3, c = (lane & 7) * 4;
   const int t = step ? *step : 0;
   const int n_keys = n_fixed > 0 ? n_fixed : t + 1;
-  const int r0 = img * NB;
-  if (anc) {
-    const int* a0 = anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)r0 * anc_ld;
-    for (int i = threadIdx.x; i < NB * n_keys; i += blockDim.x) {
-      const int b = i / n_keys, j = i - b * n_keys;
-      s_anc[b * BEAM_ATT_ANC_LD + j] = a0[(size_t)b * anc_ld + j];
+  const int* anc_r = anc ? anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)r * anc_ld : nullptr;
+  const int src_base = img * (anc ? G : 1);
+  const float scale = rsqrtf((float)HD);
+  float4 q4 = *reinterpret_cast<const float4*>(q + (size_t)r * ldq + h * HD + c);
+  q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
+  float gm, sum;
+  float4 acc;
+  attention_walk<SPLIT>(q4, kv + h * HD + c, row_stride, pos_stride, anc_r, src_base, n_keys, g, sp, D, gm, sum, acc);
+  if constexpr (SPLIT > 1) {
+    if (sp > 0) {
+      float* pp = s_part_img + (pair * (SPLIT - 1) + sp - 1) * 36;
+      if (g == 0) *reinterpret_cast<float4*>(pp + 4 + c) = acc;
+      if (lane == 0) { pp[0] = gm; pp[1] = sum; }
     }
     __syncthreads();
+    if (sp > 0) return;
+    attention_merge_splits<SPLIT>(s_part_img + pair * (SPLIT - 1) * 36, c, gm, sum, acc);
   }
-  const float scale = rsqrtf((float)HD);
-  float4 q4[NB];
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    q4[b] = *reinterpret_cast<const float4*>(q + (size_t)(r0 + b) * ldq + h * HD + c);
-    q4[b].x *= scale; q4[b].y *= scale; q4[b].z *= scale; q4[b].w *= scale;
-  }
-  const KV* kbase = kv + (size_t)img * src_mul * row_stride + h * HD + c;
-  float mx[NB], sum[NB];
-  float4 acc[NB];
-#pragma unroll
-  for (int b = 0; b < NB; ++b) { mx[b] = -INFINITY; sum[b] = 0.f; acc[b] = make_float4(0.f, 0.f, 0.f, 0.f); }
-  const unsigned gmask = 0xFFu << (g * 8);
-  for (int j = g + 4 * sp; j < n_keys; j += 4 * SPLIT) {
-    int slot[NB];
-    bool lead[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      slot[b] = anc ? s_anc[b * BEAM_ATT_ANC_LD + j] : 0;
-      lead[b] = true;
-#pragma unroll
-      for (int e = 0; e < b; ++e) lead[b] = lead[b] && (slot[e] != slot[b]);
-    }
-    float4 kk[NB], vv[NB];
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      if (lead[b]) {
-        const KV* ptr = kbase + (size_t)slot[b] * row_stride + (size_t)j * pos_stride;
-        kk[b] = kv_load4(ptr);
-        vv[b] = kv_load4(ptr + D);
-      }
-    }
-#pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      if (!lead[b]) continue;
-#pragma unroll
-      for (int v = b; v < NB; ++v) {
-        if (slot[v] != slot[b]) continue;
-        float d = fmaf(q4[v].x, kk[b].x, fmaf(q4[v].y, kk[b].y, fmaf(q4[v].z, kk[b].z, q4[v].w * kk[b].w)));
-        d += __shfl_xor_sync(gmask, d, 1);
-        d += __shfl_xor_sync(gmask, d, 2);
-        d += __shfl_xor_sync(gmask, d, 4);
-        const float nm = fmaxf(mx[v], d);
-        const float corr = expf(mx[v] - nm), e0 = expf(d - nm);   // corr = 0 on the first key of this state
-        sum[v] = sum[v] * corr + e0;
-        acc[v].x = fmaf(e0, vv[b].x, acc[v].x * corr); acc[v].y = fmaf(e0, vv[b].y, acc[v].y * corr);
-        acc[v].z = fmaf(e0, vv[b].z, acc[v].z * corr); acc[v].w = fmaf(e0, vv[b].w, acc[v].w * corr);
-        mx[v] = nm;
-      }
-    }
-  }
-  __syncwarp();
-  // merge the four quarter-warp states of every beam, then the key splits through shared memory
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    float gm = fmaxf(mx[b], __shfl_xor_sync(0xffffffffu, mx[b], 8));
-    gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 16));
-    const float sc = (mx[b] == -INFINITY) ? 0.f : expf(mx[b] - gm);
-    sum[b] *= sc; acc[b].x *= sc; acc[b].y *= sc; acc[b].z *= sc; acc[b].w *= sc;
-#pragma unroll
-    for (int o = 8; o < 32; o <<= 1) {
-      sum[b] += __shfl_xor_sync(0xffffffffu, sum[b], o);
-      acc[b].x += __shfl_xor_sync(0xffffffffu, acc[b].x, o);
-      acc[b].y += __shfl_xor_sync(0xffffffffu, acc[b].y, o);
-      acc[b].z += __shfl_xor_sync(0xffffffffu, acc[b].z, o);
-      acc[b].w += __shfl_xor_sync(0xffffffffu, acc[b].w, o);
-    }
-    mx[b] = gm;
-    if (sp > 0) {
-      float* pp = s_part + (((hl * (SPLIT - 1) + sp - 1) * NB) + b) * 36;
-      if (g == 0) *reinterpret_cast<float4*>(pp + 4 + c) = acc[b];
-      if (lane == 0) { pp[0] = gm; pp[1] = sum[b]; }
-    }
-  }
-  __syncthreads();
-  if (sp > 0) return;
-#pragma unroll
-  for (int b = 0; b < NB; ++b) {
-    float M = mx[b];
-#pragma unroll
-    for (int qd = 0; qd < SPLIT - 1; ++qd) M = fmaxf(M, s_part[(((hl * (SPLIT - 1) + qd) * NB) + b) * 36]);
-    const float w0 = (mx[b] == -INFINITY) ? 0.f : expf(mx[b] - M);
-    float sm = sum[b] * w0;
-    float4 a = make_float4(acc[b].x * w0, acc[b].y * w0, acc[b].z * w0, acc[b].w * w0);
-#pragma unroll
-    for (int qd = 0; qd < SPLIT - 1; ++qd) {
-      const float* pp = s_part + (((hl * (SPLIT - 1) + qd) * NB) + b) * 36;
-      const float wq = (pp[0] == -INFINITY) ? 0.f : expf(pp[0] - M);
-      const float4 pa = *reinterpret_cast<const float4*>(pp + 4 + c);
-      sm = fmaf(wq, pp[1], sm);
-      a.x = fmaf(wq, pa.x, a.x); a.y = fmaf(wq, pa.y, a.y); a.z = fmaf(wq, pa.z, a.z); a.w = fmaf(wq, pa.w, a.w);
-    }
-    if (g == 0) {
-      const float inv = 1.0f / sm;
-      const float4 o4 = make_float4(a.x * inv, a.y * inv, a.z * inv, a.w * inv);
-      const size_t off = (size_t)(r0 + b) * D + h * HD + c;
-      *reinterpret_cast<float4*>(out + off) = o4;
-      if (out_hi) {
-        const float f[4] = {o4.x, o4.y, o4.z, o4.w};
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          __nv_bfloat16 hi, lo;
-          split_bf16(f[u], hi, lo);
-          out_hi[off + u] = hi;
-          if (out_lo) out_lo[off + u] = lo;
-        }
-      }
-    }
-  }
+  if (g == 0) attention_store(acc, sum, (size_t)r * D + h * HD + c, out, out_hi, out_lo);
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
@@ -381,25 +302,36 @@ __global__ void greedy_pick_kernel(const float* __restrict__ logits, int V, cons
   if (threadIdx.x == 0) { float s = 0.f; for (int i = 0; i < nw; ++i) s += red_v[i]; s_sum = s; }
   __syncthreads();
   sum = s_sum;
+  // fed-back token: argmax of the softmax PROBABILITIES, lowest index on ties (tfm.py:134-135, quirk Q7);
+  // returned id: argmax of the raw LOGITS (tfm.py:142, preds_index = out.max(2)) — the two differ only where two distinct
+  // logits round to the same fp32 probability.
   float bv = -INFINITY; int bi = 0x7fffffff;
+  float lv = -INFINITY; int li = 0x7fffffff;
   for (int i = threadIdx.x; i < V; i += blockDim.x) {
-    const float pr = expf(x[i] - mx) / sum;
+    const float xi = x[i];
+    const float pr = expf(xi - mx) / sum;
     if (pr > bv || (pr == bv && i < bi)) { bv = pr; bi = i; }
-    if (logits_out) logits_out[((size_t)r * ids_ld + t) * V + i] = x[i];
+    if (xi > lv || (xi == lv && i < li)) { lv = xi; li = i; }
+    if (logits_out) logits_out[((size_t)r * ids_ld + t) * V + i] = xi;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
     if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    const float pv = __shfl_xor_sync(0xffffffffu, lv, o);
+    const int pi = __shfl_xor_sync(0xffffffffu, li, o);
+    if (pv > lv || (pv == lv && pi < li)) { lv = pv; li = pi; }
   }
   __syncthreads();
-  if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; }
+  if (lane == 0) { red_v[wid] = bv; red_i[wid] = bi; red_v[16 + wid] = lv; red_i[16 + wid] = li; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int i = 1; i < nw; ++i)
+    for (int i = 1; i < nw; ++i) {
       if (red_v[i] > bv || (red_v[i] == bv && red_i[i] < bi)) { bv = red_v[i]; bi = red_i[i]; }
-    ids[(size_t)r * ids_ld + t] = bi;
+      if (red_v[16 + i] > lv || (red_v[16 + i] == lv && red_i[16 + i] < li)) { lv = red_v[16 + i]; li = red_i[16 + i]; }
+    }
+    ids[(size_t)r * ids_ld + t] = li;
     tokens[(size_t)r * tok_ld + t + 1] = bi;
     if (bi == end_id && !ended[r]) {
       ended[r] = 1;

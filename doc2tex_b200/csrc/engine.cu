@@ -24,9 +24,7 @@
 #include "gemm_simt.cuh"
 #include "lstm_kernels.cuh"
 #include "gemm_tc.cuh"
-#include "gemm_tc2.cuh"
 #include "gemm_tc3.cuh"
-#include "gemm_tc4.cuh"
 #include "decode_cluster.cuh"
 
 using namespace d2t;
@@ -105,10 +103,8 @@ struct d2t_engine {
 
   SlotPool enc_pool, dec_pool;
   bool keep_taps = false;
-  bool use_pdl = true;   // D2T_PDL=0 disables programmatic dependent launch in the decode step
-  bool use_tc3 = true;   // D2T_TC3=0 / option "tc3": stem convolutions fed from bf16 activation planes by cp.async
-  bool use_tc4 = false;  // D2T_TC4=1 / option "tc4": CTA-pair + cp.async planes kernel for the 256-wide stem convolutions
-  bool use_tc2 = false;  // D2T_TC2=1 / option "tc2": CTA-pair (cta_group::2) kernel for the large stem convolutions
+  bool use_pdl = true;   // option "pdl": programmatic dependent launch in the decode step
+  bool use_tc3 = true;   // option "tc3": stem convolutions fed from bf16 activation planes by cp.async
   // ViTEncoder (fix_embed: False, interpolate_embed: True): pos_embed is resampled bicubically to the grid of each image
   // size (vit_encoder.py:58-95) — options "pos_interpolate", "pos_grid_h", "pos_grid_w"; tables cached per grid
   bool pos_interpolate = false;
@@ -117,12 +113,22 @@ struct d2t_engine {
   bool time_conv = false;   // option "time_conv": bracket layer3.1.conv1 with events (d2t_debug_conv_time)
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> conv_events;
   double conv_flops = 0.0;
-  bool fuse_pick = true;    // D2T_FUSE_PICK=0: separate embed / advance launches in the greedy decode step
-  bool lean_acts = true;    // D2T_LEAN_ACTS=0: every stem layer writes fp32 AND operand planes, read or not
-  bool attn_group = false;  // D2T_ATTN_GROUP=1 / option "attn_group": beam-grouped decode attention (measured slower, off)
-  int split_k = 1;       // D2T_SPLIT_K / option "split_k": 0 = never, 1 = auto split-K of the LayerNorm-fed decode projections
-  bool fuse_ln = false;  // D2T_FUSE_LN=1: cluster-fused residual+LayerNorm epilogue (measured slower than the stand-alone
-                         // LayerNorm kernel on B200: cluster launch + DSMEM exchange cost more than the saved launch)
+  // option "time_decode": the decode loop runs eagerly and brackets the memory-bound launches of decoder layer 1 with events
+  struct DecEvent { int kind; double bytes; cudaEvent_t a, b; };   // kind: 0 self-attn, 1 cross-attn, 2 beam step, 3 greedy pick
+  std::vector<DecEvent> dec_events;
+  int cur_step = 0;   // host copy of the step being enqueued (eager mode only; the device reads its own counter)
+  bool fuse_pick = true;    // option "fuse_pick": 0 = separate embed / advance launches in the greedy decode step
+  bool lean_acts = true;    // option "lean_acts": 0 = every stem layer writes fp32 AND operand planes, read or not
+  int split_k = 1;       // option "split_k": 0 = never, 1 = auto split-K of the LayerNorm-fed decode projections
+  bool attn_image_block = true;   // option "attn_image_block": beam search — one block owns all hypotheses of an image, so the
+                                  // records they share (encoder memory, common prefixes) are served by that SM's L1
+  int attn_split = 0;       // option "attn_split": warps per (row, head) of the per-row decode attention (0 = auto)
+  bool stack_mma = true;    // option "stack_mma": bf16x3 decode projections issue 2 MMAs per k-step against [W_hi ; W_lo]
+  int steps_per_graph = 8;  // option "steps_per_graph": decode steps captured per CUDA graph (= the early-exit poll interval)
+  bool kv_bf16 = true;      // option "kv_bf16": bf16 KV caches in the single-pass bf16 mode (fp32-parity modes keep fp32)
+  bool fuse_pool = true;    // option "fuse_pool": 2x2 max-pools 1 and 2 fused into the producing convolution's epilogue
+  bool time_decode = false; // option "time_decode": bracket the decode-attention / beam-step launches with events
+  bool dbg_decode = false, dbg_timeline = false;   // options "dbg_decode" / "dbg_timeline": phase / per-launch timestamps
   std::map<std::string, Tap> taps;
 
   // decode graph cache
@@ -134,8 +140,8 @@ struct d2t_engine {
   // Off by default: measured 330 us per step against the chain's 292 us (B=256, step 99) — at N = 16/32 rows per cluster a
   // tcgen05.mma retires every ~90 ns whatever its N, so the 48 MMAs of a K=256 bf16x3 projection cost as much as the
   // chain's wide tiles, and the 40 cluster hand-offs per step add another ~60 us.
-  bool use_cluster_step = false;  // D2T_CLUSTER_STEP=1 / option "cluster_step"
-  int decode_groups = 0;      // D2T_DECODE_GROUPS / option "decode_groups": concurrent row groups of a decode call (0 = auto)
+  bool use_cluster_step = false;  // option "cluster_step"
+  int decode_groups = 0;      // option "decode_groups": concurrent row groups of a decode call (0 = auto)
   cudaStream_t side[D2T_MAX_GROUPS] = {};   // side[g], g >= 1: stream of row group g (group 0 runs on `work`)
   cudaEvent_t ev_fork = nullptr, ev_join[D2T_MAX_GROUPS] = {};
   cudaEvent_t ev_poll = nullptr;   // early-exit poll of the decode loop (checked one poll late, see tfm_decode)
@@ -149,6 +155,12 @@ struct d2t_engine {
     return code;
   }
 };
+
+// Captured decode-step graphs bake in the kernel selection: dropped whenever weights or a decode-affecting option change.
+static void drop_graphs(d2t_engine* e) {
+  for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+}
 
 int finalize_attn_extras(d2t_engine* e);
 int prepare_cluster_step(d2t_engine* e);
@@ -277,23 +289,11 @@ int run_contraction(d2t_engine* e, const ConvGemm& p, const TcWeight* tcw, int p
     if (e->use_tc3 && tc3_supported(p, precision)) {
       auto m3 = e->tc3.find(p.w);
       if (m3 != e->tc3.end() && m3->second.ready) {
-        if (e->use_tc4 && tc4_supported(p, precision, e->active_sms)) {
-          cudaError_t st4 = launch_conv_gemm_tc4(p, m3->second, precision, s, e->active_sms);
-          if (st4 != cudaSuccess) return e->fail(D2T_ERR_CUDA, "pair + cp.async contraction launch failed: %s", cudaGetErrorString(st4));
-          e->launches += 1;
-          return 0;
-        }
         cudaError_t st3 = launch_conv_gemm_tc3(p, m3->second, precision, s, e->active_sms);
         if (st3 != cudaSuccess) return e->fail(D2T_ERR_CUDA, "cp.async-fed contraction launch failed: %s", cudaGetErrorString(st3));
         e->launches += 1;
         return 0;
       }
-    }
-    if (e->use_tc2 && tc2_supported(p, *tcw, precision, e->active_sms)) {
-      cudaError_t st2 = launch_conv_gemm_tc2(p, *tcw, precision, s, e->active_sms);
-      if (st2 != cudaSuccess) return e->fail(D2T_ERR_CUDA, "cta_group::2 contraction launch failed: %s", cudaGetErrorString(st2));
-      e->launches += 1;
-      return 0;
     }
     cudaError_t st = launch_conv_gemm_tc(p, *tcw, precision, s, e->active_sms);
     if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tcgen05 contraction launch failed: %s", cudaGetErrorString(st));
@@ -354,7 +354,7 @@ enum OutNeed { NEED_F32 = 1, NEED_PLANES = 2, NEED_BOTH = 3 };
 bool routes_to_tc3(d2t_engine* e, const ConvGemm& p) {
   const int prec = e->cfg.precision;
   if (prec != D2T_PREC_BF16X3 && prec != D2T_PREC_BF16) return false;
-  if (!e->use_tc3 || e->use_tc4 || !tc3_supported(p, prec) || !tc_supported(p)) return false;
+  if (!e->use_tc3 || !tc3_supported(p, prec) || !tc_supported(p)) return false;
   auto w = e->tcw.find(p.w);
   auto m = e->tc3.find(p.w);
   return w != e->tcw.end() && w->second.ready && w->second.N == p.N && w->second.K == p.K && m != e->tc3.end() && m->second.ready;
@@ -511,19 +511,7 @@ int d2t_create(const d2t_config* cfg, int device, d2t_engine** out) {
   e->device = device;
   e->num_sms = prop.multiProcessorCount;
   e->enc_sms = e->active_sms = e->num_sms;
-  if (const char* v = getenv("D2T_PDL")) e->use_pdl = atoi(v) != 0;
-  if (const char* v = getenv("D2T_FUSE_LN")) e->fuse_ln = atoi(v) != 0;
-  if (const char* v = getenv("D2T_TC2")) e->use_tc2 = atoi(v) != 0;
-  if (const char* v = getenv("D2T_TC3")) e->use_tc3 = atoi(v) != 0;
-  if (const char* v = getenv("D2T_TC4")) e->use_tc4 = atoi(v) != 0;
-  if (const char* v = getenv("D2T_TC3_MT2")) tc3_two_mtiles() = atoi(v) != 0;
   cudaSetDevice(device);
-  if (const char* v = getenv("D2T_DECODE_GROUPS")) e->decode_groups = atoi(v);
-  if (const char* v = getenv("D2T_SPLIT_K")) e->split_k = atoi(v);
-  if (const char* v = getenv("D2T_ATTN_GROUP")) e->attn_group = atoi(v) != 0;
-  if (const char* v = getenv("D2T_LEAN_ACTS")) e->lean_acts = atoi(v) != 0;
-  if (const char* v = getenv("D2T_FUSE_PICK")) e->fuse_pick = atoi(v) != 0;
-  if (const char* v = getenv("D2T_CLUSTER_STEP")) e->use_cluster_step = atoi(v) != 0;
   if (cudaMallocHost(&e->h_counters, 4 * D2T_MAX_GROUPS * sizeof(int)) != cudaSuccess) {
     g_create_error = "cudaMallocHost failed";
     delete e;
@@ -560,6 +548,7 @@ int d2t_destroy(d2t_engine* e) {
   cudaDeviceSynchronize();
   for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
   for (auto& ev : e->conv_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
+  for (auto& ev : e->dec_events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (void* p : e->owned) cudaFree(p);
   e->enc_pool.destroy();
   e->dec_pool.destroy();
@@ -602,9 +591,10 @@ int d2t_finalize_weights(d2t_engine* e) {
   CUDA_TRY(e, cudaDeviceSynchronize());
   for (void* p : e->owned) cudaFree(p);
   e->owned.clear(); e->conv.clear(); e->dev.clear(); e->tcw.clear(); e->tc3.clear();
-  for (auto& g : e->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  e->pos_tables.clear();   // the cached bicubic tables live in `owned` and were resampled from the OLD pos_embed
+  drop_graphs(e);
   for (auto& ev : e->conv_events) { cudaEventDestroy(ev.first); cudaEventDestroy(ev.second); }
-  e->graphs.clear();
+  e->conv_events.clear();
   const d2t_config& c = e->cfg;
   const int C = c.stem_channels, D = c.hidden;
   const int c16 = C / 16, c8 = C / 8, c4 = C / 4, c2 = C / 2;
@@ -799,36 +789,60 @@ int d2t_encoder_geometry(const d2t_engine* e, int H, int W, int* gh, int* gw, in
 int d2t_set_option(d2t_engine* e, const char* key, int value) {
   if (!e || !key) return D2T_ERR_INVALID;
   const std::string k = key;
+  bool decode_affecting = true;
   if (k == "encoder_sms") {
     if (value < 8 || value > e->num_sms) return e->fail(D2T_ERR_INVALID, "encoder_sms must be in [8, %d]", e->num_sms);
     e->enc_sms = value;
+    decode_affecting = false;
   } else if (k == "decode_groups") {
     if (value < 0 || value > D2T_MAX_GROUPS) return e->fail(D2T_ERR_INVALID, "decode_groups must be in [0, %d]", D2T_MAX_GROUPS);
     e->decode_groups = value;
   } else if (k == "pos_interpolate") {
-    e->pos_interpolate = value != 0;
+    e->pos_interpolate = value != 0; decode_affecting = false;
   } else if (k == "pos_grid_h") {
-    e->pos_grid_h = value;
+    e->pos_grid_h = value; decode_affecting = false;
   } else if (k == "pos_grid_w") {
-    e->pos_grid_w = value;
+    e->pos_grid_w = value; decode_affecting = false;
   } else if (k == "time_conv") {
-    e->time_conv = value != 0;
-  } else if (k == "attn_group") {
-    e->attn_group = value != 0;
+    e->time_conv = value != 0; decode_affecting = false;
+  } else if (k == "time_decode") {
+    e->time_decode = value != 0;
+  } else if (k == "attn_image_block") {
+    e->attn_image_block = value != 0;
+  } else if (k == "attn_split") {
+    e->attn_split = value;
+  } else if (k == "stack_mma") {
+    e->stack_mma = value != 0;
+  } else if (k == "steps_per_graph") {
+    if (value < 1 || value > 16) return e->fail(D2T_ERR_INVALID, "steps_per_graph must be in [1, 16]");
+    e->steps_per_graph = value;
   } else if (k == "split_k") {
     e->split_k = value;
   } else if (k == "cluster_step") {
     e->use_cluster_step = value != 0;
   } else if (k == "pdl") {
     e->use_pdl = value != 0;
-  } else if (k == "tc2") {
-    e->use_tc2 = value != 0;
+  } else if (k == "fuse_pick") {
+    e->fuse_pick = value != 0;
+  } else if (k == "kv_bf16") {
+    e->kv_bf16 = value != 0;
+  } else if (k == "lean_acts") {
+    e->lean_acts = value != 0; decode_affecting = false;
+  } else if (k == "fuse_pool") {
+    e->fuse_pool = value != 0; decode_affecting = false;
   } else if (k == "tc3") {
-    e->use_tc3 = value != 0;
-  } else if (k == "tc4") {
-    e->use_tc4 = value != 0;
+    e->use_tc3 = value != 0; decode_affecting = false;
+  } else if (k == "dbg_decode") {
+    e->dbg_decode = value != 0;
+  } else if (k == "dbg_timeline") {
+    e->dbg_timeline = value != 0;
   } else {
     return e->fail(D2T_ERR_INVALID, "unknown option '%s'", key);
+  }
+  if (decode_affecting) {   // a captured step graph replays the OLD kernel selection
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    drop_graphs(e);
   }
   return D2T_OK;
 }
@@ -848,6 +862,25 @@ int d2t_debug_conv_time(d2t_engine* e, double* total_ms, int64_t* launches, doub
   *launches = (int64_t)e->conv_events.size();
   *flops_per_launch = e->conv_flops;
   e->conv_events.clear();
+  return D2T_OK;
+}
+
+int d2t_debug_decode_time(d2t_engine* e, int kind, double* total_ms, int64_t* launches, double* total_bytes) {
+  if (!e || !total_ms || !launches || !total_bytes) return D2T_ERR_INVALID;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaDeviceSynchronize());
+  double ms_sum = 0.0, bytes = 0.0;
+  int64_t n = 0;
+  std::vector<d2t_engine::DecEvent> keep;
+  for (auto& ev : e->dec_events) {
+    if (ev.kind != kind) { keep.push_back(ev); continue; }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.a, ev.b) == cudaSuccess) { ms_sum += ms; bytes += ev.bytes; ++n; }
+    cudaEventDestroy(ev.a);
+    cudaEventDestroy(ev.b);
+  }
+  e->dec_events.swap(keep);
+  *total_ms = ms_sum; *launches = n; *total_bytes = bytes;
   return D2T_OK;
 }
 

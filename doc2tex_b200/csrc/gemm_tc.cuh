@@ -176,9 +176,7 @@ struct TcCfg {
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;   // two accumulators; power of two (BN in {64,128,256})
-  static constexpr int LN_PART_BYTES = 8 * TC_BM * 2 * 4;   // [4 CTAs x 2 epilogue slots][128 rows][sum, sumsq]
-  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ +
-                                       (A_TMA ? LN_PART_BYTES : 0);
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static_assert(STAGES >= 2, "need at least a double buffer");
   static_assert(!A_TMA || STAGES * STAGE_BYTES >= EPI_TILE_BYTES, "epilogue tiles must fit in the aliased stage memory");
 };
@@ -194,9 +192,12 @@ struct TcWeight {
 // A_TMA: the A operand planes already exist in HBM as bf16 [M, K] matrices (written by the producing kernel's
 // epilogue) and are fetched by TMA like the weights; the gather/convert warps then have nothing to do.  This is the
 // low-latency path for the small decode-step GEMMs: every k-block of a tile is in flight at once.
-// LN_FUSE (TMA-fed-A, BN = 64, N = 256 only): the four n-tile CTAs of one m-tile form a thread-block cluster, exchange
-// per-row partial sums through distributed shared memory and apply the post-norm LayerNorm in the epilogue.
-template <bool TF32, int PASSES, int BN, bool A_TMA, bool LN_FUSE = false>
+// STACK (TMA-fed-A, bf16x3): a tcgen05.mma retires every ~90 ns whatever its N (<= 256), so the three passes of a k-step
+// are issued as TWO instructions: A_hi x [W_hi ; W_lo] (the two weight planes are adjacent in the stage = one 2*BN-row B
+// operand, accumulator columns [0, 2*BN)) and A_lo x W_hi (columns [0, BN)); the epilogue adds the two column halves.
+// The one-tile-per-CTA variant never uses its second accumulator, so TMEM holds the wide one for free.  A third fewer
+// serial MMAs on the critical path of every decode-step projection.
+template <bool TF32, int PASSES, int BN, bool A_TMA, bool STACK = false>
 __global__ void __launch_bounds__(tc_threads(A_TMA), 1)
 conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi,
                     const __grid_constant__ CUtensorMap map_lo, const __grid_constant__ CUtensorMap map_a_hi,
@@ -218,8 +219,6 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
   volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + TC_EPI_STAGE_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t ln_part = bars + 256;                                              // LN_FUSE: [8][128][2] floats
-  float* const ln_part_gen = reinterpret_cast<float*>(smem_gen + STAGES * Cfg::STAGE_BYTES + TC_EPI_STAGE_BYTES + 256);
   const bool dbg = p.dbg != nullptr && blockIdx.x == 0;
   if (dbg && threadIdx.x == 0) p.dbg[0] = tc::gtime();
   const int KS = (A_TMA && p.k_splits > 1) ? p.k_splits : 1;   // split-K slices (TMA-fed-A variant only)
@@ -335,7 +334,15 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
       for (int j = slot; j < BN / 32; j += NSLOT) {
         uint32_t r[32];
         tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + j * 32), r);
-        tc::tmem_ld_wait();
+        if constexpr (STACK) {   // columns [BN, 2*BN) hold A_hi x W_lo of the same outputs
+          uint32_t r2[32];
+          tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(BN + j * 32), r2);
+          tc::tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 32; ++q) r[q] = __float_as_uint(__uint_as_float(r[q]) + __uint_as_float(r2[q]));
+        } else {
+          tc::tmem_ld_wait();
+        }
 #pragma unroll
         for (int q = 0; q < 8; ++q)
           *reinterpret_cast<uint4*>(stg + lane * TC_EPI_PITCH + q * 4) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
@@ -364,45 +371,6 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
           } else if (act == ACT_GELU) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[i] = tc::gelu_erf4(v[i]);   // out-of-line: keeps the unrolled epilogue small
-          }
-          if constexpr (LN_FUSE) {
-            // row statistics over this warp's 32 columns -> all four CTAs of the cluster (distributed shared memory)
-            const uint32_t my_rank = tc::cluster_ctarank();
-            const float4 lw = __ldg(reinterpret_cast<const float4*>(p.ln_w + n));
-            const float4 lb = __ldg(reinterpret_cast<const float4*>(p.ln_b + n));
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float s1 = (v[i].x + v[i].y) + (v[i].z + v[i].w);
-              float s2 = (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
-#pragma unroll
-              for (int o = 1; o < 8; o <<= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-              }
-              if ((lane & 7) == 0) {
-                const int row = quad * 32 + sub_r + 4 * i;
-                const uint32_t a = ln_part + (uint32_t)(((my_rank * 2 + slot) * TC_BM + row) * 8);
-#pragma unroll
-                for (uint32_t rk = 0; rk < 4; ++rk) tc::st_cluster_f32x2(a, rk, s1, s2);
-              }
-            }
-            tc::cluster_sync_all();   // every thread of the four CTAs (the TMA / MMA warps arrive after their loops)
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row = quad * 32 + sub_r + 4 * i;
-              const float2 pr = *reinterpret_cast<const float2*>(ln_part_gen + ((lane & 7) * TC_BM + row) * 2);
-              float s1 = pr.x, s2 = pr.y;
-#pragma unroll
-              for (int o = 1; o < 8; o <<= 1) {
-                s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-              }
-              const float mean = s1 * (1.0f / 256.0f);
-              const float var = fmaxf(s2 * (1.0f / 256.0f) - mean * mean, 0.f);
-              const float rstd = 1.0f / sqrtf(var + p.ln_eps);
-              v[i].x = (v[i].x - mean) * rstd * lw.x + lb.x; v[i].y = (v[i].y - mean) * rstd * lw.y + lb.y;
-              v[i].z = (v[i].z - mean) * rstd * lw.z + lb.z; v[i].w = (v[i].w - mean) * rstd * lw.w + lb.w;
-            }
           }
           if (second && p.out2_bf16) {   // bf16 KV cache: same element offsets, 2-byte elements
             __nv_bfloat16* dst16 = reinterpret_cast<__nv_bfloat16*>(p.out2) + (dst - p.out2);
@@ -579,7 +547,6 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
       }
     }
     __syncwarp();
-    if constexpr (LN_FUSE) tc::cluster_sync_all();
   } else {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
@@ -600,10 +567,19 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
           const uint32_t b_hi = a_hi + PLANES * Cfg::A_BYTES;
           const uint64_t da_hi = tc::make_smem_desc(a_hi), db_hi = tc::make_smem_desc(b_hi);
           const uint64_t da_lo = tc::make_smem_desc(a_hi + Cfg::A_BYTES), db_lo = tc::make_smem_desc(b_hi + Cfg::B_BYTES);
+          if constexpr (STACK) {
+            constexpr uint32_t idesc2 = tc::make_idesc(1, 2 * BN);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              tc::umma<false>(d, da_hi + 2 * k, db_hi + 2 * k, idesc2, (kb | k) != 0);   // [hi.hi | hi.lo]
+              tc::umma<false>(d, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);               // += lo.hi
+            }
+          } else {
 #pragma unroll
           for (int k = 0; k < 4; ++k)  // 4 x (UMMA_K * elem) = 4 x 32 B = one 128-byte row
             tc::umma<TF32>(d, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb | k) != 0);
-          if constexpr (PASSES == 3) {
+          }
+          if constexpr (PASSES == 3 && !STACK) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) tc::umma<TF32>(d, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
 #pragma unroll
@@ -616,7 +592,6 @@ conv_gemm_tc_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi
       }
     }
     __syncwarp();
-    if constexpr (LN_FUSE) tc::cluster_sync_all();
   }
   tc::tcgen05_before_sync();
   __syncthreads();
@@ -730,11 +705,12 @@ inline cudaError_t tc_make_act_map(const void* plane, int M, int K, CUtensorMap*
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <bool TF32, int PASSES, int BN, bool A_TMA, bool LN_FUSE = false>
+template <bool TF32, int PASSES, int BN, bool A_TMA, bool STACK = false>
 inline cudaError_t tc_launch_one(const ConvGemm& p, const TcWeight& w, cudaStream_t s, int num_sms) {
   using Cfg = TcCfg<TF32, PASSES, BN, A_TMA>;
+  static_assert(!STACK || (A_TMA && PASSES == 3 && !TF32 && BN <= 128), "stacked operand: bf16x3, one tile per CTA, N <= 256");
   static bool attr_set = false;
-  auto kern = conv_gemm_tc_kernel<TF32, PASSES, BN, A_TMA, LN_FUSE>;
+  auto kern = conv_gemm_tc_kernel<TF32, PASSES, BN, A_TMA, STACK>;
   if (!attr_set) {
     cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
     if (st != cudaSuccess) return st;
@@ -746,15 +722,8 @@ inline cudaError_t tc_launch_one(const ConvGemm& p, const TcWeight& w, cudaStrea
   constexpr int mi = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
   const CUtensorMap* ah = A_TMA ? reinterpret_cast<const CUtensorMap*>(p.a_map_hi) : &w.map_hi[mi];
   const CUtensorMap* al = (A_TMA && p.a_map_lo) ? reinterpret_cast<const CUtensorMap*>(p.a_map_lo) : ah;
-  if (LN_FUSE) launch_cluster_x() = 4;   // the four 64-column tiles of a 256-wide row block form one cluster
   return launch_kernel(kern, dim3(grid), dim3(tc_threads(A_TMA)), Cfg::SMEM_BYTES, s, p, w.map_hi[mi], w.map_lo[mi], *ah, *al,
                        tiles_m, tiles_n);
-}
-
-// Fused residual + LayerNorm epilogue: 256-wide rows, TMA-fed A planes, one 4-CTA cluster per 128-row block.
-inline bool tc_can_fuse_ln(const ConvGemm& p, int num_sms) {
-  return p.N == 256 && p.a_map_hi != nullptr && p.out2 == nullptr && p.act == ACT_NONE && p.KH == 1 && p.KW == 1 &&
-         ((p.M + TC_BM - 1) / TC_BM) * 4 <= num_sms;
 }
 
 template <bool TF32, int PASSES>
@@ -763,11 +732,13 @@ inline cudaError_t tc_launch_bn(const ConvGemm& p, const TcWeight& w, cudaStream
     // pre-split A planes + plain [M,K] operand -> TMA-fed A (decode-step GEMMs), one tile per CTA
     if (p.a_map_hi != nullptr && p.KH == 1 && p.KW == 1 && p.H == 1 && p.W == 1 && (PASSES == 1 || p.a_map_lo != nullptr)) {
       const int tiles_m = (p.M + TC_BM - 1) / TC_BM;
-      if (p.ln_w != nullptr) {
-        if (!tc_can_fuse_ln(p, num_sms)) return cudaErrorInvalidValue;
-        return tc_launch_one<false, PASSES, 64, true, true>(p, w, s, num_sms);
-      }
       const int ks = p.k_splits > 1 ? p.k_splits : 1;
+      if constexpr (PASSES == 3) {
+        if (p.stack) {
+          if (tiles_m * ((p.N + 63) / 64) * ks <= num_sms) return tc_launch_one<false, 3, 64, true, true>(p, w, s, num_sms);
+          if (ks == 1 && tiles_m * ((p.N + 127) / 128) <= num_sms) return tc_launch_one<false, 3, 128, true, true>(p, w, s, num_sms);
+        }
+      }
       if (tiles_m * ((p.N + 63) / 64) * ks <= num_sms) return tc_launch_one<false, PASSES, 64, true>(p, w, s, num_sms);
       if (ks == 1 && tiles_m * ((p.N + 127) / 128) <= num_sms) return tc_launch_one<false, PASSES, 128, true>(p, w, s, num_sms);
     }

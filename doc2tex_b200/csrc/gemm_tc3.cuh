@@ -9,7 +9,6 @@
 // stages.  Stages are half as deep (64-byte rows, 64B swizzle, 32 bf16 per k-block) so that twice as many fit:
 // 4 x 48 KB for the 3-pass 256-wide tile.
 #pragma once
-#include <cstdlib>
 #include "gemm_tc.cuh"
 
 namespace d2t {
@@ -296,214 +295,6 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Swapped variant for the narrow layers (Cout <= 128: conv0_2, layer1, conv1).  A tcgen05.mma costs about the same
-// 60-90 ns whether its N is 64, 128 or 256 (measured), so a [128 pixels] x [Cout = 64 / 128] tile wastes the
-// instruction.  Here the roles are exchanged: D^T[channel, pixel] = W[channel, k] . X[pixel, k]^T with the weight tile as
-// the 128-row A operand (M = 128 channels; rows beyond Cout are don't-care lanes) and a 256-PIXEL tile as the B operand
-// (N = 256): half (Cout 128) or a quarter (Cout 64) of the instructions for the same FLOPs.  The accumulator (lane =
-// channel, column = pixel) needs no transpose on the way out: for one pixel the 32 lanes of a warp hold 32 consecutive
-// channels = one coalesced 128-byte NHWC segment.  Two 256-column accumulators: the epilogue overlaps the next tile.
-// ------------------------------------------------------------------------------------------------------------------
-template <int PASSES>
-__global__ void __launch_bounds__(448, 1)
-conv_gemm_tc3s_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi,
-                      const __grid_constant__ CUtensorMap map_lo, int tiles_m, int w_rows) {
-  using Cfg = Tc3Cfg<PASSES, 128, 2>;                       // 256 pixel rows + 128 weight rows per stage
-  constexpr int ROWS = 256;
-  constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES;
-  constexpr int EPI_WARPS = 4, TMA_WARP = 12, MMA_WARP = 13;
-  constexpr int TMEM_COLS = 512;
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (tc::smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* smem_gen = smem_raw + (smem_base - tc::smem_u32(smem_raw));
-  const uint32_t bars = smem_base + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGE_BYTES;
-  auto full_bar = [&](int s) { return bars + 8u * s; };
-  auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-  auto tfull_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
-  auto tempty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
-  const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);
-  volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + STAGES * Cfg::STAGE_BYTES + Cfg::EPI_STAGE_BYTES + 8 * (2 * STAGES + 4));
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_tiles = tiles_m;
-  const int nkb = (p.K + Cfg::KB_ELEMS - 1) / Cfg::KB_ELEMS;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(full_bar(s), TC_PROD_THREADS + 1);
-      tc::mbar_init(empty_bar(s), 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      tc::mbar_init(tfull_bar(a), 1);
-      tc::mbar_init(tempty_bar(a), EPI_WARPS * 32);
-    }
-    tc::fence_barrier_init();
-  }
-  if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, TMEM_COLS);
-  if (warp == TMA_WARP && lane == 0) {
-    tc::tma_prefetch_desc(&map_hi);
-    if (PLANES == 2) tc::tma_prefetch_desc(&map_lo);
-  }
-  tc::tcgen05_before_sync();
-  __syncthreads();
-  tc::tcgen05_after_sync();
-  const uint32_t tmem_base = *tmem_slot_gen;
-  pdl_wait();
-  pdl_trigger();
-
-  if (warp < EPI_WARPS) {
-    // =========================== epilogue: lane = output channel, column = pixel ===========================
-    const int quad = warp & 3;
-    const int n = quad * 32 + lane;
-    const int M = p.M, N = p.N, ldc = p.ldc, ldr = p.ldr, act = p.act & 15;
-    const bool chok = n < N;
-    const float sc = (chok && p.scale) ? __ldg(p.scale + n) : 1.0f;
-    const float sh = (chok && p.shift) ? __ldg(p.shift + n) : 0.0f;
-    const float* const res = p.res;
-    float* const out = p.out;
-    __nv_bfloat16* const out_hi = p.out_hi;
-    __nv_bfloat16* const out_lo = p.out_lo;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      tc::mbar_wait(tfull_bar(acc), (it >> 1) & 1);
-      tc::tcgen05_after_sync();
-#pragma unroll 1
-      for (int j = 0; j < ROWS / 32; ++j) {
-        uint32_t r[32];
-        tc::tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * ROWS + j * 32), r);
-        tc::tmem_ld_wait();
-        const int m0 = tile * ROWS + j * 32;
-        if (chok) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {   // fully unrolled: r[] must stay in registers
-            const int m = m0 + i;
-            if (m < M) {
-              float v = fmaf(__uint_as_float(r[i]), sc, sh);
-              if (res) v += __ldg(res + (size_t)m * ldr + n);
-              v = apply_act(v, act);
-              const size_t o = (size_t)m * ldc + n;
-              if (out) out[o] = v;
-              if (out_hi) {
-                const __nv_bfloat16 h = __float2bfloat16_rn(v);
-                out_hi[o] = h;
-                if (out_lo) out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
-              }
-            }
-          }
-        }
-      }
-      tc::tcgen05_before_sync();
-      tc::mbar_arrive(tempty_bar(acc));
-    }
-  } else if (warp < TMA_WARP) {
-    // =========================== pixel-tile producers: cp.async from the bf16 NHWC planes (256 rows) ===========================
-    constexpr int RPT = 4;
-    const int pt = threadIdx.x - EPI_WARPS * 32;   // 0..255
-    const int chunk = pt & 3;
-    const int rg = pt >> 2;
-    const __nv_bfloat16* const xh = p.x_hi;
-    const __nv_bfloat16* const xl = p.x_lo;
-    int kit = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      long long base[RPT];
-      int ih0[RPT], iw0[RPT];
-      bool ok[RPT];
-      uint32_t soff[RPT];
-#pragma unroll
-      for (int i = 0; i < RPT; ++i) {
-        const int r = rg + 64 * i;
-        const int m = tile * ROWS + r;
-        ok[i] = m < p.M;
-        const int mm = ok[i] ? m : 0;
-        const int ow = mm % p.OW;
-        const int t = mm / p.OW;
-        const int oh = t % p.OH;
-        const int b = t / p.OH;
-        ih0[i] = oh * p.SH - p.PH;
-        iw0[i] = ow * p.SW - p.PW;
-        base[i] = (long long)b * p.H * p.W * p.C;
-        soff[i] = (uint32_t)(r >> 3) * 512u + (uint32_t)(r & 7) * 64u + (uint32_t)((chunk ^ ((r >> 1) & 3)) << 4);
-      }
-      for (int kb = 0; kb < nkb; ++kb, ++kit) {
-        const int s = kit % STAGES;
-        const int k = kb * Cfg::KB_ELEMS + chunk * Cfg::CH_ELEMS;
-        const bool kok = k < p.K;
-        const int tap = kok ? k / p.C : 0;
-        const int ci = k - tap * p.C;
-        const int kh = tap / p.KW, kw = tap - kh * p.KW;
-        tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
-        const uint32_t x_hi = smem_base + s * Cfg::STAGE_BYTES;
-#pragma unroll
-        for (int i = 0; i < RPT; ++i) {
-          const int ih = ih0[i] + kh, iw = iw0[i] + kw;
-          const bool valid = kok && ok[i] && (unsigned)ih < (unsigned)p.H && (unsigned)iw < (unsigned)p.W;
-          const long long e = valid ? base[i] + ((long long)ih * p.W + iw) * p.C + ci : 0;
-          tc::cp_async_16(x_hi + soff[i], xh + e, valid ? 16u : 0u);
-          if (PLANES == 2) tc::cp_async_16(x_hi + Cfg::A_BYTES + soff[i], xl + e, valid ? 16u : 0u);
-        }
-        tc::cp_async_mbar_arrive_noinc(full_bar(s));
-      }
-    }
-    asm volatile("cp.async.wait_all;" ::: "memory");
-  } else if (warp == TMA_WARP) {
-    // =========================== weight tile (TMA, 64-byte rows): all Cout rows, one k-block ===========================
-    if (lane == 0) {
-      int kit = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        for (int kb = 0; kb < nkb; ++kb, ++kit) {
-          const int s = kit % STAGES;
-          tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
-          tc::mbar_arrive_expect_tx(full_bar(s), (uint32_t)(PLANES * w_rows * 64));
-          const uint32_t w_hi = smem_base + s * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES;
-          tc::tma_load_2d(w_hi, &map_hi, full_bar(s), kb * Cfg::KB_ELEMS, 0);
-          if (PLANES == 2) tc::tma_load_2d(w_hi + Cfg::B_BYTES, &map_lo, full_bar(s), kb * Cfg::KB_ELEMS, 0);
-        }
-      }
-    }
-    __syncwarp();
-  } else {
-    // =========================== MMA issuer: D[channel, pixel] += W . X^T ===========================
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc(1, ROWS);   // M = 128 channels, N = 256 pixels
-      int kit = 0, it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        tc::mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
-        tc::tcgen05_after_sync();
-        const uint32_t d = tmem_base + (uint32_t)(acc * ROWS);
-        for (int kb = 0; kb < nkb; ++kb, ++kit) {
-          const int s = kit % STAGES;
-          tc::mbar_wait(full_bar(s), (kit / STAGES) & 1);
-          tc::tcgen05_after_sync();
-          const uint32_t x_hi = smem_base + s * Cfg::STAGE_BYTES;
-          const uint32_t w_hi = x_hi + PLANES * Cfg::A_BYTES;
-          const uint64_t dx_hi = tc::make_smem_desc_sw64(x_hi), dx_lo = tc::make_smem_desc_sw64(x_hi + Cfg::A_BYTES);
-          const uint64_t dw_hi = tc::make_smem_desc_sw64(w_hi), dw_lo = tc::make_smem_desc_sw64(w_hi + Cfg::B_BYTES);
-#pragma unroll
-          for (int k = 0; k < 2; ++k) tc::umma<false>(d, dw_hi + 2 * k, dx_hi + 2 * k, idesc, (kb | k) != 0);
-          if constexpr (PASSES == 3) {
-#pragma unroll
-            for (int k = 0; k < 2; ++k) tc::umma<false>(d, dw_hi + 2 * k, dx_lo + 2 * k, idesc, 1u);
-#pragma unroll
-            for (int k = 0; k < 2; ++k) tc::umma<false>(d, dw_lo + 2 * k, dx_hi + 2 * k, idesc, 1u);
-          }
-          tc::umma_commit(empty_bar(s));
-        }
-        tc::umma_commit(tfull_bar(acc));
-      }
-    }
-    __syncwarp();
-  }
-  tc::tcgen05_before_sync();
-  __syncthreads();
-  if (warp == MMA_WARP) {
-    tc::tcgen05_after_sync();
-    tc::tmem_dealloc(tmem_base, TMEM_COLS);
-  }
-}
-
 // host side ---------------------------------------------------------------------------------------------------------
 // Extra weight tensor maps with 64-byte boxes (32 bf16) and 64B swizzle, for 64 / 128 / 256 weight rows.
 struct Tc3Maps {
@@ -538,7 +329,7 @@ inline cudaError_t tc3_prepare_maps(const TcWeight& w, Tc3Maps* out) {
 inline bool tc3_supported(const ConvGemm& p, int precision) {
   if (precision != 2 && precision != 3) return false;
   if (p.x_hi == nullptr || (precision == 2 && p.x_lo == nullptr)) return false;
-  return p.out2 == nullptr && p.a_map_hi == nullptr && p.ln_w == nullptr && p.C % 8 == 0 && p.K % 8 == 0 && p.ldc % 4 == 0 &&
+  return p.out2 == nullptr && p.a_map_hi == nullptr && p.C % 8 == 0 && p.K % 8 == 0 && p.ldc % 4 == 0 &&
          (p.res == nullptr || p.ldr % 4 == 0) && p.N % 4 == 0;
 }
 
@@ -558,47 +349,15 @@ inline cudaError_t tc3_launch_one(const ConvGemm& p, const Tc3Maps& m, cudaStrea
   return launch_kernel(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, p, m.hi[mi], m.lo[mi], tiles_m, tiles_n);
 }
 
-// D2T_TC3_MT2=1: two m-tiles per CTA.  Measured SLOWER on B200 (encoder 34.7 -> 39.9 ms in bf16x3): halving the
-// weight fill does not pay for the lost epilogue overlap, because the binding resource is shared-memory bandwidth
-// (operand fill writes + tcgen05 operand reads exceed 128 B/clk per SM), not the L2->SM fill.  Off by default.
-inline bool& tc3_two_mtiles() {
-  static bool on = false;
-  return on;
-}
-
-template <int PASSES>
-inline cudaError_t tc3s_launch(const ConvGemm& p, const Tc3Maps& m, cudaStream_t s, int num_sms) {
-  using Cfg = Tc3Cfg<PASSES, 128, 2>;
-  static bool attr_set = false;
-  auto kern = conv_gemm_tc3s_kernel<PASSES>;
-  if (!attr_set) {
-    cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
-    if (st != cudaSuccess) return st;
-    attr_set = true;
-  }
-  const int tiles_m = (p.M + 255) / 256;
-  const int grid = tiles_m < num_sms ? tiles_m : num_sms;
-  const int mi = p.N <= 64 ? 0 : 1;            // weight box of 64 or 128 rows
-  return launch_kernel(kern, dim3(grid), dim3(448), Cfg::SMEM_BYTES, s, p, m.hi[mi], m.lo[mi], tiles_m, mi == 0 ? 64 : 128);
-}
-
 inline cudaError_t launch_conv_gemm_tc3(const ConvGemm& p, const Tc3Maps& m, int precision, cudaStream_t s, int num_sms) {
-  // narrow layers: channels on the M side, 256 pixels on the N side (conv_gemm_tc3s_kernel).  Parity-green and measured
-  // SLOWER (encoder 34.0 -> 40.3 ms): ncu shows these layers bound by the activation traffic of the epilogue (conv0_2
-  // 2.6 GB in 1.12 ms, tensor pipe 19 %), not by MMA issue, and the lane = channel epilogue stores 4-byte / 2-byte
-  // scalars where the pixel-major one stores 16-byte vectors (0.5-1.4 TB/s against 1.4-2.9 TB/s).  D2T_TC3_SWAP=1 enables.
-  static const bool swap_on = getenv("D2T_TC3_SWAP") && atoi(getenv("D2T_TC3_SWAP")) != 0;
-  if (swap_on && p.N <= 128 && (long long)((p.M + 255) / 256) >= 2LL * num_sms)
-    return precision == 2 ? tc3s_launch<3>(p, m, s, num_sms) : tc3s_launch<1>(p, m, s, num_sms);
   const int bn = tc_pick_bn(p.M, p.N, num_sms);
-  // two m-tiles per CTA when the 256-row x 256-column tiles still give every SM at least two tiles
-  // Single-pass bf16 on the 512-channel 3x3 convolutions is the one place where it pays (measured: 0.828 -> 0.734 ms per
-  // launch, 0.54 -> 0.61 of the sustained bf16 peak): there the weight stage is re-read for half as many MMAs.  On the
-  // narrower / shallower convolutions and in the 3-pass mode it loses (encoder 24.4 -> 27.4 ms when applied everywhere).
-  static const bool auto_off = getenv("D2T_TC3_MT2_AUTO") && atoi(getenv("D2T_TC3_MT2_AUTO")) == 0;
-  const bool want = tc3_two_mtiles() || (!auto_off && precision == 3 && p.N >= 512 && p.K >= 4608 && p.res == nullptr);
+  // Two m-tiles per CTA (both accumulators against one weight stage) pay in exactly one place: single-pass bf16 on the
+  // 512-channel 3x3 convolutions without residual (measured 0.828 -> 0.734 ms per launch; there the weight stage is re-read
+  // for half as many MMAs).  Everywhere else, and in the 3-pass mode, the lost epilogue overlap costs more (encoder
+  // 24.4 -> 27.4 ms in bf16, 34.7 -> 39.9 ms in bf16x3 when applied everywhere).
+  const bool want = precision == 3 && p.N >= 512 && p.K >= 4608 && p.res == nullptr;
   const bool mt2 = want && bn == 256 && (long long)((p.M + 255) / 256) * (p.N / 256) >= 2LL * num_sms;
-  if (mt2) return precision == 2 ? tc3_launch_one<3, 256, 2>(p, m, s, num_sms) : tc3_launch_one<1, 256, 2>(p, m, s, num_sms);
+  if (mt2) return tc3_launch_one<1, 256, 2>(p, m, s, num_sms);
   if (precision == 2) {
     switch (bn) {
       case 256: return tc3_launch_one<3, 256>(p, m, s, num_sms);

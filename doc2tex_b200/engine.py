@@ -188,7 +188,7 @@ class Engine:
         return 2 if self.cfg.head == _lib.HEAD["TFM"] else 1
 
     def set_option(self, key: str, value: int):
-        """Engine knobs: "encoder_sms" (SM budget of the encoder's persistent kernels), "pdl" (0/1)."""
+        """Engine knobs (documented at d2t_set_option in include/doc2tex_b200.h)."""
         self._check(self.lib.d2t_set_option(self.h, key.encode(), int(value)), f"d2t_set_option({key})")
 
     # ---- test / profiling hooks ----
@@ -234,6 +234,13 @@ class Engine:
         ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
         self._check(self.lib.d2t_debug_conv_time(self.h, C.byref(ms), C.byref(n), C.byref(fl)), "d2t_debug_conv_time")
         return ms.value, n.value, fl.value
+
+    def decode_time(self, kind: int):
+        """(total ms, launches, algorithmic bytes) of the decode launches of one kind timed since the last call (enable with
+        set_option("time_decode", 1)): 0 self-attention, 1 cross-attention, 2 beam step, 3 greedy pick."""
+        ms, n, by = C.c_double(), C.c_int64(), C.c_double()
+        self._check(self.lib.d2t_debug_decode_time(self.h, kind, C.byref(ms), C.byref(n), C.byref(by)), "d2t_debug_decode_time")
+        return ms.value, n.value, by.value
 
     def launch_count(self) -> int:
         return int(self.lib.d2t_launch_count(self.h))

@@ -152,13 +152,26 @@ int d2t_decode_attn_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, i
                          float* trace_score_dev, int* steps_out, d2t_stream stream);
 
 /*
- * Engine knobs (no reference counterpart).  key = "encoder_sms": number of SMs the encoder's persistent
- * tensor-core kernels may occupy (default: all) — leaving a few SMs free lets the latency-bound decode of
- * batch i overlap the encode of batch i+1 on another stream (doc2tex_b200/pipeline.py); "pdl": 0/1;
- * "decode_groups": concurrent row groups of one decode call (parallel CUDA-graph branches, 0/1 = one chain);
- * "split_k": split-K of the LayerNorm-fed decode projections (default 1); "cluster_step": 1 = the experimental
- * cluster-resident decode step kernel (decode_cluster.cuh) instead of the launch-per-sublayer chain;
- * "attn_group": 1 = beam-grouped decode attention (experimental, measured slower); "time_conv": see d2t_debug_conv_time.
+ * Engine knobs (no reference counterpart; every switch of the engine is set here, none through the environment).
+ * Changing a decode-affecting key drops the cached CUDA graphs of the decode step.
+ *   "encoder_sms"      SMs the encoder's persistent tensor-core kernels may occupy (default: all) — leaving a few SMs free
+ *                      lets the latency-bound decode of batch i overlap the encode of batch i+1 (doc2tex_b200/pipeline.py)
+ *   "pdl"              0/1 programmatic dependent launch inside the decode step (default 1)
+ *   "steps_per_graph"  decode steps captured per CUDA graph, 1..16 (default 8 = the early-exit poll interval)
+ *   "decode_groups"    concurrent row groups of one decode call (parallel graph branches; 0/1 = one chain, default)
+ *   "split_k"          0 = never, 1 = auto split-K of the LayerNorm-fed decode projections (default 1)
+ *   "stack_mma"        0/1 bf16x3 decode projections: two MMAs per k-step against the stacked [W_hi ; W_lo] operand (default 1)
+ *   "attn_image_block" 0/1 beam search: one attention block owns all hypotheses of an image (L1 serves shared records; default 1)
+ *   "attn_split"       warps per (row, head) of the decode attention: 0 = auto, 1, 2
+ *   "fuse_pick"        0/1 greedy pick also embeds the next token and advances the step counter (default 1)
+ *   "kv_bf16"          0/1 bf16 KV caches in the single-pass bf16 mode (default 1; the fp32-parity modes always keep fp32)
+ *   "cluster_step"     1 = experimental cluster-resident decode step kernel (decode_cluster.cuh; measured slower, default 0)
+ *   "tc3"              0/1 stem convolutions fed from bf16 activation planes by cp.async (default 1)
+ *   "lean_acts"        0/1 stem layers write only the representations their consumers read (default 1)
+ *   "fuse_pool"        0/1 max-pools 1 and 2 fused into the producing convolution's epilogue (default 1)
+ *   "pos_interpolate", "pos_grid_h", "pos_grid_w"   ViTEncoder (fix_embed: False) bicubic pos-embed resampling
+ *   "time_conv", "time_decode"   see d2t_debug_conv_time / d2t_debug_decode_time
+ *   "dbg_decode", "dbg_timeline" phase / per-launch timestamps of the last decode step on stderr
  */
 int d2t_set_option(d2t_engine* e, const char* key, int value);
 
@@ -189,6 +202,13 @@ int d2t_debug_gemm_bench(d2t_engine* e, const float* a_dev, const float* w_dev, 
  * bracketed durations (ms), the number of launches timed and the algorithmic FLOPs of one launch (2*M*N*K), and
  * clears the record. */
 int d2t_debug_conv_time(d2t_engine* e, double* total_ms, int64_t* launches, double* flops_per_launch);
+/* Live timing of the memory-bound decode kernels (bench.py's decode roofline): after d2t_set_option(e, "time_decode", 1) the
+ * decode loop runs eagerly (events cannot be timed inside a captured graph) and brackets, with CUDA events on the launching
+ * stream, the launches of kind 0 = self-attention and 1 = cross-attention of decoder layer 1 (decode_attention_*_kernel),
+ * 2 = beam_step_kernel, 3 = greedy_pick_kernel.  This call synchronises and returns, for one kind, the summed durations (ms),
+ * the number of launches and their summed ALGORITHMIC bytes (rows x (t+1) x 2 x d_model x elem for the
+ * self-attention of step t; images x ntok x 2 x d_model x elem for the cross-attention), and clears that record. */
+int d2t_debug_decode_time(d2t_engine* e, int kind, double* total_ms, int64_t* launches, double* total_bytes);
 /* Number of kernel launches issued by this engine since creation (bench bookkeeping;
  * launches replayed from a CUDA graph are counted per replay). */
 int64_t d2t_launch_count(const d2t_engine* e);

@@ -426,20 +426,71 @@ def test_merged_decode_schedule_equals_sequential(built_lib, merge):
     e.set_option("encoder_sms", 148)
 
 
-def test_grouped_beam_attention_equals_per_row_kernel(built_lib):
-    """Option attn_group: the five hypotheses of an image attend together (shared records fetched once).  Same beams,
-    lengths and traces as the per-row kernel; scores within fp32 rounding (different merge order)."""
+@pytest.mark.parametrize("beam,split", [(5, 0), (5, 1), (3, 0), (10, 0)])
+def test_image_block_attention_equals_per_row_kernel(built_lib, beam, split):
+    """Option attn_image_block: one attention block owns all hypotheses of an image (shared records served by L1).  Per
+    (row, head) the arithmetic is the per-row kernel's with the same key split, so beams, lengths, traces AND scores are
+    bit-identical when the splits agree (per-row auto split = 2 at these row counts, image-block default = 2)."""
     e = engine_for("TFM", 1.5, "bf16x3")
     ctx, _, _ = e.encode(synth.make_images(6, 64, 256, seed=55).cuda())
-    b0 = e.decode_beam(ctx, 5, trace=True)
-    e.set_option("attn_group", 1)
+    e.set_option("attn_image_block", 0)
+    e.set_option("attn_split", split)
     try:
-        b1 = e.decode_beam(ctx, 5, trace=True)
+        b0 = e.decode_beam(ctx, beam, trace=True)
+        e.set_option("attn_image_block", 1)
+        b1 = e.decode_beam(ctx, beam, trace=True)
     finally:
-        e.set_option("attn_group", 0)
+        e.set_option("attn_image_block", 1)
+        e.set_option("attn_split", 0)
     assert b0[3] == b1[3] and torch.equal(b0[0], b1[0]) and torch.equal(b0[1], b1[1])
     assert torch.equal(b0[4][:, :b0[3]], b1[4][:, :b1[3]])
-    assert float((b0[2] - b1[2]).abs().max()) <= 1e-4 * float(b0[2].abs().max())
+    if beam <= 8:   # same split on both sides -> same summation order
+        assert torch.equal(b0[2], b1[2])
+    else:           # beam 10: image-block runs one warp per (row, head), the per-row kernel two
+        assert float((b0[2] - b1[2]).abs().max()) <= 1e-4 * float(b0[2].abs().max())
+
+
+@pytest.mark.parametrize("spg", [1, 3, 16])
+def test_steps_per_graph_do_not_change_results(built_lib, spg):
+    """steps_per_graph captures several decode steps in one CUDA graph (tail steps replay a one-step graph); tokens, early
+    exit step, beams and traces must not depend on it (151 = 9 x 16 + 7, 50 x 3 + 1)."""
+    e = engine_for("TFM", 1.5, "bf16x3")
+    ctx, _, _ = e.encode(synth.make_images(4, 64, 256, seed=91).cuda())
+    e.set_option("steps_per_graph", 8)
+    ids0, lg0, st0 = e.decode_greedy(ctx, is_test=True)
+    full0, _, _ = e.decode_greedy(ctx, is_test=False, return_logits=False)
+    b0 = e.decode_beam(ctx, 5, trace=True)
+    e.set_option("steps_per_graph", spg)
+    try:
+        ids1, lg1, st1 = e.decode_greedy(ctx, is_test=True)
+        full1, _, _ = e.decode_greedy(ctx, is_test=False, return_logits=False)
+        b1 = e.decode_beam(ctx, 5, trace=True)
+    finally:
+        e.set_option("steps_per_graph", 8)
+    assert st0 == st1 and torch.equal(ids0[:, :st0], ids1[:, :st1]) and torch.equal(lg0[:, :st0], lg1[:, :st1])
+    assert torch.equal(full0, full1)
+    assert b0[3] == b1[3] and all(torch.equal(a, b) for a, b in zip(b0[:3], b1[:3]))
+    assert torch.equal(b0[4][:, :b0[3]], b1[4][:, :b1[3]])
+
+
+@pytest.mark.parametrize("B", [3, 40])
+def test_stacked_mma_matches_three_pass(built_lib, B):
+    """Option stack_mma: the bf16x3 decode projections issue A_hi x [W_hi ; W_lo] and A_lo x W_hi (2 MMAs per k-step) instead
+    of three; same products, different fp32 summation order -> logits within the fp32-parity tolerance, tokens and beams
+    identical.  B = 40 x beam 5 = 200 rows -> two m-tiles."""
+    e = engine_for("TFM", 1.5, "bf16x3")
+    ctx, _, _ = e.encode(synth.make_images(B, 64, 256, seed=17).cuda())
+    out = {}
+    try:
+        for mode in (0, 1):
+            e.set_option("stack_mma", mode)
+            ids, lg, st = e.decode_greedy(ctx, max_steps=40, is_test=False)
+            out[mode] = (ids.cpu(), lg.cpu(), e.decode_beam(ctx, 5, max_steps=40))
+    finally:
+        e.set_option("stack_mma", 1)
+    assert torch.equal(out[0][0], out[1][0])
+    assert rel_err(out[1][1], out[0][1]) < 1e-4
+    assert torch.equal(out[0][2][0], out[1][2][0]) and torch.equal(out[0][2][1], out[1][2][1])
 
 
 @pytest.mark.parametrize("groups", [2, 3, 8])
