@@ -17,7 +17,7 @@ SYMBOLS = [
     "d2t_create", "d2t_destroy", "d2t_last_error", "d2t_version", "d2t_load_tensor",
     "d2t_finalize_weights", "d2t_encode", "d2t_encoder_geometry", "d2t_decode_greedy",
     "d2t_decode_beam", "d2t_decode_attn_greedy", "d2t_decode_attn_beam", "d2t_set_option", "d2t_set_debug", "d2t_debug_tap",
-    "d2t_debug_gemm", "d2t_debug_gemm_bench", "d2t_debug_conv_time", "d2t_debug_decode_time", "d2t_launch_count",
+    "d2t_debug_gemm", "d2t_debug_gemm_bench", "d2t_debug_conv_time", "d2t_debug_decode_time", "d2t_debug_beam_runner_up", "d2t_launch_count",
 ]
 
 PREC = {"fp32": 0, "tf32x3": 1, "bf16x3": 2, "bf16": 3}
@@ -65,6 +65,7 @@ def load():
     lib.d2t_debug_gemm_bench.argtypes = [vp, fp, fp, fp, i32, i32, i32, i32, i32, i32, C.POINTER(C.c_float), vp]
     lib.d2t_debug_conv_time.argtypes = [vp, C.POINTER(C.c_double), i64p, C.POINTER(C.c_double)]
     lib.d2t_debug_decode_time.argtypes = [vp, i32, C.POINTER(C.c_double), i64p, C.POINTER(C.c_double)]
+    lib.d2t_debug_beam_runner_up.argtypes = [vp, fp]
     lib.d2t_launch_count.argtypes = [vp]
     lib.d2t_launch_count.restype = C.c_int64
     for name in SYMBOLS:

@@ -16,6 +16,7 @@ struct TfmBuffers {
   int *tokens = nullptr, *anc = nullptr, *n_live = nullptr, *n_done = nullptr, *finished = nullptr;
   int *done_seq = nullptr, *done_len = nullptr, *ended = nullptr, *counters = nullptr, *trace = nullptr;
   float *scores = nullptr, *done_score = nullptr, *trace_score = nullptr, *logits_out = nullptr;
+  float* runner_up = nullptr;   // caller buffer (d2t_debug_beam_runner_up), offset to this group's first image
   long long* ids = nullptr;
   // bf16 hi/lo operand planes of the decoder activations + their TMA maps (tensor-core precisions only)
   long long* dbg = nullptr;   // D2T_DBG_DECODE=1: phase timestamps of one decode-step GEMM
@@ -372,6 +373,7 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
     st.tokens = b.tokens; st.anc = b.anc; st.scores = b.scores; st.n_live = b.n_live; st.n_done = b.n_done;
     st.finished = b.finished; st.done_seq = b.done_seq; st.done_len = b.done_len; st.done_score = b.done_score;
     st.counters = b.counters; st.trace = b.trace; st.trace_score = b.trace_score;
+    st.runner_up = b.runner_up;
     st.L = L; st.beam = beam; st.B = B; st.V = V; st.end_id = TFM_END; st.max_steps = T;
     // algorithmic bytes: the logits of every row, and the token + ancestry prefixes read from one buffer and written to the other
     DecTimer tm(e, true, 2, (double)R * V * 4 + 4.0 * R * (e->cur_step + 1) * 4, s);
@@ -534,6 +536,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     grp.R0 = grp.B0 * rows_per_img;
     grp.Rg = grp.Bg * rows_per_img;
     if ((rc = alloc_group(e, grp, ntok, beam, T, want_logits, counters_all + 4 * g, s))) return rc;
+    grp.b.runner_up = (beam > 0 && e->beam_runner_up) ? e->beam_runner_up + (size_t)grp.B0 * T : nullptr;
   }
   // cross-attention K/V of the encoder memory, once per image and layer (the reference re-projects
   // them at every step: nn.MultiheadAttention inside tfm.py:130 / :165)
@@ -587,7 +590,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
       const void* ptrs[] = {b.crosskv, b.selfkv, b.x, b.x2, b.q, b.att, b.ffn, b.logits, b.counters, b.tokens, b.anc,
                             b.scores, b.n_live, b.n_done, b.finished, b.done_seq, b.done_len, b.done_score, b.trace,
                             b.trace_score, b.ended, b.ids, b.logits_out, b.dbg, b.x_hi, b.x_lo, b.att_hi, b.att_lo, b.ffn_hi, b.ffn_lo,
-                            b.crosskv_tmp, b.crosskv_f32};
+                            b.crosskv_tmp, b.crosskv_f32, b.runner_up};
       for (const void* q : ptrs) key.push_back((long long)(uintptr_t)q);
     }
     for (auto& g : e->graphs) if (g.key == key) { *exec_out = g.exec; *nodes_out = g.nodes; return 0; }

@@ -428,6 +428,7 @@ struct BeamState {
   int* counters;        // step, -, done_step, n_finished
   int* trace;           // optional [B][max_steps][beam][2]
   float* trace_score;   // optional [B][max_steps][beam]
+  float* runner_up;     // optional [B][max_steps]: score of the best candidate NOT selected at that step (near-tie audit)
   int L, beam, B, V, end_id, max_steps;
 };
 
@@ -478,8 +479,9 @@ beam_step_kernel(const float* __restrict__ logits, BeamState st) {
     s_cand[i] = st.scores[img * beam + s] + lp;
   }
   __syncthreads();
-  // k rounds of block-wide argmax (value desc, index asc)
-  for (int round = 0; round < k; ++round) {
+  // k rounds of block-wide argmax (value desc, index asc); one more when the near-tie audit wants the runner-up's score
+  const int rounds = k + (st.runner_up != nullptr ? 1 : 0);
+  for (int round = 0; round < rounds; ++round) {
     float bv = -INFINITY; int bi = 0x7fffffff;
     for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
       const float v = s_cand[i];
@@ -496,7 +498,8 @@ beam_step_kernel(const float* __restrict__ logits, BeamState st) {
     if (threadIdx.x == 0) {
       for (int i = 1; i < nw; ++i)
         if (red_v[i] > bv || (red_v[i] == bv && red_i[i] < bi)) { bv = red_v[i]; bi = red_i[i]; }
-      top_v[round] = bv; top_i[round] = bi;
+      if (round < k) { top_v[round] = bv; top_i[round] = bi; }
+      else st.runner_up[(size_t)img * st.max_steps + t] = bv;
       if (bi != 0x7fffffff) s_cand[bi] = -INFINITY;  // exclude from later rounds
     }
     __syncthreads();

@@ -116,6 +116,7 @@ struct d2t_engine {
   // option "time_decode": the decode loop runs eagerly and brackets the memory-bound launches of decoder layer 1 with events
   struct DecEvent { int kind; double bytes; cudaEvent_t a, b; };   // kind: 0 self-attn, 1 cross-attn, 2 beam step, 3 greedy pick
   std::vector<DecEvent> dec_events;
+  float* beam_runner_up = nullptr;   // d2t_debug_beam_runner_up: caller-owned (B, max_steps) buffer filled by d2t_decode_beam
   int cur_step = 0;   // host copy of the step being enqueued (eager mode only; the device reads its own counter)
   bool fuse_pick = true;    // option "fuse_pick": 0 = separate embed / advance launches in the greedy decode step
   bool lean_acts = true;    // option "lean_acts": 0 = every stem layer writes fp32 AND operand planes, read or not
@@ -881,6 +882,15 @@ int d2t_debug_decode_time(d2t_engine* e, int kind, double* total_ms, int64_t* la
   }
   e->dec_events.swap(keep);
   *total_ms = ms_sum; *launches = n; *total_bytes = bytes;
+  return D2T_OK;
+}
+
+int d2t_debug_beam_runner_up(d2t_engine* e, float* runner_up_dev) {
+  if (!e) return D2T_ERR_INVALID;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  drop_graphs(e);   // the pointer is baked into the captured beam step
+  e->beam_runner_up = runner_up_dev;
   return D2T_OK;
 }
 

@@ -164,11 +164,17 @@ class Engine:
                        logits.data_ptr() if return_logits else None, C.byref(steps), self._stream()), "d2t_decode_greedy")
         return ids, logits, steps.value
 
-    def decode_beam(self, ctx: torch.Tensor, beam: int, max_steps: Optional[int] = None, trace: bool = False):
-        """Batched TransformerPrediction.forward_beam / AttentionV2.forward_beam: per image best ids (padded), length, score."""
+    def decode_beam(self, ctx: torch.Tensor, beam: int, max_steps: Optional[int] = None, trace: bool = False,
+                    runner_up: Optional[torch.Tensor] = None):
+        """Batched TransformerPrediction.forward_beam / AttentionV2.forward_beam: per image best ids (padded), length, score.
+        runner_up (TFM head, tests): a (B, T) fp32 device tensor that receives, per step, the score of the best candidate NOT
+        selected — with the trace scores it gives the margin of every beam decision (near-tie audit)."""
         ctx = self._dev(ctx, torch.float32)
         B, ntok, _ = ctx.shape
         T = self.cfg.max_seq_len + 1 if max_steps is None else max_steps
+        if runner_up is not None:
+            assert runner_up.is_cuda and runner_up.dtype == torch.float32 and tuple(runner_up.shape) == (B, T) and runner_up.is_contiguous()
+            self._check(self.lib.d2t_debug_beam_runner_up(self.h, runner_up.data_ptr()), "d2t_debug_beam_runner_up")
         ids = torch.empty(B, T, device=self.device, dtype=torch.int64)
         lens = torch.empty(B, device=self.device, dtype=torch.int32)
         score = torch.empty(B, device=self.device, dtype=torch.float32)
@@ -180,6 +186,8 @@ class Engine:
                        score.data_ptr(), tr.data_ptr() if trace else None,
                        trs.data_ptr() if trace else None, C.byref(steps), self._stream()),
                     "d2t_decode_beam")
+        if runner_up is not None:
+            self._check(self.lib.d2t_debug_beam_runner_up(self.h, None), "d2t_debug_beam_runner_up")
         return ids, lens, score, steps.value, tr, trs
 
     @property

@@ -178,7 +178,7 @@ class _Init:
 
 
 def make_state_dict(cfg: dict, seed: int = 1111, suppress_end: bool = False,
-                    end_bias: float | None = None) -> "OrderedDict[str, torch.Tensor]":
+                    end_bias: float | None = None, sharpen: float = 1.0) -> "OrderedDict[str, torch.Tensor]":
     """Seeded random weights in the reference's ``Model.state_dict()`` schema.
 
     Distributions follow the reference initialisers (kaiming fan_out convs
@@ -189,6 +189,10 @@ def make_state_dict(cfg: dict, seed: int = 1111, suppress_end: bool = False,
     -1e4 (the "full-length" decode regime of §8d); ``end_bias`` sets it to an
     arbitrary value instead (a positive bias makes random-init beams actually
     complete, which is what exercises the END bookkeeping of tools/beam.py:92-100).
+    ``sharpen`` multiplies the output projection (TFM ``proj`` / Attn ``generator`` weight and bias) by a constant: the
+    random-init heads emit nearly uniform distributions, where beam candidates tie to within a few fp32 ulps of the
+    cumulative score; a sharpened head is peaked like a trained one, so every top-k decision has a margin that no fp32
+    summation order can flip and beam traces can be asserted identical for 100 % of the images.
     """
     if suppress_end:
         end_bias = -1e4
@@ -285,6 +289,7 @@ def make_state_dict(cfg: dict, seed: int = 1111, suppress_end: bool = False,
                 sd[p + n + ".weight"] = rng.normal((d,), 0.1, 1.0)
                 sd[p + n + ".bias"] = rng.normal((d,), 0.1)
         w, b = rng.linear_default(V, d)
+        w, b = w * sharpen, b * sharpen
         if end_bias is not None:
             b[TFM_END] = end_bias
         sd[PRED + "proj.weight"], sd[PRED + "proj.bias"] = w, b
@@ -306,6 +311,7 @@ def make_state_dict(cfg: dict, seed: int = 1111, suppress_end: bool = False,
         sd[r + "bias_ih"] = rng.uniform((4 * hs,), -bnd, bnd)
         sd[r + "bias_hh"] = rng.uniform((4 * hs,), -bnd, bnd)
         w, b = rng.linear_default(V, hs)
+        w, b = w * sharpen, b * sharpen
         if end_bias is not None:
             b[ATTN_END] = end_bias
         sd[PRED + "attention_cell.generator.weight"] = w

@@ -209,6 +209,11 @@ int d2t_debug_conv_time(d2t_engine* e, double* total_ms, int64_t* launches, doub
  * the number of launches and their summed ALGORITHMIC bytes (rows x (t+1) x 2 x d_model x elem for the
  * self-attention of step t; images x ntok x 2 x d_model x elem for the cross-attention), and clears that record. */
 int d2t_debug_decode_time(d2t_engine* e, int kind, double* total_ms, int64_t* launches, double* total_bytes);
+/* Near-tie audit of the TFM beam search (tests): runner_up_dev = a caller-owned (B, max_steps) fp32 buffer that every later
+ * d2t_decode_beam call fills with the cumulative score of the best candidate it did NOT select at each step (-inf when there is
+ * none; untouched after an image finished); NULL switches the audit off.  The margin of a decision is the smallest gap between
+ * neighbours among trace_score_dev[b, t, :k] and this value. */
+int d2t_debug_beam_runner_up(d2t_engine* e, float* runner_up_dev);
 /* Number of kernel launches issued by this engine since creation (bench bookkeeping;
  * launches replayed from a CUDA graph are counted per replay). */
 int64_t d2t_launch_count(const d2t_engine* e);

@@ -154,6 +154,18 @@ def encoder_forward(sd: SD, img: torch.Tensor, heads: int = 8, taps: Optional[di
     return x, grid, pad
 
 
+def topk_margin(cand: torch.Tensor, k: int) -> Tuple[float, float]:
+    """Near-tie audit of one beam decision: the smallest gap between neighbours among the k selected
+    candidates AND the best one left out (the top k+1 of ``cand``), and the fp32 spacing (ulp) at their magnitude.
+    A decision whose gap is a few ulps can legitimately flip under any other fp32 summation order."""
+    import numpy as np
+    vals = torch.topk(cand.reshape(-1), min(k + 1, cand.numel())).values
+    if vals.numel() < 2:
+        return float("inf"), 0.0
+    gap = float((vals[:-1] - vals[1:]).min())
+    return gap, float(np.spacing(np.float32(float(vals.abs().max()))))
+
+
 # --------------------------------------------------------------------------------------
 # TFM head
 # --------------------------------------------------------------------------------------
@@ -208,12 +220,13 @@ class TFMHead:
                     break
             return out.max(dim=2)[1], out, tgt[:, 1:]
 
-    def beam(self, ctx1: torch.Tensor, beam_size: int, trace: Optional[list] = None):
+    def beam(self, ctx1: torch.Tensor, beam_size: int, trace: Optional[list] = None, margins: Optional[list] = None):
         """forward_beam for ONE image with a FRESH beam (tfm.py:145-186, tools/beam.py:38-140;
         the library never resets its Beam — quirk Q6 — the demo does, which is the semantics kept).
 
         Returns (seq list[int], score float).  ``trace`` (optional list) receives per step
-        ``(parents, words, scores)`` of the top-k candidates in top-k order."""
+        ``(parents, words, scores)`` of the top-k candidates in top-k order; ``margins`` (optional list) the per-step
+        ``topk_margin`` (gap, ulp) of the decision."""
         assert ctx1.shape[0] == 1
         with torch.no_grad():
             L = self.max_seq_len + 2
@@ -232,6 +245,8 @@ class TFMHead:
                 cand = (scores[:, None] + logp).reshape(-1)
                 top_s, top_i = torch.topk(cand, k=k)
                 parents, words = top_i // V, top_i % V
+                if margins is not None:
+                    margins.append(topk_margin(cand, k))
                 if trace is not None:
                     trace.append((parents.tolist(), words.tolist(), top_s.tolist()))
                 new_h, new_s = [], []
@@ -334,7 +349,8 @@ class AttnV2Head:
         out = F.linear(h, sd[P + "attention_cell.generator.weight"], sd[P + "attention_cell.generator.bias"])
         return out, h, c, alpha
 
-    def beam(self, ctx1: torch.Tensor, beam_size: int = 5, batch_max_length: int = 150, trace: Optional[list] = None):
+    def beam(self, ctx1: torch.Tensor, beam_size: int = 5, batch_max_length: int = 150, trace: Optional[list] = None,
+             margins: Optional[list] = None):
         """AttentionV2.forward_beam (seq2seq_v2.py:12-174), batch 1, with its quirks:
         step 0 ranks row 0 only (:98-99); hidden follows the parent but the coverage memory is re-indexed by top-k
         POSITION (:137-147); if the LAST executed step completed nothing, live beam 0 wins over earlier completions
@@ -361,6 +377,8 @@ class AttnV2Head:
                 out, h, c, alpha = self._cell(h, c, H, emb, mem)
                 V = out.shape[1]
                 scores = top_k_scores.expand_as(out) + F.log_softmax(out, dim=-1)
+                if margins is not None:
+                    margins.append(topk_margin(scores[0] if step == 0 else scores, beam_size))
                 if step == 0:
                     top_k_scores, top_k_words = scores[0].topk(beam_size, 0, True, True)
                 else:

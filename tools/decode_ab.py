@@ -1,0 +1,83 @@
+"""A/B timing of the decode step under engine options (us per step, CUDA-event timed decode calls of 151 steps).
+
+    python tools/decode_ab.py [--precision bf16x3] [--timeline]
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from doc2tex_b200 import synth  # noqa: E402
+from doc2tex_b200.engine import Engine  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--precision", default="bf16x3")
+ap.add_argument("--timeline", action="store_true")
+ap.add_argument("--sets", default="")
+a = ap.parse_args()
+
+cfg = synth.make_config("TFM")
+sd = synth.make_state_dict(cfg, seed=1111, suppress_end=True)
+eng = Engine(cfg, "cuda:0", precision=a.precision)
+eng.load_state_dict(sd)
+img = synth.make_images(256, 64, 256, seed=2024).cuda()
+ctx, _, _ = eng.encode(img)
+
+BASE = {"stack_mma": 0, "attn_image_block": 0, "steps_per_graph": 1, "attn_split": 0}
+SETS = [
+    ("round-1 chain", {}),
+    ("+ stack_mma", {"stack_mma": 1}),
+    ("+ attn_image_block", {"attn_image_block": 1}),
+    ("+ attn_image_block, split 1", {"attn_image_block": 1, "attn_split": 1}),
+    ("+ 8 steps per graph", {"steps_per_graph": 8}),
+    ("all on (default)", {"stack_mma": 1, "attn_image_block": 1, "steps_per_graph": 8}),
+    ("all on, 16 steps per graph", {"stack_mma": 1, "attn_image_block": 1, "steps_per_graph": 16}),
+]
+WORK = [("greedy", 32), ("greedy", 256), ("greedy", 1024), ("beam", 32), ("beam", 256), ("beam", 1024)]
+
+
+def run(mode, n):
+    c = ctx.repeat((n + 255) // 256, 1, 1)[:n].contiguous()
+    best = 1e9
+    for i in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        if mode == "greedy":
+            eng.decode_greedy(c, 151, is_test=True, return_logits=False)
+        else:
+            eng.decode_beam(c, 5, 151)
+        e1.record()
+        torch.cuda.synchronize()
+        if i > 0:
+            best = min(best, e0.elapsed_time(e1))
+    return best
+
+
+for name, opts in SETS:
+    o = dict(BASE)
+    o.update(opts)
+    for k, v in o.items():
+        eng.set_option(k, v)
+    row = []
+    for mode, n in WORK:
+        if mode == "greedy" and "attn_image_block" in opts:
+            row.append("      -")
+            continue
+        ms = run(mode, n)
+        row.append(f"{1e3 * ms / 151:7.1f}")
+    print(f"{name:<34}" + " ".join(f"{m[0]}{n}r={r}" for (m, n), r in zip([(m, n * (5 if m == 'beam' else 1)) for m, n in WORK], row)), flush=True)
+
+if a.timeline:
+    for k, v in {"stack_mma": 1, "attn_image_block": 1, "steps_per_graph": 1}.items():
+        eng.set_option(k, v)
+    eng.set_option("dbg_timeline", 1)
+    for mode, n in (("greedy", 256), ("greedy", 1024), ("beam", 256)):
+        print(f"--- timeline {mode} {n} images", file=sys.stderr, flush=True)
+        c = ctx.repeat((n + 255) // 256, 1, 1)[:n].contiguous()
+        if mode == "greedy":
+            eng.decode_greedy(c, 100, is_test=True, return_logits=False)
+        else:
+            eng.decode_beam(c, 5, 100)
+    eng.set_option("dbg_timeline", 0)
