@@ -81,6 +81,39 @@ int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long 
   const bool kv16 = kv_is_bf16(e);
   const __nv_bfloat16* kvh = reinterpret_cast<const __nv_bfloat16*>(kv);
   cudaError_t st;
+  // Staged kernel (default): one block per (image, head) stages every K / V record it needs into shared memory in one
+  // cp.async round trip — before the dependency wait where the data allows — and computes out of shared memory.
+  if (e->attn_staged && R % rows_per_src == 0 && rows_per_src <= 16 && D == heads * 32) {
+    const int G = rows_per_src, B = R / G;
+    const int n_max = n_fixed > 0 ? n_fixed : anc_ld > 0 ? anc_ld : 0;   // self-attention: at most max_steps positions
+    int cap = e->attn_cap;
+    if (cap <= 0) {
+      // one round whenever possible: every position once, plus (beam) the diverged tails of the G hypotheses
+      const int want = n_fixed > 0 ? n_fixed : (anc ? n_max + 64 : n_max);
+      cap = ((want + 7) / 8) * 8;
+    }
+    if (cap > 32 * STAGED_MAX_PASS) cap = 32 * STAGED_MAX_PASS;
+    if (cap < 32) cap = 32;
+    if (n_max > 0) {
+      const size_t rec = kv16 ? StagedRec<__nv_bfloat16>::BYTES : StagedRec<float>::BYTES;
+      const size_t smem = (size_t)cap * rec + (anc ? (size_t)G * anc_ld * 4 : 0) + 16 + (size_t)G * 128;
+      if (smem <= 200 * 1024) {
+        static bool attr_f = false, attr_h = false;
+        if (kv16) {
+          if (!attr_h) { CUDA_TRY(e, cudaFuncSetAttribute(decode_attention_staged_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_h = true; }
+          st = launch_kernel(decode_attention_staged_kernel<__nv_bfloat16>, dim3(B * heads), dim3(G * 32), smem, s, q, D, kvh, row_stride,
+                             2 * D, anc, anc_parity, anc_ld, G, step, n_fixed, out, D, out_hi, out_lo, cap, heads);
+        } else {
+          if (!attr_f) { CUDA_TRY(e, cudaFuncSetAttribute(decode_attention_staged_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_f = true; }
+          st = launch_kernel(decode_attention_staged_kernel<float>, dim3(B * heads), dim3(G * 32), smem, s, q, D, kv, row_stride,
+                             2 * D, anc, anc_parity, anc_ld, G, step, n_fixed, out, D, out_hi, out_lo, cap, heads);
+        }
+        CUDA_TRY(e, st);
+        e->launches += 1;
+        return 0;
+      }
+    }
+  }
   // Beam search: the hypotheses of an image share the encoder memory and most of their prefixes.  One block owns ALL
   // hypotheses of an image (for a slice of the heads), so their loads of a shared record are issued together on one SM and
   // every fetch after the first is an L1 hit; the per-row mapping spreads them over SMs and pays L2 -> SM for each

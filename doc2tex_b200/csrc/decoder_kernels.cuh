@@ -257,6 +257,214 @@ decode_attention_image_kernel(const float* __restrict__ q, int ldq, const KV* __
   if (g == 0) attention_store(acc, sum, (size_t)r * D + h * HD + c, out, out_hi, out_lo);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Staged single-query attention: the decode attention above is LATENCY bound, not bandwidth bound — a warp walks its keys
+// two at a time and pays one L2 / HBM round trip per pair (13 dependent round trips at step 100; ncu: 7.5 TB/s nominal at
+// 1 280 beam rows with every repeat served by L2, 52 % of the warp slots idle on long-scoreboard stalls).  Here a block owns
+// one head of one image (all G hypotheses of it: warp = hypothesis), stages EVERY record it needs into shared memory with
+// 16-byte cp.async in ONE round trip, and computes softmax(q K^T) V out of shared memory:
+//   * beam search: position j of hypothesis b lives in physical row anc[b][j]; hypotheses share the prefix up to their
+//     common ancestor, so positions [0, c) (c = first position where the ancestry rows differ) are staged ONCE for the image
+//     and only the tail [c, n) once per hypothesis; the encoder memory (cross-attention) is staged once for all G.
+//   * programmatic dependent launch: everything except q and the record of the CURRENT position was written at least two
+//     kernels ago (earlier steps; the ancestry table by the previous step's beam kernel; the encoder memory before the loop),
+//     so it is staged BEFORE griddepcontrol.wait and overlaps the projection GEMM that precedes this kernel.
+//   * more records than the shared-memory capacity (long encoder memories, wide beams): rounds of `cap` records with an
+//     online-softmax merge between rounds.
+// Record = [K head slice (32) | V head slice (32) | 16 B pad]: the pad makes the key-per-lane 16-byte reads conflict free.
+//   grid = images x 8 heads; block = G warps; dynamic smem = cap * REC + G * anc_ld * 4 + G * 128 bytes
+// ---------------------------------------------------------------------------------------------
+template <typename KV>
+struct StagedRec {
+  static constexpr int HD = 32;
+  static constexpr int HALF_BYTES = HD * (int)sizeof(KV);          // K (or V) head slice
+  static constexpr int BYTES = 2 * HALF_BYTES + 16;                // + pad
+  static constexpr int PIECES = 2 * HALF_BYTES / 16;               // 16-byte cp.async pieces per record
+  static constexpr int EL_PER_PIECE = 16 / (int)sizeof(KV);
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// 32-dim dot product of the query (shared memory, broadcast reads) with one staged K head slice
+__device__ __forceinline__ float staged_dot(const float* __restrict__ sq, const uint8_t* __restrict__ rec, float) {
+  float d = 0.f;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const float4 k = *reinterpret_cast<const float4*>(rec + 16 * u);
+    const float4 qq = *reinterpret_cast<const float4*>(sq + 4 * u);
+    d = fmaf(qq.x, k.x, fmaf(qq.y, k.y, fmaf(qq.z, k.z, fmaf(qq.w, k.w, d))));
+  }
+  return d;
+}
+__device__ __forceinline__ float staged_dot(const float* __restrict__ sq, const uint8_t* __restrict__ rec, __nv_bfloat16) {
+  float d = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(rec + 16 * u);
+    const float4 q0 = *reinterpret_cast<const float4*>(sq + 8 * u), q1 = *reinterpret_cast<const float4*>(sq + 8 * u + 4);
+    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
+    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.z));
+    const float2 e = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.w));
+    d = fmaf(q0.x, a.x, fmaf(q0.y, a.y, fmaf(q0.z, b.x, fmaf(q0.w, b.y, d))));
+    d = fmaf(q1.x, c.x, fmaf(q1.y, c.y, fmaf(q1.z, e.x, fmaf(q1.w, e.y, d))));
+  }
+  return d;
+}
+__device__ __forceinline__ float staged_v(const uint8_t* rec_v, int lane, float) { return reinterpret_cast<const float*>(rec_v)[lane]; }
+__device__ __forceinline__ float staged_v(const uint8_t* rec_v, int lane, __nv_bfloat16) {
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rec_v)[lane]);
+}
+
+constexpr int STAGED_MAX_PASS = 8;   // 32-key passes per round: cap <= 256 records per hypothesis and round
+
+template <typename KV>
+__global__ void __launch_bounds__(512)
+decode_attention_staged_kernel(const float* __restrict__ q, int ldq, const KV* __restrict__ kv, long long row_stride,
+                               int pos_stride, const int* __restrict__ anc, long long anc_parity_stride, int anc_ld,
+                               int G, const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
+                               __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int cap, int nheads) {
+  using R = StagedRec<KV>;
+  extern __shared__ __align__(16) uint8_t staged_smem[];
+  uint8_t* const s_rec = staged_smem;
+  int* const s_anc = reinterpret_cast<int*>(staged_smem + (size_t)cap * R::BYTES);
+  float* const s_q = reinterpret_cast<float*>(staged_smem + (((size_t)cap * R::BYTES + (anc ? (size_t)G * anc_ld * 4 : 0) + 15) & ~(size_t)15));
+  __shared__ int s_common;
+  const uint32_t s_rec_addr = (uint32_t)__cvta_generic_to_shared(s_rec);
+
+  const int img = blockIdx.x / nheads, h = blockIdx.x - img * nheads;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nthr = blockDim.x;
+  const int r = img * G + wid;                       // this warp's row (hypothesis)
+  const bool self = n_fixed <= 0;
+  // ---- before the dependency wait: only data written at least two kernels ago ----
+  const int t = step ? *step : 0;
+  const int n = self ? t + 1 : n_fixed;
+  const long long src0 = (long long)img * (anc ? G : 1);   // first physical row of this image
+  int c = n;                                               // positions [0, c) are common to all hypotheses
+  if (anc) {
+    const int* a0 = anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)img * G * anc_ld;
+    if (threadIdx.x == 0) s_common = n;
+    for (int i = threadIdx.x; i < G * n; i += nthr) {
+      const int b = i / n, j = i - b * n;
+      s_anc[b * anc_ld + j] = a0[(size_t)b * anc_ld + j];
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += nthr) {
+      const int a = s_anc[j];
+      bool same = true;
+      for (int b = 1; b < G; ++b) same = same && (s_anc[b * anc_ld + j] == a);
+      if (!same) atomicMin(&s_common, j);
+    }
+    __syncthreads();
+    c = s_common;
+  }
+  const KV* const kvh = kv + h * R::HD;
+  // records of positions [p0, p1): the common part first (one record per position), then G records per position
+  auto stage = [&](int p0, int p1, int j_lo, int j_hi) {   // stages positions [j_lo, j_hi) of the round [p0, p1)
+    const int ns = max(0, min(p1, c) - p0);                // common records of this round
+    const int pc = max(p0, c);                             // first per-hypothesis position
+    const int piece = threadIdx.x % R::PIECES;
+    const int ja = max(j_lo, p0), jb = min(j_hi, p1);      // positions [ja, jb)
+    const int first = ja < c ? ja - p0 : ns + (ja - pc) * G;
+    const int last = jb <= c ? jb - p0 : ns + (jb - pc) * G;
+    if (ja >= jb) return;
+    for (int rec = first + threadIdx.x / R::PIECES; rec < last; rec += nthr / R::PIECES) {
+      int j, slot;
+      if (rec < ns) { j = p0 + rec; slot = anc ? s_anc[j] : 0; }
+      else { const int e = rec - ns; j = pc + e / G; const int b = e - (e / G) * G; slot = s_anc[b * anc_ld + j]; }
+      const KV* src = kvh + (size_t)(src0 + slot) * row_stride + (size_t)j * pos_stride +
+                      (piece < R::PIECES / 2 ? piece * R::EL_PER_PIECE : D + (piece - R::PIECES / 2) * R::EL_PER_PIECE);
+      cp_async16(s_rec_addr + (uint32_t)rec * R::BYTES + (uint32_t)piece * 16u, src);
+    }
+  };
+  // first round boundaries: as many positions as fit into `cap` records
+  auto round_end = [&](int p0) {
+    const int common_left = max(0, c - p0);
+    if (common_left >= cap) return p0 + cap;
+    const int tail = (cap - common_left) / G;            // per-hypothesis positions that still fit
+    return min(n, max(p0, c) + tail);
+  };
+  int p0 = 0, p1 = round_end(0);
+  stage(p0, p1, 0, self ? min(p1, t) : p1);              // everything but the current position of the self-attention
+  pdl_wait();
+  pdl_trigger();
+  if (self && t < p1) stage(p0, p1, t, t + 1);           // K / V of the current position: written by the preceding projection
+  s_q[wid * 32 + lane] = q[(size_t)r * ldq + h * R::HD + lane] * rsqrtf((float)R::HD);
+  cp_async_wait_all();
+  __syncthreads();
+
+  float M = -INFINITY, L = 0.f, acc = 0.f;               // online softmax state across rounds; lane = output channel
+  const float* const sq = s_q + wid * 32;
+  for (;;) {
+    const int ns = max(0, min(p1, c) - p0), pc = max(p0, c);
+    auto rec_of = [&](int j) { return j < c ? j - p0 : ns + (j - pc) * G + (anc ? wid : 0); };
+    float sc[STAGED_MAX_PASS];
+    float m_r = -INFINITY;
+#pragma unroll
+    for (int ps = 0; ps < STAGED_MAX_PASS; ++ps) {
+      const int j = p0 + ps * 32 + lane;
+      sc[ps] = -INFINITY;
+      if (p0 + ps * 32 < p1 && j < p1) sc[ps] = staged_dot(sq, s_rec + (size_t)rec_of(j) * R::BYTES, KV());
+      m_r = fmaxf(m_r, sc[ps]);
+    }
+    m_r = warp_max(m_r);
+    const float Mn = fmaxf(M, m_r);
+    const float corr = (M == -INFINITY) ? 0.f : expf(M - Mn);
+    float l_r = 0.f;
+#pragma unroll
+    for (int ps = 0; ps < STAGED_MAX_PASS; ++ps) {
+      sc[ps] = (sc[ps] == -INFINITY) ? 0.f : expf(sc[ps] - Mn);
+      l_r += sc[ps];
+    }
+    l_r = warp_sum(l_r);
+    L = L * corr + l_r;
+    acc *= corr;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // four independent chains over the keys
+#pragma unroll
+    for (int ps = 0; ps < STAGED_MAX_PASS; ++ps) {
+      const int jb = p0 + ps * 32;
+      if (jb < p1) {
+        const int cnt = min(32, p1 - jb);
+        int jj = 0;
+        for (; jj + 4 <= cnt; jj += 4) {
+          const float w0 = __shfl_sync(0xffffffffu, sc[ps], jj), w1 = __shfl_sync(0xffffffffu, sc[ps], jj + 1);
+          const float w2 = __shfl_sync(0xffffffffu, sc[ps], jj + 2), w3 = __shfl_sync(0xffffffffu, sc[ps], jj + 3);
+          a0 = fmaf(w0, staged_v(s_rec + (size_t)rec_of(jb + jj) * R::BYTES + R::HALF_BYTES, lane, KV()), a0);
+          a1 = fmaf(w1, staged_v(s_rec + (size_t)rec_of(jb + jj + 1) * R::BYTES + R::HALF_BYTES, lane, KV()), a1);
+          a2 = fmaf(w2, staged_v(s_rec + (size_t)rec_of(jb + jj + 2) * R::BYTES + R::HALF_BYTES, lane, KV()), a2);
+          a3 = fmaf(w3, staged_v(s_rec + (size_t)rec_of(jb + jj + 3) * R::BYTES + R::HALF_BYTES, lane, KV()), a3);
+        }
+        for (; jj < cnt; ++jj) {
+          const float w0 = __shfl_sync(0xffffffffu, sc[ps], jj);
+          a0 = fmaf(w0, staged_v(s_rec + (size_t)rec_of(jb + jj) * R::BYTES + R::HALF_BYTES, lane, KV()), a0);
+        }
+      }
+    }
+    acc += (a0 + a1) + (a2 + a3);
+    M = Mn;
+    if (p1 >= n) break;
+    // next round (only when the records did not fit): restage after everybody is done with the buffer
+    __syncthreads();
+    p0 = p1;
+    p1 = round_end(p0);
+    stage(p0, p1, p0, p1);
+    cp_async_wait_all();
+    __syncthreads();
+  }
+  const float o = acc / L;
+  const size_t off = (size_t)r * D + h * R::HD + lane;
+  out[off] = o;
+  if (out_hi) {
+    __nv_bfloat16 hi, lo;
+    split_bf16(o, hi, lo);
+    out_hi[off] = hi;
+    if (out_lo) out_lo[off] = lo;
+  }
+}
+
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     out[i] = __float2bfloat16_rn(in[i]);

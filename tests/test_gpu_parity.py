@@ -433,6 +433,7 @@ def test_image_block_attention_equals_per_row_kernel(built_lib, beam, split):
     bit-identical when the splits agree (per-row auto split = 2 at these row counts, image-block default = 2)."""
     e = engine_for("TFM", 1.5, "bf16x3")
     ctx, _, _ = e.encode(synth.make_images(6, 64, 256, seed=55).cuda())
+    e.set_option("attn_staged", 0)
     e.set_option("attn_image_block", 0)
     e.set_option("attn_split", split)
     try:
@@ -442,12 +443,47 @@ def test_image_block_attention_equals_per_row_kernel(built_lib, beam, split):
     finally:
         e.set_option("attn_image_block", 1)
         e.set_option("attn_split", 0)
+        e.set_option("attn_staged", 1)
     assert b0[3] == b1[3] and torch.equal(b0[0], b1[0]) and torch.equal(b0[1], b1[1])
     assert torch.equal(b0[4][:, :b0[3]], b1[4][:, :b1[3]])
     if beam <= 8:   # same split on both sides -> same summation order
         assert torch.equal(b0[2], b1[2])
     else:           # beam 10: image-block runs one warp per (row, head), the per-row kernel two
         assert float((b0[2] - b1[2]).abs().max()) <= 1e-4 * float(b0[2].abs().max())
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("cap", [0, 32, 40])
+def test_staged_attention_equals_walking_kernel(built_lib, precision, cap):
+    """Option attn_staged: every K / V record of a (image, head) block staged in shared memory by cp.async, softmax over the
+    whole round instead of the online walk.  Same math in a different fp32 order: per-step logits within the fp32-parity
+    tolerance of the walking kernel, greedy tokens and beams identical (bf16x3).  cap = 32 / 40 forces several staging
+    rounds (online merge across rounds; 40 is not a multiple of the beam width), also for the 67-token encoder memory."""
+    from doc2tex_b200.engine import Engine
+    cfg, sd = state_dict_for("TFM", 1.5, 4.0)
+    e = Engine(cfg, "cuda:0", precision=precision)
+    e.load_state_dict(sd)
+    ctx, _, _ = e.encode(synth.make_images(7, 64, 256, seed=123).cuda())
+    out = {}
+    for staged in (0, 1):
+        e.set_option("attn_staged", staged)
+        e.set_option("attn_cap", cap)
+        ids, lg, st = e.decode_greedy(ctx, max_steps=70, is_test=False)
+        beam = e.decode_beam(ctx, 5, max_steps=70, trace=True)
+        beam3 = e.decode_beam(ctx, 3, max_steps=70)
+        out[staged] = (ids.cpu(), lg.cpu(), [x.cpu() for x in beam[:3]], beam[4].cpu(), [x.cpu() for x in beam3[:3]])
+    e.close()
+    a, b = out[0], out[1]
+    same = (a[0] == b[0]).cumprod(dim=1).bool()
+    first = torch.ones_like(same)
+    first[:, 1:] = same[:, :-1]
+    err = ((a[1] - b[1]).abs().amax(dim=2) / a[1].abs().amax(dim=2).clamp_min(1e-6))[first]
+    assert float(err.max()) < (1e-4 if precision == "bf16x3" else 2e-2), float(err.max())
+    if precision == "bf16x3":
+        assert torch.equal(a[0], b[0])
+        assert torch.equal(a[2][0], b[2][0]) and torch.equal(a[2][1], b[2][1]) and torch.equal(a[3], b[3])
+        assert float((a[2][2] - b[2][2]).abs().max()) <= 1e-4 * float(a[2][2].abs().max())
+        assert torch.equal(a[4][0], b[4][0]) and torch.equal(a[4][1], b[4][1])
 
 
 @pytest.mark.parametrize("spg", [1, 3, 16])

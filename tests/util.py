@@ -49,16 +49,18 @@ def golden_images(g, n, H=64, W=256):
 
 # A beam decision whose candidates are separated by fewer than this many fp32 ulps of the cumulative score is a NEAR-TIE:
 # any other fp32 summation order may legitimately flip it.  Decisions with a wider margin must be identical.
-NEAR_TIE_ULPS = 16.0
+NEAR_TIE_ULPS = 32.0
 
 
-def decision_margins_ulp(trace, trace_score, runner_up):
-    """Margin of every beam decision in fp32 ulps.  trace (B,T,k,2) int (-1 = unused), trace_score (B,T,k) fp32 in top-k
-    order, runner_up (B,T) fp32 = best candidate NOT selected (-inf when there is none).  Returns (B,T) float64 with +inf
-    where no decision was taken (image finished)."""
+def decision_margins(trace, trace_score, runner_up):
+    """Margin of every beam decision: the smallest gap between neighbours among the k selected candidates and the best one
+    left out.  trace (B,T,k,2) int (-1 = unused), trace_score (B,T,k) fp32 in top-k order, runner_up (B,T) fp32 = best
+    candidate NOT selected (-inf when there is none).  Returns (gap, ulp): two (B,T) float64 arrays — the absolute gap
+    (+inf where no decision was taken: image finished / a single candidate) and the fp32 spacing at the scores' magnitude."""
     tr = np.asarray(trace); ts = np.asarray(trace_score, dtype=np.float64); ru = np.asarray(runner_up, dtype=np.float64)
     B, T, K = ts.shape
-    out = np.full((B, T), np.inf)
+    gap = np.full((B, T), np.inf)
+    ulp = np.full((B, T), 1.0)
     for b in range(B):
         for t in range(T):
             k = int((tr[b, t, :, 0] >= 0).sum())
@@ -70,6 +72,6 @@ def decision_margins_ulp(trace, trace_score, runner_up):
             if len(vals) < 2:
                 continue
             v = np.array(vals)
-            ulp = float(np.spacing(np.float32(np.abs(v).max())))
-            out[b, t] = float((v[:-1] - v[1:]).min()) / ulp
-    return out
+            ulp[b, t] = float(np.spacing(np.float32(np.abs(v).max())))
+            gap[b, t] = float((v[:-1] - v[1:]).min())
+    return gap, ulp
