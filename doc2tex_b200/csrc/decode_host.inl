@@ -83,20 +83,23 @@ int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long 
   cudaError_t st;
   // Staged kernel (default): one block per (image, head) stages every K / V record it needs into shared memory in one
   // cp.async round trip — before the dependency wait where the data allows — and computes out of shared memory.
-  if (e->attn_staged && R % rows_per_src == 0 && rows_per_src <= 16 && D == heads * 32) {
+  // (beam search by default: there the hypotheses of an image share most records and the per-row walk re-fetches them G times;
+  // attn_staged = 2 also routes the greedy rows here, measured slower: one warp per 41 KB of shared memory idles the SM)
+  if (e->attn_staged && (rows_per_src > 1 || e->attn_staged >= 2) && R % rows_per_src == 0 && rows_per_src <= 16 && D == heads * 32) {
     const int G = rows_per_src, B = R / G;
-    const int n_max = n_fixed > 0 ? n_fixed : anc_ld > 0 ? anc_ld : 0;   // self-attention: at most max_steps positions
+    // self-attention: at most max_steps positions; with attn_fit the step graph being captured knows its last step
+    const int n_max = n_fixed > 0 ? n_fixed : (e->attn_fit && e->attn_n_hint > 0) ? e->attn_n_hint : anc_ld > 0 ? anc_ld : 0;
     int cap = e->attn_cap;
     if (cap <= 0) {
       // one round whenever possible: every position once, plus (beam) the diverged tails of the G hypotheses
-      const int want = n_fixed > 0 ? n_fixed : (anc ? n_max + 64 : n_max);
+      const int want = n_fixed > 0 ? n_fixed : (anc ? n_max + 48 : n_max);
       cap = ((want + 7) / 8) * 8;
     }
     if (cap > 32 * STAGED_MAX_PASS) cap = 32 * STAGED_MAX_PASS;
     if (cap < 32) cap = 32;
     if (n_max > 0) {
       const size_t rec = kv16 ? StagedRec<__nv_bfloat16>::BYTES : StagedRec<float>::BYTES;
-      const size_t smem = (size_t)cap * rec + (anc ? (size_t)G * anc_ld * 4 : 0) + 16 + (size_t)G * 128;
+      const size_t smem = (size_t)cap * rec + (anc ? (size_t)G * anc_ld * 4 : 0) + 16;
       if (smem <= 200 * 1024) {
         static bool attr_f = false, attr_h = false;
         if (kv16) {
@@ -616,8 +619,13 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
   // ---- step graphs: `spg` consecutive steps per graph (the step index lives on the device, so one graph serves every
   // step), plus a one-step graph for the tail ----
   const int spg = e->steps_per_graph < 1 ? 1 : e->steps_per_graph;
-  auto get_graph = [&](int n_steps, cudaGraphExec_t* exec_out, int* nodes_out) -> int {
-    std::vector<long long> key = {(long long)B, G, ntok, beam, T, want_logits ? 1 : 0, n_steps};
+  // attn_fit: the staged beam attention sizes its shared memory for the last step of the graph it is captured into, so
+  // every block of `spg` steps gets its own graph (19 for 151 steps) and early steps run more blocks per SM
+  const bool fit = e->attn_fit && e->attn_staged && beam > 0;
+  auto get_graph = [&](int n_steps, int first_step, cudaGraphExec_t* exec_out, int* nodes_out) -> int {
+    const int hint = fit ? std::min(T, first_step + n_steps) : 0;
+    e->attn_n_hint = hint;
+    std::vector<long long> key = {(long long)B, G, ntok, beam, T, want_logits ? 1 : 0, n_steps, hint};
     for (const TfmGroup& grp : groups) {
       const TfmBuffers& b = grp.b;
       const void* ptrs[] = {b.crosskv, b.selfkv, b.x, b.x2, b.q, b.att, b.ffn, b.logits, b.counters, b.tokens, b.anc,
@@ -641,7 +649,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     st = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(st));
-    if (e->graphs.size() >= 16) {  // bounded cache
+    if (e->graphs.size() >= 128) {  // bounded cache
       cudaGraphExecDestroy(e->graphs.front().exec);
       e->graphs.erase(e->graphs.begin());
     }
@@ -650,12 +658,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     *exec_out = exec; *nodes_out = nodes;
     return 0;
   };
-  cudaGraphExec_t exec_n = nullptr, exec_1 = nullptr;
-  int nodes_n = 0, nodes_1 = 0;
-  if (c.use_graphs && !e->time_decode) {
-    if (spg > 1 && T >= spg && (rc = get_graph(spg, &exec_n, &nodes_n))) return rc;
-    if ((spg == 1 || T % spg != 0 || T < spg) && (rc = get_graph(1, &exec_1, &nodes_1))) return rc;
-  }
+  const bool use_graphs = c.use_graphs && !e->time_decode;
   // the reference stops when EVERY row / image of the batch is done: all groups done, at the latest group's step
   auto all_done_step = [&]() -> int {
     int last = 0;
@@ -675,15 +678,16 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
   bool poll_pending = false;
   while (executed < T) {
     int did = 1;
-    if (exec_n && T - executed >= spg) {
-      CUDA_TRY(e, cudaGraphLaunch(exec_n, s));
-      e->launches += nodes_n;
-      did = spg;
-    } else if (exec_1) {
-      CUDA_TRY(e, cudaGraphLaunch(exec_1, s));
-      e->launches += nodes_1;
+    if (use_graphs) {
+      did = (spg > 1 && T - executed >= spg) ? spg : 1;
+      cudaGraphExec_t exec = nullptr;
+      int nodes = 0;
+      if ((rc = get_graph(did, executed, &exec, &nodes))) return rc;   // cached after the first decode of this shape
+      CUDA_TRY(e, cudaGraphLaunch(exec, s));
+      e->launches += nodes;
     } else {
       e->cur_step = executed;
+      e->attn_n_hint = fit ? executed + 1 : 0;
       if ((rc = enqueue_step())) return rc;
     }
     const int before = executed;

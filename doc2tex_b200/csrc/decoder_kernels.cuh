@@ -288,35 +288,41 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// 32-dim dot product of the query (shared memory, broadcast reads) with one staged K head slice
-__device__ __forceinline__ float staged_dot(const float* __restrict__ sq, const uint8_t* __restrict__ rec, float) {
-  float d = 0.f;
+// 32-dim dot product of the (pre-scaled) query held in registers with one staged K head slice
+__device__ __forceinline__ float staged_dot(const float (&qv)[32], const uint8_t* __restrict__ rec, float) {
+  float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-  for (int u = 0; u < 8; ++u) {
-    const float4 k = *reinterpret_cast<const float4*>(rec + 16 * u);
-    const float4 qq = *reinterpret_cast<const float4*>(sq + 4 * u);
-    d = fmaf(qq.x, k.x, fmaf(qq.y, k.y, fmaf(qq.z, k.z, fmaf(qq.w, k.w, d))));
+  for (int u = 0; u < 8; u += 2) {
+    const float4 k0 = *reinterpret_cast<const float4*>(rec + 16 * u);
+    const float4 k1 = *reinterpret_cast<const float4*>(rec + 16 * u + 16);
+    d0 = fmaf(qv[4 * u], k0.x, fmaf(qv[4 * u + 1], k0.y, fmaf(qv[4 * u + 2], k0.z, fmaf(qv[4 * u + 3], k0.w, d0))));
+    d1 = fmaf(qv[4 * u + 4], k1.x, fmaf(qv[4 * u + 5], k1.y, fmaf(qv[4 * u + 6], k1.z, fmaf(qv[4 * u + 7], k1.w, d1))));
   }
-  return d;
+  return d0 + d1;
 }
-__device__ __forceinline__ float staged_dot(const float* __restrict__ sq, const uint8_t* __restrict__ rec, __nv_bfloat16) {
-  float d = 0.f;
+__device__ __forceinline__ float staged_dot(const float (&qv)[32], const uint8_t* __restrict__ rec, __nv_bfloat16) {
+  float d0 = 0.f, d1 = 0.f;
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const uint4 raw = *reinterpret_cast<const uint4*>(rec + 16 * u);
-    const float4 q0 = *reinterpret_cast<const float4*>(sq + 8 * u), q1 = *reinterpret_cast<const float4*>(sq + 8 * u + 4);
     const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
     const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
     const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.z));
     const float2 e = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.w));
-    d = fmaf(q0.x, a.x, fmaf(q0.y, a.y, fmaf(q0.z, b.x, fmaf(q0.w, b.y, d))));
-    d = fmaf(q1.x, c.x, fmaf(q1.y, c.y, fmaf(q1.z, e.x, fmaf(q1.w, e.y, d))));
+    d0 = fmaf(qv[8 * u], a.x, fmaf(qv[8 * u + 1], a.y, fmaf(qv[8 * u + 2], b.x, fmaf(qv[8 * u + 3], b.y, d0))));
+    d1 = fmaf(qv[8 * u + 4], c.x, fmaf(qv[8 * u + 5], c.y, fmaf(qv[8 * u + 6], e.x, fmaf(qv[8 * u + 7], e.y, d1))));
   }
-  return d;
+  return d0 + d1;
 }
-__device__ __forceinline__ float staged_v(const uint8_t* rec_v, int lane, float) { return reinterpret_cast<const float*>(rec_v)[lane]; }
-__device__ __forceinline__ float staged_v(const uint8_t* rec_v, int lane, __nv_bfloat16) {
-  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(rec_v)[lane]);
+// four consecutive V channels of one staged record
+__device__ __forceinline__ float4 staged_v4(const uint8_t* rec_v, int c4, float) {
+  return *reinterpret_cast<const float4*>(rec_v + 4 * c4);
+}
+__device__ __forceinline__ float4 staged_v4(const uint8_t* rec_v, int c4, __nv_bfloat16) {
+  const uint2 u = *reinterpret_cast<const uint2*>(rec_v + 2 * c4);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
+  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
 }
 
 constexpr int STAGED_MAX_PASS = 8;   // 32-key passes per round: cap <= 256 records per hypothesis and round
@@ -331,7 +337,6 @@ decode_attention_staged_kernel(const float* __restrict__ q, int ldq, const KV* _
   extern __shared__ __align__(16) uint8_t staged_smem[];
   uint8_t* const s_rec = staged_smem;
   int* const s_anc = reinterpret_cast<int*>(staged_smem + (size_t)cap * R::BYTES);
-  float* const s_q = reinterpret_cast<float*>(staged_smem + (((size_t)cap * R::BYTES + (anc ? (size_t)G * anc_ld * 4 : 0) + 15) & ~(size_t)15));
   __shared__ int s_common;
   const uint32_t s_rec_addr = (uint32_t)__cvta_generic_to_shared(s_rec);
 
@@ -347,67 +352,80 @@ decode_attention_staged_kernel(const float* __restrict__ q, int ldq, const KV* _
   if (anc) {
     const int* a0 = anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)img * G * anc_ld;
     if (threadIdx.x == 0) s_common = n;
-    for (int i = threadIdx.x; i < G * n; i += nthr) {
-      const int b = i / n, j = i - b * n;
-      s_anc[b * anc_ld + j] = a0[(size_t)b * anc_ld + j];
-    }
+    for (int j = lane; j < n; j += 32) s_anc[wid * anc_ld + j] = a0[(size_t)wid * anc_ld + j];   // warp = hypothesis
     __syncthreads();
-    for (int j = threadIdx.x; j < n; j += nthr) {
+    int first_diff = n;
+    for (int j = n - 1 - (int)threadIdx.x; j >= 0; j -= nthr) {   // the ancestry rows differ at the END of the prefix
       const int a = s_anc[j];
       bool same = true;
       for (int b = 1; b < G; ++b) same = same && (s_anc[b * anc_ld + j] == a);
-      if (!same) atomicMin(&s_common, j);
+      if (!same) first_diff = j;
     }
+    if (first_diff < n) atomicMin(&s_common, first_diff);
     __syncthreads();
     c = s_common;
   }
   const KV* const kvh = kv + h * R::HD;
-  // records of positions [p0, p1): the common part first (one record per position), then G records per position
-  auto stage = [&](int p0, int p1, int j_lo, int j_hi) {   // stages positions [j_lo, j_hi) of the round [p0, p1)
-    const int ns = max(0, min(p1, c) - p0);                // common records of this round
-    const int pc = max(p0, c);                             // first per-hypothesis position
-    const int piece = threadIdx.x % R::PIECES;
-    const int ja = max(j_lo, p0), jb = min(j_hi, p1);      // positions [ja, jb)
-    const int first = ja < c ? ja - p0 : ns + (ja - pc) * G;
-    const int last = jb <= c ? jb - p0 : ns + (jb - pc) * G;
+  const int piece = threadIdx.x % R::PIECES;
+  const int piece_off = piece < R::PIECES / 2 ? piece * R::EL_PER_PIECE : D + (piece - R::PIECES / 2) * R::EL_PER_PIECE;
+  const int tgrp = threadIdx.x / R::PIECES, ngrp = nthr / R::PIECES;   // record slots staged per sweep of the block
+  // Records of the round [p0, p1): positions < c once (index j - p0), then G records per position (ns + (j - pc) * G + b).
+  // stage() copies the records of positions [ja, jb) of that round, one 16-byte piece per thread and record.
+  auto stage = [&](int p0, int p1, int ja, int jb) {
+    ja = max(ja, p0); jb = min(jb, p1);
     if (ja >= jb) return;
-    for (int rec = first + threadIdx.x / R::PIECES; rec < last; rec += nthr / R::PIECES) {
-      int j, slot;
-      if (rec < ns) { j = p0 + rec; slot = anc ? s_anc[j] : 0; }
-      else { const int e = rec - ns; j = pc + e / G; const int b = e - (e / G) * G; slot = s_anc[b * anc_ld + j]; }
-      const KV* src = kvh + (size_t)(src0 + slot) * row_stride + (size_t)j * pos_stride +
-                      (piece < R::PIECES / 2 ? piece * R::EL_PER_PIECE : D + (piece - R::PIECES / 2) * R::EL_PER_PIECE);
-      cp_async16(s_rec_addr + (uint32_t)rec * R::BYTES + (uint32_t)piece * 16u, src);
+    const int ns = max(0, min(p1, c) - p0), pc = max(p0, c);
+    for (int j = ja + tgrp; j < min(jb, c); j += ngrp) {                       // common part
+      const KV* src = kvh + (size_t)(src0 + (anc ? s_anc[j] : 0)) * row_stride + (size_t)j * pos_stride + piece_off;
+      cp_async16(s_rec_addr + (uint32_t)(j - p0) * R::BYTES + (uint32_t)piece * 16u, src);
+    }
+    if (jb > c) {                                                               // per-hypothesis tail (beam search only)
+      const int b = tgrp % G, jsub = tgrp / G, jstep = max(1, ngrp / G);       // ngrp = 2 G (fp32) or 4 G (bf16) record slots
+      if (jsub < jstep) {
+        for (int j = max(ja, pc) + jsub; j < jb; j += jstep) {
+          const KV* src = kvh + (size_t)(src0 + s_anc[b * anc_ld + j]) * row_stride + (size_t)j * pos_stride + piece_off;
+          cp_async16(s_rec_addr + (uint32_t)(ns + (j - pc) * G + b) * R::BYTES + (uint32_t)piece * 16u, src);
+        }
+      }
     }
   };
-  // first round boundaries: as many positions as fit into `cap` records
-  auto round_end = [&](int p0) {
+  auto round_end = [&](int p0) {   // as many positions as fit into `cap` records
     const int common_left = max(0, c - p0);
     if (common_left >= cap) return p0 + cap;
-    const int tail = (cap - common_left) / G;            // per-hypothesis positions that still fit
-    return min(n, max(p0, c) + tail);
+    return min(n, max(p0, c) + (cap - common_left) / G);
   };
   int p0 = 0, p1 = round_end(0);
   stage(p0, p1, 0, self ? min(p1, t) : p1);              // everything but the current position of the self-attention
   pdl_wait();
   pdl_trigger();
   if (self && t < p1) stage(p0, p1, t, t + 1);           // K / V of the current position: written by the preceding projection
-  s_q[wid * 32 + lane] = q[(size_t)r * ldq + h * R::HD + lane] * rsqrtf((float)R::HD);
+  float qv[32];                                           // the whole (row, head) query in every lane: broadcast loads
+  {
+    const float4* qp = reinterpret_cast<const float4*>(q + (size_t)r * ldq + h * R::HD);
+    const float scale = rsqrtf((float)R::HD);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float4 v = __ldg(qp + u);
+      qv[4 * u] = v.x * scale; qv[4 * u + 1] = v.y * scale; qv[4 * u + 2] = v.z * scale; qv[4 * u + 3] = v.w * scale;
+    }
+  }
   cp_async_wait_all();
   __syncthreads();
 
-  float M = -INFINITY, L = 0.f, acc = 0.f;               // online softmax state across rounds; lane = output channel
-  const float* const sq = s_q + wid * 32;
+  const int g = lane >> 3, c4 = (lane & 7) * 4;          // value pass: quarter warp g takes key 4 i + g, lane owns 4 channels
+  float M = -INFINITY, L = 0.f;                          // online softmax state across rounds
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (;;) {
     const int ns = max(0, min(p1, c) - p0), pc = max(p0, c);
-    auto rec_of = [&](int j) { return j < c ? j - p0 : ns + (j - pc) * G + (anc ? wid : 0); };
+    const int tail_off = ns - pc * G + (anc ? wid : 0);
+    auto rec_of = [&](int j) { return j < c ? j - p0 : j * G + tail_off; };
     float sc[STAGED_MAX_PASS];
     float m_r = -INFINITY;
 #pragma unroll
     for (int ps = 0; ps < STAGED_MAX_PASS; ++ps) {
       const int j = p0 + ps * 32 + lane;
       sc[ps] = -INFINITY;
-      if (p0 + ps * 32 < p1 && j < p1) sc[ps] = staged_dot(sq, s_rec + (size_t)rec_of(j) * R::BYTES, KV());
+      if (j < p1) sc[ps] = staged_dot(qv, s_rec + (size_t)rec_of(j) * R::BYTES, KV());
       m_r = fmaxf(m_r, sc[ps]);
     }
     m_r = warp_max(m_r);
@@ -421,29 +439,21 @@ decode_attention_staged_kernel(const float* __restrict__ q, int ldq, const KV* _
     }
     l_r = warp_sum(l_r);
     L = L * corr + l_r;
-    acc *= corr;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;        // four independent chains over the keys
+    acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
 #pragma unroll
     for (int ps = 0; ps < STAGED_MAX_PASS; ++ps) {
       const int jb = p0 + ps * 32;
       if (jb < p1) {
         const int cnt = min(32, p1 - jb);
-        int jj = 0;
-        for (; jj + 4 <= cnt; jj += 4) {
-          const float w0 = __shfl_sync(0xffffffffu, sc[ps], jj), w1 = __shfl_sync(0xffffffffu, sc[ps], jj + 1);
-          const float w2 = __shfl_sync(0xffffffffu, sc[ps], jj + 2), w3 = __shfl_sync(0xffffffffu, sc[ps], jj + 3);
-          a0 = fmaf(w0, staged_v(s_rec + (size_t)rec_of(jb + jj) * R::BYTES + R::HALF_BYTES, lane, KV()), a0);
-          a1 = fmaf(w1, staged_v(s_rec + (size_t)rec_of(jb + jj + 1) * R::BYTES + R::HALF_BYTES, lane, KV()), a1);
-          a2 = fmaf(w2, staged_v(s_rec + (size_t)rec_of(jb + jj + 2) * R::BYTES + R::HALF_BYTES, lane, KV()), a2);
-          a3 = fmaf(w3, staged_v(s_rec + (size_t)rec_of(jb + jj + 3) * R::BYTES + R::HALF_BYTES, lane, KV()), a3);
-        }
-        for (; jj < cnt; ++jj) {
-          const float w0 = __shfl_sync(0xffffffffu, sc[ps], jj);
-          a0 = fmaf(w0, staged_v(s_rec + (size_t)rec_of(jb + jj) * R::BYTES + R::HALF_BYTES, lane, KV()), a0);
+        for (int i = 0; i < cnt; i += 4) {              // 4 keys per warp instruction, 16-byte value reads
+          const float w = __shfl_sync(0xffffffffu, sc[ps], i + g);
+          if (i + g < cnt) {
+            const float4 v = staged_v4(s_rec + (size_t)rec_of(jb + i + g) * R::BYTES + R::HALF_BYTES, c4, KV());
+            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
+          }
         }
       }
     }
-    acc += (a0 + a1) + (a2 + a3);
     M = Mn;
     if (p1 >= n) break;
     // next round (only when the records did not fit): restage after everybody is done with the buffer
@@ -454,15 +464,14 @@ decode_attention_staged_kernel(const float* __restrict__ q, int ldq, const KV* _
     cp_async_wait_all();
     __syncthreads();
   }
-  const float o = acc / L;
-  const size_t off = (size_t)r * D + h * R::HD + lane;
-  out[off] = o;
-  if (out_hi) {
-    __nv_bfloat16 hi, lo;
-    split_bf16(o, hi, lo);
-    out_hi[off] = hi;
-    if (out_lo) out_lo[off] = lo;
+#pragma unroll
+  for (int o = 8; o < 32; o <<= 1) {
+    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
+    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
   }
+  if (g == 0) attention_store(acc, L, (size_t)r * D + h * R::HD + c4, out, out_hi, out_lo);
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {

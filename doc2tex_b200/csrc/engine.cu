@@ -123,7 +123,10 @@ struct d2t_engine {
   int split_k = 1;       // option "split_k": 0 = never, 1 = auto split-K of the LayerNorm-fed decode projections
   bool attn_image_block = true;   // option "attn_image_block": beam search — one block owns all hypotheses of an image, so the
                                   // records they share (encoder memory, common prefixes) are served by that SM's L1
-  bool attn_staged = true;  // option "attn_staged": decode attention stages all K / V records of a block in shared memory (cp.async)
+  int attn_staged = 1;      // option "attn_staged": 1 = beam-search attention stages all K / V records of an (image, head) block in
+                            // shared memory (cp.async), 2 = greedy rows too, 0 = off
+  bool attn_fit = true;     // option "attn_fit": one step graph per block of steps, shared memory sized for its last step
+  int attn_n_hint = 0;      // largest number of self-attention positions of the steps being enqueued (attn_fit)
   int attn_cap = 0;         // option "attn_cap": records per staging round of that kernel (0 = auto, <= 256)
   int attn_split = 0;       // option "attn_split": warps per (row, head) of the per-row decode attention (0 = auto)
   bool stack_mma = true;    // option "stack_mma": bf16x3 decode projections issue 2 MMAs per k-step against [W_hi ; W_lo]
@@ -813,7 +816,9 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
   } else if (k == "attn_image_block") {
     e->attn_image_block = value != 0;
   } else if (k == "attn_staged") {
-    e->attn_staged = value != 0;
+    e->attn_staged = value;
+  } else if (k == "attn_fit") {
+    e->attn_fit = value != 0;
   } else if (k == "attn_cap") {
     e->attn_cap = value;
   } else if (k == "attn_split") {

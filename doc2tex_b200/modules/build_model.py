@@ -11,7 +11,11 @@ Appendix C, so reference checkpoints load with ``strict=True``), and the same ca
         -> (prediction, logits, decoder_attn, addition_outputs)        # :45-53
 
 Differences, all on purpose:
-  * inference only — ``is_train=True`` raises (the reference trains through the same class);
+  * inference only — ``train(True)`` raises (the reference trains through the same class).  ``is_train`` follows the
+    reference: the TFM head never looks at it (PredictBuilder drops it, build_pred.py:46-49; tfm.py:188-195 branches on
+    ``self.training``), so ``model(image, text)`` with the default ``is_train=True`` — the call of the batched evaluation
+    loop, engine/inferencing.py:151-153 — decodes greedily in eval mode; the LSTM heads use it for teacher forcing only
+    (seq2seq_v2.py:276), which is training and raises here;
   * the arithmetic runs in hand-written sm_100a kernels behind the C ABI; there is no PyTorch
     or CPU fallback (a missing library / non-CUDA device raises);
   * beam search accepts B > 1 for both heads (the reference asserts B == 1, tfm.py:146-148 and
@@ -109,8 +113,10 @@ class Model(nn.Module):
         return ctx, grid, pad
 
     def forward_decoder(self, contextual_feature, text, is_train=True, is_test=False, rtl_text=None):
-        if is_train:
-            raise EngineError("is_train=True is not supported by the inference engine")
+        if is_train and self.stages["Pred"] != "TFM":
+            # Attn / Attnv2: is_train=True = teacher forcing on the ground-truth text (seq2seq_v2.py:276) — a training path
+            raise EngineError("is_train=True (teacher forcing) of the LSTM heads is training; the inference engine decodes "
+                              "with is_train=False as engine/inferencing.py:73-76 does")
         eng = self.engine
         beam_size = self.opt.get("beam_size", 1)
         addition_outputs = {}

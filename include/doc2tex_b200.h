@@ -161,8 +161,10 @@ int d2t_decode_attn_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, i
  *   "decode_groups"    concurrent row groups of one decode call (parallel graph branches; 0/1 = one chain, default)
  *   "split_k"          0 = never, 1 = auto split-K of the LayerNorm-fed decode projections (default 1)
  *   "stack_mma"        0/1 bf16x3 decode projections: two MMAs per k-step against the stacked [W_hi ; W_lo] operand (default 1)
- *   "attn_staged"      0/1 decode attention: one block per (image, head) stages every K / V record it needs in shared memory with
- *                      cp.async (before the dependency wait where the data allows) and computes out of shared memory (default 1)
+ *   "attn_staged"      beam-search decode attention: one block per (image, head) stages every K / V record its hypotheses need in
+ *                      shared memory with cp.async (shared prefixes once; before the dependency wait where the data allows) and
+ *                      computes out of shared memory: 1 = beam search only (default), 2 = greedy rows too, 0 = off
+ *   "attn_fit"         0/1 one CUDA graph per block of steps so that kernel sizes its shared memory for that block's last step (default 1)
  *   "attn_cap"         records per staging round of that kernel (0 = auto; at most 256)
  *   "attn_image_block" 0/1 (attn_staged = 0) beam search: one attention block owns all hypotheses of an image (L1 serves shared records; default 1)
  *   "attn_split"       warps per (row, head) of the decode attention: 0 = auto, 1, 2

@@ -66,12 +66,17 @@ def margins(logits):
     return (top2[..., 0] - top2[..., 1])
 
 
-def tfm_case(name, H, W, B, end_bias, beam_imgs):
+def margin_ulp(mg):
+    """Smallest decision margin of one beam run in fp32 ulps of the cumulative score (oracle_model.topk_margin per step)."""
+    return min((g / u if u > 0 else 1e9) for g, u in mg) if mg else 1e9
+
+
+def tfm_case(name, H, W, B, end_bias, beam_imgs, sharpen=1.0):
     cfg = synth.make_config("TFM")
-    sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias)
+    sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias, sharpen=sharpen)
     img = synth.make_images(B, H, W, seed=2024)
     m = ref_model(cfg, sd)
-    out = {"end_bias": np.array(np.nan if end_bias is None else end_bias)}
+    out = {"end_bias": np.array(np.nan if end_bias is None else end_bias), "sharpen": np.array(sharpen)}
     with torch.no_grad():
         ctx_ref, shape, pad = m.forward_encoder(img)
         taps = {}
@@ -106,16 +111,17 @@ def tfm_case(name, H, W, B, end_bias, beam_imgs):
         out["greedy_logits"] = logits_ref[:, steps, :].numpy()
         out["greedy_margin"] = margins(logits_ref).numpy()
 
-        seqs, scores, traces = [], [], []
+        seqs, scores, traces, mulp = [], [], [], []
         for i in range(beam_imgs):
             s_ref, sc_ref = ref_beam(m, ctx_ref[i:i + 1], 5, 150)
-            tr = []
-            s_or, sc_or = head.beam(ctx_or[i:i + 1], 5, trace=tr)
+            tr, mg = [], []
+            s_or, sc_or = head.beam(ctx_or[i:i + 1], 5, trace=tr, margins=mg)
             assert s_ref == s_or, f"beam seq differs for image {i}"
             assert abs(sc_ref - sc_or) <= 1e-3 * max(1.0, abs(sc_ref)), (sc_ref, sc_or)
-            print(f"[{name}] beam img {i}: len {len(s_ref)} score {sc_ref:.4f} steps {len(tr)}")
-            seqs.append(s_ref); scores.append(sc_ref); traces.append(tr)
+            print(f"[{name}] beam img {i}: len {len(s_ref)} score {sc_ref:.4f} steps {len(tr)} min decision margin {margin_ulp(mg):.1f} ulp")
+            seqs.append(s_ref); scores.append(sc_ref); traces.append(tr); mulp.append(margin_ulp(mg))
         if beam_imgs:
+            out["beam_margin_ulp"] = np.array(mulp)
             L = max(len(s) for s in seqs)
             out["beam_seq"] = np.array([s + [-1] * (L - len(s)) for s in seqs])
             out["beam_len"] = np.array([len(s) for s in seqs])
@@ -152,29 +158,47 @@ def attn_case(name, H, W, B, end_bias, head="Attnv2"):
                         margin=margins(probs_ref).numpy())
 
 
-def attn_beam_case(name, H, W, B, end_bias, beam=5, head="Attnv2"):
-    """AttentionV2.forward_beam of the live reference, one image at a time (it asserts batch 1, seq2seq_v2.py:18-19)."""
+def pick_seeds(sd, head, n, H, W, beam, min_ulp, first_seed=2024, tries=200):
+    """Image seeds whose whole beam run clears `min_ulp` (oracle audit): no decision of the REFERENCE is a near-tie, so an
+    engine must reproduce the trace exactly (choose fixture seeds whose minimum margin clears epsilon)."""
+    head_or = om.AttnV2Head(sd, include_cls=(head == "Attn"))
+    seeds = []
+    for seed in range(first_seed, first_seed + tries):
+        ctx, _, _ = om.encoder_forward(sd, synth.make_images(1, H, W, seed=seed))
+        mg = []
+        head_or.beam(ctx, beam, 150, margins=mg)
+        if margin_ulp(mg) >= min_ulp:
+            seeds.append(seed)
+            if len(seeds) == n:
+                return seeds
+    raise RuntimeError(f"only {len(seeds)} of {n} seeds clear {min_ulp} ulp in {tries} tries")
+
+
+def attn_beam_case(name, H, W, B, end_bias, beam=5, head="Attnv2", sharpen=1.0, min_ulp=None):
+    """AttentionV2.forward_beam of the live reference, one image at a time (it asserts batch 1, seq2seq_v2.py:18-19).
+    min_ulp: pick the image seeds so that every beam decision of the reference clears that margin."""
     cfg = synth.make_config(head)
-    sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias)
-    img = synth.make_images(B, H, W, seed=2024)
+    sd = synth.make_state_dict(cfg, seed=1111, end_bias=end_bias, sharpen=sharpen)
+    seeds = list(range(2024, 2024 + B)) if min_ulp is None else pick_seeds(sd, head, B, H, W, beam, min_ulp)
+    img = torch.cat([synth.make_images(1, H, W, seed=s_) for s_ in seeds], 0)
     m = ref_model(cfg, sd)
     head_ref = m.predicter.Prediction
     head_or = om.AttnV2Head(sd, include_cls=(head == "Attn"))
-    seqs, scores, traces = [], [], []
+    seqs, scores, traces, mulp = [], [], [], []
     with torch.no_grad():
         ctx_ref, _, _ = m.forward_encoder(img)
         ctx_or, _, _ = om.encoder_forward(sd, img)
         for i in range(B):
             seq_ref, sc_ref, _ = head_ref.forward_beam(ctx_ref[i:i + 1], batch_max_length=150, beam_size=beam)
             s_ref = seq_ref[0].tolist()
-            tr = []
-            s_or, sc_or = head_or.beam(ctx_or[i:i + 1], beam, 150, trace=tr)
+            tr, mg = [], []
+            s_or, sc_or = head_or.beam(ctx_or[i:i + 1], beam, 150, trace=tr, margins=mg)
             assert s_ref == s_or, f"attn beam seq differs for image {i}: {s_ref[:12]} vs {s_or[:12]}"
             assert abs(float(sc_ref) - sc_or) <= 1e-3 * max(1.0, abs(float(sc_ref))), (float(sc_ref), sc_or)
             live = [len(t[0]) for t in tr]
-            print(f"[{name}] attn beam img {i}: len {len(s_ref)} score {float(sc_ref):.4f} steps {len(tr)} "
-                  f"live rows per step (first 12) {live[:12]} ... last {live[-1]}")
-            seqs.append(s_ref); scores.append(float(sc_ref)); traces.append(tr)
+            print(f"[{name}] attn beam img {i} (seed {seeds[i]}): len {len(s_ref)} score {float(sc_ref):.4f} steps {len(tr)} "
+                  f"min decision margin {margin_ulp(mg):.1f} ulp; live rows per step (first 12) {live[:12]} ... last {live[-1]}")
+            seqs.append(s_ref); scores.append(float(sc_ref)); traces.append(tr); mulp.append(margin_ulp(mg))
     L = max(len(s) for s in seqs)
     T = max(len(t) for t in traces)
     par = np.full((B, T, beam), -1, dtype=np.int64)
@@ -184,7 +208,8 @@ def attn_beam_case(name, H, W, B, end_bias, beam=5, head="Attnv2"):
         for st, (p_, w_, sc_) in enumerate(t):
             par[i, st, :len(p_)] = p_; wrd[i, st, :len(w_)] = w_; sco[i, st, :len(sc_)] = sc_
     np.savez_compressed(os.path.join(GOLD, name + ".npz"),
-                        end_bias=np.array(np.nan if end_bias is None else end_bias),
+                        end_bias=np.array(np.nan if end_bias is None else end_bias), sharpen=np.array(sharpen),
+                        img_seeds=np.array(seeds), beam_margin_ulp=np.array(mulp),
                         beam_seq=np.array([s_ + [-1] * (L - len(s_)) for s_ in seqs]),
                         beam_len=np.array([len(s_) for s_ in seqs]), beam_score=np.array(scores, dtype=np.float64),
                         beam_steps=np.array([len(t) for t in traces]),
@@ -222,6 +247,9 @@ def attn_base_cases():
     attn_case("attn_64x256_end", 64, 256, 2, 3.0, head="Attn")
     attn_beam_case("attn_beam_64x256_end04", 64, 256, 2, 0.4, head="Attn")
     attn_beam_case("attn_beam_64x256_end05", 64, 256, 2, 0.5, head="Attn")
+    # sharpened (trained-like, peaked) head: every decision of the reference clears 64 ulp -> 100 % of the traces must match
+    attn_beam_case("attn_beam_sharp_end70", 64, 256, 2, 7.0, head="Attn", sharpen=16.0, min_ulp=64)   # 151 steps, 3 live at the end
+    attn_beam_case("attn_beam_sharp_end75", 64, 256, 2, 7.5, head="Attn", sharpen=16.0, min_ulp=64)   # beams end after 24-60 steps
 
 
 def encoder_variant_cases():
@@ -235,17 +263,30 @@ def attn_beam_cases():
                                                                    # nothing -> live beam 0 beats the completed ones (Q11)
     attn_beam_case("attnv2_beam_64x256_end05", 64, 256, 3, 0.5)    # all five complete by step 10: best = fp32 score / len
     attn_beam_case("attnv2_beam_64x256_end30", 64, 256, 2, 3.0)    # everything completes within the first two steps
+    # The random-init LSTM head is nearly uniform and its hypotheses converge to the same state, so the cases above contain
+    # decisions the REFERENCE separates by 0-4 ulp (audit stored as beam_margin_ulp).  Sharpened (trained-like, peaked) head +
+    # image seeds picked by the oracle audit: every decision clears 64 ulp -> 100 % of the traces must match.
+    attn_beam_case("attnv2_beam_sharp_end70", 64, 256, 3, 7.0, sharpen=16.0, min_ulp=64)   # 151 steps, beam shrinks to 2-3, Q11 ending
+    attn_beam_case("attnv2_beam_sharp_end75", 64, 256, 3, 7.5, sharpen=16.0, min_ulp=64)   # beam shrinks 5,4,3,2,1; live beam 0 wins (Q11)
+    attn_beam_case("attnv2_beam_sharp_end80", 64, 256, 2, 8.0, sharpen=16.0, min_ulp=64)   # all five complete within 11 steps
 
 
 if __name__ == "__main__":
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
     print("torch", torch.__version__, "threads", torch.get_num_threads())
+    if len(sys.argv) > 1:   # python oracle/make_golden.py attn_beam_cases converter_case ...: only the named groups
+        for fn in sys.argv[1:]:
+            globals()[fn]()
+        sys.exit(0)
     tfm_case("tfm_64x256_natural", 64, 256, 2, None, 2)
     tfm_case("tfm_64x256_full", 64, 256, 2, -1e4, 2)       # END suppressed: full 151 steps
     tfm_case("tfm_64x256_end15", 64, 256, 2, 1.5, 2)       # 3 beams complete, 2 run out of steps
     tfm_case("tfm_64x256_end20", 64, 256, 2, 2.0, 2)       # all 5 beams complete by step 1
     tfm_case("tfm_96x384_full", 96, 384, 1, -1e4, 1)
+    # sharpened head: the 151-step 5-live beams clear >= 30 ulp at every decision (the plain random-init ones tie at 0-3 ulp)
+    tfm_case("tfm_64x256_sharp_full", 64, 256, 2, -1e4, 2, sharpen=8.0)
+    tfm_case("tfm_64x256_sharp_end10", 64, 256, 2, 10.0, 2, sharpen=8.0)
     attn_case("attnv2_64x256_natural", 64, 256, 2, None)
     attn_case("attnv2_64x256_full", 64, 256, 2, -1e4)
     attn_case("attnv2_64x256_end", 64, 256, 2, 3.0)

@@ -22,16 +22,23 @@ ap.add_argument("--height", type=int, default=64)
 ap.add_argument("--width", type=int, default=256)
 ap.add_argument("--warm", type=int, default=1)
 ap.add_argument("--graphs", action="store_true")
+ap.add_argument("--opt", action="append", default=[], help="engine option key=value (repeatable)")
+ap.add_argument("--images", type=int, default=0, help="decode this many images (ctx repeated) instead of --batch")
 a = ap.parse_args()
 
 cfg = synth.make_config("TFM")
 sd = synth.make_state_dict(cfg, seed=1111, suppress_end=True)
 eng = Engine(cfg, "cuda:0", precision=a.precision, use_graphs=a.graphs)
 eng.load_state_dict(sd)
+for kv in a.opt:
+    k, v = kv.split("=")
+    eng.set_option(k, int(v))
 img = synth.make_images(a.batch, a.height, a.width, seed=2024).cuda()
 for i in range(a.warm + 1):
     l0 = eng.launch_count()
     ctx, _, _ = eng.encode(img)
+    if a.images > 0:
+        ctx = ctx.repeat((a.images + a.batch - 1) // a.batch, 1, 1)[:a.images].contiguous()
     l1 = eng.launch_count()
     if a.mode == "greedy":
         eng.decode_greedy(ctx, a.steps, is_test=True, return_logits=False)
