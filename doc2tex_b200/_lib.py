@@ -17,7 +17,7 @@ SYMBOLS = [
     "d2t_create", "d2t_destroy", "d2t_last_error", "d2t_version", "d2t_load_tensor",
     "d2t_finalize_weights", "d2t_encode", "d2t_encoder_geometry", "d2t_decode_greedy",
     "d2t_decode_beam", "d2t_decode_attn_greedy", "d2t_decode_attn_beam", "d2t_set_option", "d2t_set_debug", "d2t_debug_tap",
-    "d2t_debug_gemm", "d2t_debug_gemm_bench", "d2t_debug_conv_time", "d2t_debug_decode_time", "d2t_debug_beam_runner_up", "d2t_launch_count",
+    "d2t_debug_gemm", "d2t_debug_gemm_bench", "d2t_debug_conv_time", "d2t_debug_decode_time", "d2t_debug_beam_runner_up", "d2t_launch_count", "d2t_prep_measure", "d2t_prep_render",
 ]
 
 PREC = {"fp32": 0, "tf32x3": 1, "bf16x3": 2, "bf16": 3}
@@ -29,6 +29,17 @@ class Config(C.Structure):
         "struct_size", "in_channels", "stem_channels", "hidden", "depth", "heads", "max_tokens",
         "head", "vocab", "dec_layers", "dec_heads", "dec_ff", "max_seq_len", "attn_hidden",
         "attn_kernel_dim", "attn_kernel_size", "precision", "use_graphs")]
+
+
+class PrepImage(C.Structure):
+    _fields_ = [("src_off", C.c_int64), ("h0", C.c_int32), ("w0", C.c_int32), ("ds", C.c_int32), ("pad_", C.c_int32)]
+
+
+class PrepPlan(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        "use_crop", "crop_x", "crop_y", "crop_w", "crop_h", "inverted", "vmin", "hb", "wb", "do_resize", "rh", "rw",
+        "kx_off", "kx_ksize", "ky_off", "ky_ksize", "out_h", "out_w")] + [
+        ("off_b", C.c_int64), ("off_t", C.c_int64), ("off_r", C.c_int64), ("dst", C.c_void_p)]
 
 
 _lib = None
@@ -66,6 +77,8 @@ def load():
     lib.d2t_debug_conv_time.argtypes = [vp, C.POINTER(C.c_double), i64p, C.POINTER(C.c_double)]
     lib.d2t_debug_decode_time.argtypes = [vp, i32, C.POINTER(C.c_double), i64p, C.POINTER(C.c_double)]
     lib.d2t_debug_beam_runner_up.argtypes = [vp, fp]
+    lib.d2t_prep_measure.argtypes = [vp, vp, vp, i32, vp, vp]
+    lib.d2t_prep_render.argtypes = [vp, vp, vp, vp, i32, vp, vp, i32, C.c_float, C.c_float, vp]
     lib.d2t_launch_count.argtypes = [vp]
     lib.d2t_launch_count.restype = C.c_int64
     for name in SYMBOLS:

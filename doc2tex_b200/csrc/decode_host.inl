@@ -81,77 +81,28 @@ int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long 
   const bool kv16 = kv_is_bf16(e);
   const __nv_bfloat16* kvh = reinterpret_cast<const __nv_bfloat16*>(kv);
   cudaError_t st;
-  // Staged kernel (default): one block per (image, head) stages every K / V record it needs into shared memory in one
-  // cp.async round trip — before the dependency wait where the data allows — and computes out of shared memory.
-  // (beam search by default: there the hypotheses of an image share most records and the per-row walk re-fetches them G times;
-  // attn_staged = 2 also routes the greedy rows here, measured slower: one warp per 41 KB of shared memory idles the SM)
-  if (e->attn_staged && (rows_per_src > 1 || e->attn_staged >= 2) && R % rows_per_src == 0 && rows_per_src <= 16 && D == heads * 32) {
-    const int G = rows_per_src, B = R / G;
-    // self-attention: at most max_steps positions; with attn_fit the step graph being captured knows its last step
-    const int n_max = n_fixed > 0 ? n_fixed : (e->attn_fit && e->attn_n_hint > 0) ? e->attn_n_hint : anc_ld > 0 ? anc_ld : 0;
-    int cap = e->attn_cap;
-    if (cap <= 0) {
-      // one round whenever possible: every position once, plus (beam) the diverged tails of the G hypotheses
-      const int want = n_fixed > 0 ? n_fixed : (anc ? n_max + 48 : n_max);
-      cap = ((want + 7) / 8) * 8;
-    }
-    if (cap > 32 * STAGED_MAX_PASS) cap = 32 * STAGED_MAX_PASS;
-    if (cap < 32) cap = 32;
-    if (n_max > 0) {
-      const size_t rec = kv16 ? StagedRec<__nv_bfloat16>::BYTES : StagedRec<float>::BYTES;
-      const size_t smem = (size_t)cap * rec + (anc ? (size_t)G * anc_ld * 4 : 0) + 16;
-      if (smem <= 200 * 1024) {
-        static bool attr_f = false, attr_h = false;
-        if (kv16) {
-          if (!attr_h) { CUDA_TRY(e, cudaFuncSetAttribute(decode_attention_staged_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_h = true; }
-          st = launch_kernel(decode_attention_staged_kernel<__nv_bfloat16>, dim3(B * heads), dim3(G * 32), smem, s, q, D, kvh, row_stride,
-                             2 * D, anc, anc_parity, anc_ld, G, step, n_fixed, out, D, out_hi, out_lo, cap, heads);
-        } else {
-          if (!attr_f) { CUDA_TRY(e, cudaFuncSetAttribute(decode_attention_staged_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_f = true; }
-          st = launch_kernel(decode_attention_staged_kernel<float>, dim3(B * heads), dim3(G * 32), smem, s, q, D, kv, row_stride,
-                             2 * D, anc, anc_parity, anc_ld, G, step, n_fixed, out, D, out_hi, out_lo, cap, heads);
-        }
-        CUDA_TRY(e, st);
-        e->launches += 1;
-        return 0;
-      }
-    }
-  }
-  // Beam search: the hypotheses of an image share the encoder memory and most of their prefixes.  One block owns ALL
-  // hypotheses of an image (for a slice of the heads), so their loads of a shared record are issued together on one SM and
-  // every fetch after the first is an L1 hit; the per-row mapping spreads them over SMs and pays L2 -> SM for each
-  // (ncu, 1 280 rows: 265 MB through L2 for 57 MB of DRAM reads, L1 hit rate 7 %).
-  if (e->attn_image_block && rows_per_src > 1 && heads == 8 && R % rows_per_src == 0 && rows_per_src <= 16) {
-    const int G = rows_per_src, B = R / G;
-    const int sp = (e->attn_split == 1 || G > 8) ? 1 : 2;
-    int nh = 8;
-    while (nh > 1 && G * nh * sp > 32) nh >>= 1;   // block = G beams x nh heads x sp key splits warps (<= 32)
-    const dim3 grid(B * (8 / nh)), block(G * nh * sp * 32);
-    const size_t smem = sp > 1 ? (size_t)G * nh * (sp - 1) * 36 * sizeof(float) : 0;
-    if (kv16)
-      st = sp == 2 ? launch_kernel(decode_attention_image_kernel<32, 2, __nv_bfloat16>, grid, block, smem, s, q, D, kvh, row_stride, 2 * D, anc, anc_parity, anc_ld, G, nh, step, n_fixed, out, D, out_hi, out_lo)
-                   : launch_kernel(decode_attention_image_kernel<32, 1, __nv_bfloat16>, grid, block, smem, s, q, D, kvh, row_stride, 2 * D, anc, anc_parity, anc_ld, G, nh, step, n_fixed, out, D, out_hi, out_lo);
-    else
-      st = sp == 2 ? launch_kernel(decode_attention_image_kernel<32, 2, float>, grid, block, smem, s, q, D, kv, row_stride, 2 * D, anc, anc_parity, anc_ld, G, nh, step, n_fixed, out, D, out_hi, out_lo)
-                   : launch_kernel(decode_attention_image_kernel<32, 1, float>, grid, block, smem, s, q, D, kv, row_stride, 2 * D, anc, anc_parity, anc_ld, G, nh, step, n_fixed, out, D, out_hi, out_lo);
-    CUDA_TRY(e, st);
-    e->launches += 1;
-    return 0;
-  }
+  // Measured alternatives for beam search, both slower than this per-row walk and removed (profiles/
+  // r02_ncu_beam_attention_variants.txt): one block per image so that L1 serves the records the hypotheses share (L1 hit
+  // rate 8 -> 79 %, 42.7 vs 35.0 us: the walk is bound by dependent round trips x waves, not by L2 traffic), and a kernel
+  // that stages every record of an (image, head) in shared memory with cp.async (2 460 instructions per warp: issue-bound).
+  // What helps is more loads in flight per warp: attn_kpi keys per quarter warp and iteration (4: -7 .. -11 % per step).
+  const int kpi = e->attn_kpi;
+#define D2T_ROW_ATTN(SP, HB, TKV, KPI_, GRID, BLOCK, PTR)                                                                         \
+  launch_kernel(decode_attention_kernel<32, SP, HB, TKV, KPI_>, GRID, BLOCK, 0, s, q, D, PTR, row_stride, 2 * D, anc, anc_parity,   \
+                anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo)
+#define D2T_ROW_ATTN_KPI(SP, HB, TKV, GRID, BLOCK, PTR)                                                                           \
+  (kpi >= 8 ? D2T_ROW_ATTN(SP, HB, TKV, 8, GRID, BLOCK, PTR) : kpi >= 4 ? D2T_ROW_ATTN(SP, HB, TKV, 4, GRID, BLOCK, PTR)            \
+                                                                      : D2T_ROW_ATTN(SP, HB, TKV, 2, GRID, BLOCK, PTR))
   if (kv16) {
-    if (split >= 2 && heads == 8)
-      st = launch_kernel(decode_attention_kernel<32, 2, 2, __nv_bfloat16>, dim3(R * 2), dim3(256), 0, s, q, D, kvh, row_stride,
-                         2 * D, anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo);
-    else
-      st = launch_kernel(decode_attention_kernel<32, 1, 1, __nv_bfloat16>, dim3(R), dim3(heads * 32), 0, s, q, D, kvh,
-                         row_stride, 2 * D, anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo);
+    if (split >= 2 && heads == 8) st = D2T_ROW_ATTN_KPI(2, 2, __nv_bfloat16, dim3(R * 2), dim3(256), kvh);
+    else st = D2T_ROW_ATTN_KPI(1, 1, __nv_bfloat16, dim3(R), dim3(heads * 32), kvh);
   } else if (split >= 2 && heads == 8) {
-    st = launch_kernel(decode_attention_kernel<32, 2, 2>, dim3(R * 2), dim3(256), 0, s, q, D, kv, row_stride, 2 * D,
-                       anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo);
+    st = D2T_ROW_ATTN_KPI(2, 2, float, dim3(R * 2), dim3(256), kv);
   } else {
-    st = launch_kernel(decode_attention_kernel<32, 1>, dim3(R), dim3(heads * 32), 0, s, q, D, kv, row_stride, 2 * D,
-                       anc, anc_parity, anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo);
+    st = D2T_ROW_ATTN_KPI(1, 1, float, dim3(R), dim3(heads * 32), kv);
   }
+#undef D2T_ROW_ATTN_KPI
+#undef D2T_ROW_ATTN
   CUDA_TRY(e, st);
   e->launches += 1;
   return 0;
@@ -619,13 +570,8 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
   // ---- step graphs: `spg` consecutive steps per graph (the step index lives on the device, so one graph serves every
   // step), plus a one-step graph for the tail ----
   const int spg = e->steps_per_graph < 1 ? 1 : e->steps_per_graph;
-  // attn_fit: the staged beam attention sizes its shared memory for the last step of the graph it is captured into, so
-  // every block of `spg` steps gets its own graph (19 for 151 steps) and early steps run more blocks per SM
-  const bool fit = e->attn_fit && e->attn_staged && beam > 0;
-  auto get_graph = [&](int n_steps, int first_step, cudaGraphExec_t* exec_out, int* nodes_out) -> int {
-    const int hint = fit ? std::min(T, first_step + n_steps) : 0;
-    e->attn_n_hint = hint;
-    std::vector<long long> key = {(long long)B, G, ntok, beam, T, want_logits ? 1 : 0, n_steps, hint};
+  auto get_graph = [&](int n_steps, cudaGraphExec_t* exec_out, int* nodes_out) -> int {
+    std::vector<long long> key = {(long long)B, G, ntok, beam, T, want_logits ? 1 : 0, n_steps};
     for (const TfmGroup& grp : groups) {
       const TfmBuffers& b = grp.b;
       const void* ptrs[] = {b.crosskv, b.selfkv, b.x, b.x2, b.q, b.att, b.ffn, b.logits, b.counters, b.tokens, b.anc,
@@ -649,7 +595,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
     st = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
     if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(st));
-    if (e->graphs.size() >= 128) {  // bounded cache
+    if (e->graphs.size() >= 32) {  // bounded cache
       cudaGraphExecDestroy(e->graphs.front().exec);
       e->graphs.erase(e->graphs.begin());
     }
@@ -682,12 +628,11 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
       did = (spg > 1 && T - executed >= spg) ? spg : 1;
       cudaGraphExec_t exec = nullptr;
       int nodes = 0;
-      if ((rc = get_graph(did, executed, &exec, &nodes))) return rc;   // cached after the first decode of this shape
+      if ((rc = get_graph(did, &exec, &nodes))) return rc;   // cached after the first decode of this shape
       CUDA_TRY(e, cudaGraphLaunch(exec, s));
       e->launches += nodes;
     } else {
       e->cur_step = executed;
-      e->attn_n_hint = fit ? executed + 1 : 0;
       if ((rc = enqueue_step())) return rc;
     }
     const int before = executed;

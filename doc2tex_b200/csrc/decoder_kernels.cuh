@@ -72,41 +72,52 @@ __device__ __forceinline__ float4 kv_load4(const __nv_bfloat16* p) {
 }
 
 // The key walk of one (row, head) by one warp: returns the warp-merged online-softmax state (every lane holds gm / sum,
-// lane c holds its 4 output channels summed over the four quarter warps).  Keys j = g + 8 * sp (mod 8 * SPLIT).
-template <int SPLIT, typename KV>
+// lane c holds its 4 output channels summed over the four quarter warps).  A quarter warp takes KPI keys per iteration —
+// key j = g + 4 i + 4 KPI (sp + SPLIT it) — and issues all 2 KPI 16-byte loads before it touches any of them: the walk is
+// bound by memory latency x iterations, so the loads in flight per warp set its speed (KPI = 2: 13 dependent round trips
+// at step 100, KPI = 8: 4).  anc_r (beam search) may point to shared memory.
+template <int SPLIT, int KPI, typename KV>
 __device__ __forceinline__ void attention_walk(const float4 q4, const KV* __restrict__ kbase, long long row_stride,
-                                               int pos_stride, const int* __restrict__ anc_r, int src_base, int n_keys,
+                                               int pos_stride, const int* anc_r, int src_base, int n_keys,
                                                int g, int sp, int D, float& gm_out, float& sum_out, float4& acc_out) {
   float mx = -INFINITY, sum = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   const unsigned gmask = 0xFFu << (g * 8);   // quarter warps run different trip counts: group-local shuffles
-  for (int j0 = g + 8 * sp; j0 < n_keys; j0 += 8 * SPLIT) {
-    const int j1 = j0 + 4;
-    const bool has1 = j1 < n_keys;
-    const int s0 = anc_r ? src_base + anc_r[j0] : src_base;
-    const int s1 = has1 ? (anc_r ? src_base + anc_r[j1] : src_base) : s0;
-    const KV* p0 = kbase + (size_t)s0 * row_stride + (size_t)j0 * pos_stride;
-    const KV* p1 = kbase + (size_t)s1 * row_stride + (size_t)(has1 ? j1 : j0) * pos_stride;
-    const float4 k0 = kv_load4(p0);
-    const float4 k1 = kv_load4(p1);
-    const float4 v0 = kv_load4(p0 + D);
-    const float4 v1 = kv_load4(p1 + D);
-    float d0 = fmaf(q4.x, k0.x, fmaf(q4.y, k0.y, fmaf(q4.z, k0.z, q4.w * k0.w)));
-    float d1 = fmaf(q4.x, k1.x, fmaf(q4.y, k1.y, fmaf(q4.z, k1.z, q4.w * k1.w)));
+  for (int j0 = g + 4 * KPI * sp; j0 < n_keys; j0 += 4 * KPI * SPLIT) {
+    const KV* p[KPI];
+    float4 k[KPI], v[KPI];
+    float d[KPI];
+#pragma unroll
+    for (int i = 0; i < KPI; ++i) {
+      const int j = (j0 + 4 * i < n_keys) ? j0 + 4 * i : j0;
+      const int src = anc_r ? src_base + anc_r[j] : src_base;
+      p[i] = kbase + (size_t)src * row_stride + (size_t)j * pos_stride;
+    }
+#pragma unroll
+    for (int i = 0; i < KPI; ++i) k[i] = kv_load4(p[i]);
+#pragma unroll
+    for (int i = 0; i < KPI; ++i) v[i] = kv_load4(p[i] + D);
+#pragma unroll
+    for (int i = 0; i < KPI; ++i) d[i] = fmaf(q4.x, k[i].x, fmaf(q4.y, k[i].y, fmaf(q4.z, k[i].z, q4.w * k[i].w)));
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
-      d0 += __shfl_xor_sync(gmask, d0, o);
-      d1 += __shfl_xor_sync(gmask, d1, o);
+#pragma unroll
+      for (int i = 0; i < KPI; ++i) d[i] += __shfl_xor_sync(gmask, d[i], o);
     }
-    if (!has1) d1 = -INFINITY;
-    const float nm = fmaxf(mx, fmaxf(d0, d1));
+    float nm = mx;
+#pragma unroll
+    for (int i = 0; i < KPI; ++i) {
+      if (j0 + 4 * i >= n_keys) d[i] = -INFINITY;
+      nm = fmaxf(nm, d[i]);
+    }
     const float corr = expf(mx - nm);   // 0 on the first iteration (mx = -inf)
-    const float e0 = expf(d0 - nm), e1 = expf(d1 - nm);
-    sum = sum * corr + (e0 + e1);
-    acc.x = fmaf(e1, v1.x, fmaf(e0, v0.x, acc.x * corr));
-    acc.y = fmaf(e1, v1.y, fmaf(e0, v0.y, acc.y * corr));
-    acc.z = fmaf(e1, v1.z, fmaf(e0, v0.z, acc.z * corr));
-    acc.w = fmaf(e1, v1.w, fmaf(e0, v0.w, acc.w * corr));
+    sum *= corr; acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
+#pragma unroll
+    for (int i = 0; i < KPI; ++i) {
+      const float e = expf(d[i] - nm);
+      sum += e;
+      acc.x = fmaf(e, v[i].x, acc.x); acc.y = fmaf(e, v[i].y, acc.y); acc.z = fmaf(e, v[i].z, acc.z); acc.w = fmaf(e, v[i].w, acc.w);
+    }
     mx = nm;
   }
   // merge the four quarter-warp states
@@ -163,7 +174,7 @@ __device__ __forceinline__ void attention_store(const float4 acc, float sum, siz
 
 // HB > 1: the heads of a row are spread over HB blocks (grid = rows x HB, 8 / HB heads each): 512 quarter-size blocks
 // balance over 148 SMs better than 256 full ones.
-template <int HD, int SPLIT = 1, int HB = 1, typename KV = float>
+template <int HD, int SPLIT = 1, int HB = 1, typename KV = float, int KPI = 2>
 __global__ void __launch_bounds__(256 * SPLIT / HB)
 decode_attention_kernel(const float* __restrict__ q, int ldq, const KV* __restrict__ kv,
                         long long row_stride, int pos_stride, const int* __restrict__ anc,
@@ -188,7 +199,7 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const KV* __restri
   q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
   float gm, sum;
   float4 acc;
-  attention_walk<SPLIT>(q4, kv + h * HD + c, row_stride, pos_stride, anc_r, src_base, n_keys, g, sp, D, gm, sum, acc);
+  attention_walk<SPLIT, KPI>(q4, kv + h * HD + c, row_stride, pos_stride, anc_r, src_base, n_keys, g, sp, D, gm, sum, acc);
   if constexpr (SPLIT > 1) {
     __shared__ float s_part[8 * (SPLIT - 1) * 36];   // [head][split - 1][max, sum, pad, pad, acc[32]]
     if (sp > 0) {
@@ -201,277 +212,6 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const KV* __restri
     attention_merge_splits<SPLIT>(s_part + hl * (SPLIT - 1) * 36, c, gm, sum, acc);
   }
   if (g == 0) attention_store(acc, sum, (size_t)r * D + h * HD + c, out, out_hi, out_lo);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Image-block mapping of the same single-query attention for beam search.  The G hypotheses of an image read the same
-// encoder memory (cross-attention) and mostly the same ancestor slots (self-attention: anc[b][j] is the physical row that
-// holds position j of hypothesis b, and hypotheses with a common prefix name the same row).  With one block per ROW the
-// hypotheses of an image land on different SMs and every one of them pulls the shared records through L2 (ncu at 1 280
-// rows: 265 MB of L2 -> SM traffic for 57 MB of DRAM reads, L1 hit rate 7 %).  Here one block owns all G hypotheses of an
-// image for `nh` of its heads — warp = (hypothesis, head, key split) — so the G loads of a shared record are issued by
-// sibling warps of one SM within a few hundred cycles and all but the first hit in L1 (or merge with the miss in flight).
-// Arithmetic per (row, head) is exactly that of decode_attention_kernel with the same SPLIT.
-//   grid = images x (8 / nh); block = G x nh x SPLIT warps; dynamic smem = G*nh*(SPLIT-1)*36 floats
-// ---------------------------------------------------------------------------------------------
-template <int HD, int SPLIT, typename KV>
-__global__ void __launch_bounds__(1024)
-decode_attention_image_kernel(const float* __restrict__ q, int ldq, const KV* __restrict__ kv, long long row_stride,
-                              int pos_stride, const int* __restrict__ anc, long long anc_parity_stride, int anc_ld,
-                              int G, int nh, const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
-                              __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
-  static_assert(HD == 32, "8 lanes x float4 per head slice");
-  extern __shared__ float s_part_img[];   // [G * nh][SPLIT - 1][max, sum, pad, pad, acc[32]]
-  pdl_wait();
-  pdl_trigger();
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int hb = 8 / nh;                       // blocks per image
-  const int img = blockIdx.x / hb;
-  // warp order: key split slowest, then head, hypothesis fastest — the sibling hypotheses of one head sit in adjacent warps
-  const int sp = wid / (G * nh);
-  const int pair = wid - sp * (G * nh);        // (hypothesis, head) of this block
-  const int hl = pair / G, beam = pair - hl * G;
-  const int h = (blockIdx.x - img * hb) * nh + hl;
-  const int r = img * G + beam;
-  const int g = lane >> 3, c = (lane & 7) * 4;
-  const int t = step ? *step : 0;
-  const int n_keys = n_fixed > 0 ? n_fixed : t + 1;
-  const int* anc_r = anc ? anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)r * anc_ld : nullptr;
-  const int src_base = img * (anc ? G : 1);
-  const float scale = rsqrtf((float)HD);
-  float4 q4 = *reinterpret_cast<const float4*>(q + (size_t)r * ldq + h * HD + c);
-  q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
-  float gm, sum;
-  float4 acc;
-  attention_walk<SPLIT>(q4, kv + h * HD + c, row_stride, pos_stride, anc_r, src_base, n_keys, g, sp, D, gm, sum, acc);
-  if constexpr (SPLIT > 1) {
-    if (sp > 0) {
-      float* pp = s_part_img + (pair * (SPLIT - 1) + sp - 1) * 36;
-      if (g == 0) *reinterpret_cast<float4*>(pp + 4 + c) = acc;
-      if (lane == 0) { pp[0] = gm; pp[1] = sum; }
-    }
-    __syncthreads();
-    if (sp > 0) return;
-    attention_merge_splits<SPLIT>(s_part_img + pair * (SPLIT - 1) * 36, c, gm, sum, acc);
-  }
-  if (g == 0) attention_store(acc, sum, (size_t)r * D + h * HD + c, out, out_hi, out_lo);
-}
-
-// ---------------------------------------------------------------------------------------------
-// Staged single-query attention: the decode attention above is LATENCY bound, not bandwidth bound — a warp walks its keys
-// two at a time and pays one L2 / HBM round trip per pair (13 dependent round trips at step 100; ncu: 7.5 TB/s nominal at
-// 1 280 beam rows with every repeat served by L2, 52 % of the warp slots idle on long-scoreboard stalls).  Here a block owns
-// one head of one image (all G hypotheses of it: warp = hypothesis), stages EVERY record it needs into shared memory with
-// 16-byte cp.async in ONE round trip, and computes softmax(q K^T) V out of shared memory:
-//   * beam search: position j of hypothesis b lives in physical row anc[b][j]; hypotheses share the prefix up to their
-//     common ancestor, so positions [0, c) (c = first position where the ancestry rows differ) are staged ONCE for the image
-//     and only the tail [c, n) once per hypothesis; the encoder memory (cross-attention) is staged once for all G.
-//   * programmatic dependent launch: everything except q and the record of the CURRENT position was written at least two
-//     kernels ago (earlier steps; the ancestry table by the previous step's beam kernel; the encoder memory before the loop),
-//     so it is staged BEFORE griddepcontrol.wait and overlaps the projection GEMM that precedes this kernel.
-//   * more records than the shared-memory capacity (long encoder memories, wide beams): rounds of `cap` records with an
-//     online-softmax merge between rounds.
-// Record = [K head slice (32) | V head slice (32) | 16 B pad]: the pad makes the key-per-lane 16-byte reads conflict free.
-//   grid = images x 8 heads; block = G warps; dynamic smem = cap * REC + G * anc_ld * 4 + G * 128 bytes
-// ---------------------------------------------------------------------------------------------
-template <typename KV>
-struct StagedRec {
-  static constexpr int HD = 32;
-  static constexpr int HALF_BYTES = HD * (int)sizeof(KV);          // K (or V) head slice
-  static constexpr int BYTES = 2 * HALF_BYTES + 16;                // + pad
-  static constexpr int PIECES = 2 * HALF_BYTES / 16;               // 16-byte cp.async pieces per record
-  static constexpr int EL_PER_PIECE = 16 / (int)sizeof(KV);
-};
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-// 32-dim dot product of the (pre-scaled) query held in registers with one staged K head slice
-__device__ __forceinline__ float staged_dot(const float (&qv)[32], const uint8_t* __restrict__ rec, float) {
-  float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-  for (int u = 0; u < 8; u += 2) {
-    const float4 k0 = *reinterpret_cast<const float4*>(rec + 16 * u);
-    const float4 k1 = *reinterpret_cast<const float4*>(rec + 16 * u + 16);
-    d0 = fmaf(qv[4 * u], k0.x, fmaf(qv[4 * u + 1], k0.y, fmaf(qv[4 * u + 2], k0.z, fmaf(qv[4 * u + 3], k0.w, d0))));
-    d1 = fmaf(qv[4 * u + 4], k1.x, fmaf(qv[4 * u + 5], k1.y, fmaf(qv[4 * u + 6], k1.z, fmaf(qv[4 * u + 7], k1.w, d1))));
-  }
-  return d0 + d1;
-}
-__device__ __forceinline__ float staged_dot(const float (&qv)[32], const uint8_t* __restrict__ rec, __nv_bfloat16) {
-  float d0 = 0.f, d1 = 0.f;
-#pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(rec + 16 * u);
-    const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-    const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
-    const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.z));
-    const float2 e = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.w));
-    d0 = fmaf(qv[8 * u], a.x, fmaf(qv[8 * u + 1], a.y, fmaf(qv[8 * u + 2], b.x, fmaf(qv[8 * u + 3], b.y, d0))));
-    d1 = fmaf(qv[8 * u + 4], c.x, fmaf(qv[8 * u + 5], c.y, fmaf(qv[8 * u + 6], e.x, fmaf(qv[8 * u + 7], e.y, d1))));
-  }
-  return d0 + d1;
-}
-// four consecutive V channels of one staged record
-__device__ __forceinline__ float4 staged_v4(const uint8_t* rec_v, int c4, float) {
-  return *reinterpret_cast<const float4*>(rec_v + 4 * c4);
-}
-__device__ __forceinline__ float4 staged_v4(const uint8_t* rec_v, int c4, __nv_bfloat16) {
-  const uint2 u = *reinterpret_cast<const uint2*>(rec_v + 2 * c4);
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
-  return make_float4(a.x, a.y, b.x, b.y);
-}
-
-constexpr int STAGED_MAX_PASS = 8;   // 32-key passes per round: cap <= 256 records per hypothesis and round
-
-template <typename KV>
-__global__ void __launch_bounds__(512)
-decode_attention_staged_kernel(const float* __restrict__ q, int ldq, const KV* __restrict__ kv, long long row_stride,
-                               int pos_stride, const int* __restrict__ anc, long long anc_parity_stride, int anc_ld,
-                               int G, const int* __restrict__ step, int n_fixed, float* __restrict__ out, int D,
-                               __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, int cap, int nheads) {
-  using R = StagedRec<KV>;
-  extern __shared__ __align__(16) uint8_t staged_smem[];
-  uint8_t* const s_rec = staged_smem;
-  int* const s_anc = reinterpret_cast<int*>(staged_smem + (size_t)cap * R::BYTES);
-  __shared__ int s_common;
-  const uint32_t s_rec_addr = (uint32_t)__cvta_generic_to_shared(s_rec);
-
-  const int img = blockIdx.x / nheads, h = blockIdx.x - img * nheads;
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, nthr = blockDim.x;
-  const int r = img * G + wid;                       // this warp's row (hypothesis)
-  const bool self = n_fixed <= 0;
-  // ---- before the dependency wait: only data written at least two kernels ago ----
-  const int t = step ? *step : 0;
-  const int n = self ? t + 1 : n_fixed;
-  const long long src0 = (long long)img * (anc ? G : 1);   // first physical row of this image
-  int c = n;                                               // positions [0, c) are common to all hypotheses
-  if (anc) {
-    const int* a0 = anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)img * G * anc_ld;
-    if (threadIdx.x == 0) s_common = n;
-    for (int j = lane; j < n; j += 32) s_anc[wid * anc_ld + j] = a0[(size_t)wid * anc_ld + j];   // warp = hypothesis
-    __syncthreads();
-    int first_diff = n;
-    for (int j = n - 1 - (int)threadIdx.x; j >= 0; j -= nthr) {   // the ancestry rows differ at the END of the prefix
-      const int a = s_anc[j];
-      bool same = true;
-      for (int b = 1; b < G; ++b) same = same && (s_anc[b * anc_ld + j] == a);
-      if (!same) first_diff = j;
-    }
-    if (first_diff < n) atomicMin(&s_common, first_diff);
-    __syncthreads();
-    c = s_common;
-  }
-  const KV* const kvh = kv + h * R::HD;
-  const int piece = threadIdx.x % R::PIECES;
-  const int piece_off = piece < R::PIECES / 2 ? piece * R::EL_PER_PIECE : D + (piece - R::PIECES / 2) * R::EL_PER_PIECE;
-  const int tgrp = threadIdx.x / R::PIECES, ngrp = nthr / R::PIECES;   // record slots staged per sweep of the block
-  // Records of the round [p0, p1): positions < c once (index j - p0), then G records per position (ns + (j - pc) * G + b).
-  // stage() copies the records of positions [ja, jb) of that round, one 16-byte piece per thread and record.
-  auto stage = [&](int p0, int p1, int ja, int jb) {
-    ja = max(ja, p0); jb = min(jb, p1);
-    if (ja >= jb) return;
-    const int ns = max(0, min(p1, c) - p0), pc = max(p0, c);
-    for (int j = ja + tgrp; j < min(jb, c); j += ngrp) {                       // common part
-      const KV* src = kvh + (size_t)(src0 + (anc ? s_anc[j] : 0)) * row_stride + (size_t)j * pos_stride + piece_off;
-      cp_async16(s_rec_addr + (uint32_t)(j - p0) * R::BYTES + (uint32_t)piece * 16u, src);
-    }
-    if (jb > c) {                                                               // per-hypothesis tail (beam search only)
-      const int b = tgrp % G, jsub = tgrp / G, jstep = max(1, ngrp / G);       // ngrp = 2 G (fp32) or 4 G (bf16) record slots
-      if (jsub < jstep) {
-        for (int j = max(ja, pc) + jsub; j < jb; j += jstep) {
-          const KV* src = kvh + (size_t)(src0 + s_anc[b * anc_ld + j]) * row_stride + (size_t)j * pos_stride + piece_off;
-          cp_async16(s_rec_addr + (uint32_t)(ns + (j - pc) * G + b) * R::BYTES + (uint32_t)piece * 16u, src);
-        }
-      }
-    }
-  };
-  auto round_end = [&](int p0) {   // as many positions as fit into `cap` records
-    const int common_left = max(0, c - p0);
-    if (common_left >= cap) return p0 + cap;
-    return min(n, max(p0, c) + (cap - common_left) / G);
-  };
-  int p0 = 0, p1 = round_end(0);
-  stage(p0, p1, 0, self ? min(p1, t) : p1);              // everything but the current position of the self-attention
-  pdl_wait();
-  pdl_trigger();
-  if (self && t < p1) stage(p0, p1, t, t + 1);           // K / V of the current position: written by the preceding projection
-  float qv[32];                                           // the whole (row, head) query in every lane: broadcast loads
-  {
-    const float4* qp = reinterpret_cast<const float4*>(q + (size_t)r * ldq + h * R::HD);
-    const float scale = rsqrtf((float)R::HD);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const float4 v = __ldg(qp + u);
-      qv[4 * u] = v.x * scale; qv[4 * u + 1] = v.y * scale; qv[4 * u + 2] = v.z * scale; qv[4 * u + 3] = v.w * scale;
-    }
-  }
-  cp_async_wait_all();
-  __syncthreads();
-
-  const int g = lane >> 3, c4 = (lane & 7) * 4;          // value pass: quarter warp g takes key 4 i + g, lane owns 4 channels
-  float M = -INFINITY, L = 0.f;                          // online softmax state across rounds
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (;;) {
-    const int ns = max(0, min(p1, c) - p0), pc = max(p0, c);
-    const int tail_off = ns - pc * G + (anc ? wid : 0);
-    auto rec_of = [&](int j) { return j < c ? j - p0 : j * G + tail_off; };
-    float sc[STAGED_MAX_PASS];
-    float m_r = -INFINITY;
-#pragma unroll
-    for (int ps = 0; ps < STAGED_MAX_PASS; ++ps) {
-      const int j = p0 + ps * 32 + lane;
-      sc[ps] = -INFINITY;
-      if (j < p1) sc[ps] = staged_dot(qv, s_rec + (size_t)rec_of(j) * R::BYTES, KV());
-      m_r = fmaxf(m_r, sc[ps]);
-    }
-    m_r = warp_max(m_r);
-    const float Mn = fmaxf(M, m_r);
-    const float corr = (M == -INFINITY) ? 0.f : expf(M - Mn);
-    float l_r = 0.f;
-#pragma unroll
-    for (int ps = 0; ps < STAGED_MAX_PASS; ++ps) {
-      sc[ps] = (sc[ps] == -INFINITY) ? 0.f : expf(sc[ps] - Mn);
-      l_r += sc[ps];
-    }
-    l_r = warp_sum(l_r);
-    L = L * corr + l_r;
-    acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
-#pragma unroll
-    for (int ps = 0; ps < STAGED_MAX_PASS; ++ps) {
-      const int jb = p0 + ps * 32;
-      if (jb < p1) {
-        const int cnt = min(32, p1 - jb);
-        for (int i = 0; i < cnt; i += 4) {              // 4 keys per warp instruction, 16-byte value reads
-          const float w = __shfl_sync(0xffffffffu, sc[ps], i + g);
-          if (i + g < cnt) {
-            const float4 v = staged_v4(s_rec + (size_t)rec_of(jb + i + g) * R::BYTES + R::HALF_BYTES, c4, KV());
-            acc.x = fmaf(w, v.x, acc.x); acc.y = fmaf(w, v.y, acc.y); acc.z = fmaf(w, v.z, acc.z); acc.w = fmaf(w, v.w, acc.w);
-          }
-        }
-      }
-    }
-    M = Mn;
-    if (p1 >= n) break;
-    // next round (only when the records did not fit): restage after everybody is done with the buffer
-    __syncthreads();
-    p0 = p1;
-    p1 = round_end(p0);
-    stage(p0, p1, p0, p1);
-    cp_async_wait_all();
-    __syncthreads();
-  }
-#pragma unroll
-  for (int o = 8; o < 32; o <<= 1) {
-    acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-    acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
-    acc.z += __shfl_xor_sync(0xffffffffu, acc.z, o);
-    acc.w += __shfl_xor_sync(0xffffffffu, acc.w, o);
-  }
-  if (g == 0) attention_store(acc, L, (size_t)r * D + h * R::HD + c4, out, out_hi, out_lo);
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {

@@ -26,6 +26,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc3.cuh"
 #include "decode_cluster.cuh"
+#include "preprocess_kernels.cuh"
 
 using namespace d2t;
 
@@ -121,13 +122,7 @@ struct d2t_engine {
   bool fuse_pick = true;    // option "fuse_pick": 0 = separate embed / advance launches in the greedy decode step
   bool lean_acts = true;    // option "lean_acts": 0 = every stem layer writes fp32 AND operand planes, read or not
   int split_k = 1;       // option "split_k": 0 = never, 1 = auto split-K of the LayerNorm-fed decode projections
-  bool attn_image_block = true;   // option "attn_image_block": beam search — one block owns all hypotheses of an image, so the
-                                  // records they share (encoder memory, common prefixes) are served by that SM's L1
-  int attn_staged = 1;      // option "attn_staged": 1 = beam-search attention stages all K / V records of an (image, head) block in
-                            // shared memory (cp.async), 2 = greedy rows too, 0 = off
-  bool attn_fit = true;     // option "attn_fit": one step graph per block of steps, shared memory sized for its last step
-  int attn_n_hint = 0;      // largest number of self-attention positions of the steps being enqueued (attn_fit)
-  int attn_cap = 0;         // option "attn_cap": records per staging round of that kernel (0 = auto, <= 256)
+  int attn_kpi = 4;         // option "attn_kpi": keys in flight per quarter warp of the decode attention walk (2, 4, 8)
   int attn_split = 0;       // option "attn_split": warps per (row, head) of the per-row decode attention (0 = auto)
   bool stack_mma = true;    // option "stack_mma": bf16x3 decode projections issue 2 MMAs per k-step against [W_hi ; W_lo]
   int steps_per_graph = 8;  // option "steps_per_graph": decode steps captured per CUDA graph (= the early-exit poll interval)
@@ -813,14 +808,8 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
     e->time_conv = value != 0; decode_affecting = false;
   } else if (k == "time_decode") {
     e->time_decode = value != 0;
-  } else if (k == "attn_image_block") {
-    e->attn_image_block = value != 0;
-  } else if (k == "attn_staged") {
-    e->attn_staged = value;
-  } else if (k == "attn_fit") {
-    e->attn_fit = value != 0;
-  } else if (k == "attn_cap") {
-    e->attn_cap = value;
+  } else if (k == "attn_kpi") {
+    e->attn_kpi = value;
   } else if (k == "attn_split") {
     e->attn_split = value;
   } else if (k == "stack_mma") {
@@ -1030,6 +1019,38 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
     tap(e, "block" + std::to_string(i), xs, true);
   }
   if ((rc = layernorm(e, xs.p, e->dev[SEQ + "norm.weight"], e->dev[SEQ + "norm.bias"], ctx, rows, D, 1e-6f, s))) return rc;
+  return D2T_OK;
+}
+
+int d2t_prep_measure(d2t_engine* e, const uint8_t* packed, const d2t_prep_image* imgs, int n, int32_t* stats, d2t_stream stream) {
+  if (!e) return D2T_ERR_INVALID;
+  if (!packed || !imgs || !stats || n <= 0) return e->fail(D2T_ERR_INVALID, "bad d2t_prep_measure arguments");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  prep_stats_kernel<<<n, 1024, 0, (cudaStream_t)stream>>>(packed, imgs, stats);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
+  return D2T_OK;
+}
+
+int d2t_prep_render(d2t_engine* e, const uint8_t* packed, const d2t_prep_image* imgs, const d2t_prep_plan* plans, int n,
+                    const int32_t* coefs, uint8_t* scratch, int any_resize, float sub, float mul, d2t_stream stream) {
+  if (!e) return D2T_ERR_INVALID;
+  if (!packed || !imgs || !plans || !scratch || n <= 0) return e->fail(D2T_ERR_INVALID, "bad d2t_prep_render arguments");
+  if (any_resize && !coefs) return e->fail(D2T_ERR_INVALID, "d2t_prep_render: resize requested without coefficient tables");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  // grid.x sized for the largest image the YAML surface allows (448 x 960) at 4 pixels per thread; grid-stride beyond
+  const dim3 grid(e->num_sms >= 64 ? 420 : 128, n);
+  prep_crop_kernel<<<grid, 256, 0, s>>>(packed, imgs, plans, scratch);
+  e->launches += 1;
+  if (any_resize) {
+    prep_resample_kernel<<<grid, 256, 0, s>>>(plans, coefs, scratch, 0);
+    prep_resample_kernel<<<grid, 256, 0, s>>>(plans, coefs, scratch, 1);
+    e->launches += 2;
+  }
+  prep_finish_kernel<<<grid, 256, 0, s>>>(plans, scratch, sub, mul);
+  e->launches += 1;
+  CUDA_TRY(e, cudaGetLastError());
   return D2T_OK;
 }
 

@@ -161,12 +161,7 @@ int d2t_decode_attn_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, i
  *   "decode_groups"    concurrent row groups of one decode call (parallel graph branches; 0/1 = one chain, default)
  *   "split_k"          0 = never, 1 = auto split-K of the LayerNorm-fed decode projections (default 1)
  *   "stack_mma"        0/1 bf16x3 decode projections: two MMAs per k-step against the stacked [W_hi ; W_lo] operand (default 1)
- *   "attn_staged"      beam-search decode attention: one block per (image, head) stages every K / V record its hypotheses need in
- *                      shared memory with cp.async (shared prefixes once; before the dependency wait where the data allows) and
- *                      computes out of shared memory: 1 = beam search only (default), 2 = greedy rows too, 0 = off
- *   "attn_fit"         0/1 one CUDA graph per block of steps so that kernel sizes its shared memory for that block's last step (default 1)
- *   "attn_cap"         records per staging round of that kernel (0 = auto; at most 256)
- *   "attn_image_block" 0/1 (attn_staged = 0) beam search: one attention block owns all hypotheses of an image (L1 serves shared records; default 1)
+ *   "attn_kpi"         keys in flight per quarter warp and iteration of the decode attention walk: 2, 4 (default), 8
  *   "attn_split"       warps per (row, head) of the decode attention: 0 = auto, 1, 2
  *   "fuse_pick"        0/1 greedy pick also embeds the next token and advances the step counter (default 1)
  *   "kv_bf16"          0/1 bf16 KV caches in the single-pass bf16 mode (default 1; the fp32-parity modes always keep fp32)
@@ -179,6 +174,39 @@ int d2t_decode_attn_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, i
  *   "dbg_decode", "dbg_timeline" phase / per-launch timestamps of the last decode step on stderr
  */
 int d2t_set_option(d2t_engine* e, const char* key, int value);
+
+/*
+ * Image preprocessing on the device.  Replaces, for a LIST of differently sized grey crops, what
+ * utils/predict_utils.py::resize (14-115; imgH None, no resizer) does per image on the host with PIL / cv2 / albumentations:
+ * optional integer cv2.INTER_AREA down-sampling (:33-44), data_utils.py::pad = min-max stretch + polarity + crop to the ink
+ * bounding box + black padding to multiples of 32 (10-47), minmax_size = Pillow LANCZOS shrink to max_dimension / white
+ * canvas up to min_dimension (62-82), Normalize(mean, std) and the channel-0 slice (math_transform.py:42-50).
+ * Two calls, because the output size of an image depends on its ink box: d2t_prep_measure -> the host plans sizes and
+ * buckets (doc2tex_b200/preprocess.py) -> d2t_prep_render.  All pointers are device pointers unless noted.
+ */
+typedef struct d2t_prep_image {
+  int64_t src_off;   /* byte offset of the image (row-major uint8, h0 x w0) in the packed buffer */
+  int32_t h0, w0;    /* source size */
+  int32_t ds;        /* integer down-sampling ratio applied on the fly (1 = none); h0, w0 must be divisible by it */
+  int32_t pad_;
+} d2t_prep_image;
+
+typedef struct d2t_prep_plan {
+  int32_t use_crop, crop_x, crop_y, crop_w, crop_h, inverted, vmin;   /* data_utils.py::pad (from d2t_prep_measure) */
+  int32_t hb, wb;                 /* stage-B image: the padded crop, or the (down-sampled) source */
+  int32_t do_resize, rh, rw;      /* Pillow LANCZOS shrink to (rh, rw) */
+  int32_t kx_off, kx_ksize, ky_off, ky_ksize;   /* coefficient tables (int32 rows [first, count, k...]) in coefs_dev */
+  int32_t out_h, out_w;           /* final canvas (white beyond the image) = the bucket's (H, W) */
+  int64_t off_b, off_t, off_r;    /* byte offsets of stage B / horizontal-pass / resized images in the scratch buffer */
+  void* dst;                      /* fp32 (out_h, out_w) slot of the bucket tensor */
+} d2t_prep_plan;
+
+/* stats_dev: int32 [n][8] = {x, y, w, h, inverted, vmin, status, 0}; status 0 ok, 1 blank image, 2 no pixel crosses the threshold. */
+int d2t_prep_measure(d2t_engine* e, const uint8_t* packed_dev, const d2t_prep_image* imgs_dev, int n, int32_t* stats_dev,
+                     d2t_stream stream);
+/* sub = mean * 255, mul = 1 / (std * 255), both rounded to fp32 by the caller (albumentations' arithmetic). */
+int d2t_prep_render(d2t_engine* e, const uint8_t* packed_dev, const d2t_prep_image* imgs_dev, const d2t_prep_plan* plans_dev,
+                    int n, const int32_t* coefs_dev, uint8_t* scratch_dev, int any_resize, float sub, float mul, d2t_stream stream);
 
 /*
  * Test / profiling hooks (not part of the reference surface).

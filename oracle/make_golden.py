@@ -271,6 +271,152 @@ def attn_beam_cases():
     attn_beam_case("attnv2_beam_sharp_end80", 64, 256, 2, 8.0, sharpen=16.0, min_ulp=64)   # all five complete within 11 steps
 
 
+LATEX_VOCAB = ["a", "b", "c", "x", "y", "z", "A", "B", "0", "1", "2", "9", "+", "-", "=", "(", ")", "{", "}", "[", "]", "^", "_", ",",
+               ".", "\\frac", "\\sqrt", "\\alpha", "\\beta", "\\mathrm", "\\mathbf", "\\operatorname", "\\left(", "\\right)",
+               "\\left\\{", "\\right\\}", "\\,", "\\;", "\\sum", "\\int", "\\cdot", "\\times", "\\langle", "\\rangle", "|", "!", "'", "<", ">", "/"]
+
+
+def latex_vocab(n=500):
+    """A LaTeX-shaped synthetic vocabulary (letters, digits, brackets, text-mode commands: what the whitespace
+    post-processing of the evaluation loop acts on), padded with \\tokN to n entries."""
+    return LATEX_VOCAB + [f"\\tok{i}" for i in range(n - len(LATEX_VOCAB))]
+
+
+def converter_case():
+    """a12: the LIVE reference converters (tfm_converter.py / attn_converter.py) on random id matrices and labels: encode,
+    decode, the callers' cut at the first "[s]" (inferencing.py:119-121) and detokenize."""
+    import json
+    from doc2tex.modules.converter.attn_converter import AttnLabelConverter
+    from doc2tex.modules.converter.tfm_converter import TFMLabelConverter
+    vocab = latex_vocab()
+    g = torch.Generator().manual_seed(7)
+    out = {"vocab": vocab, "cases": {}}
+    for name, cls in (("TFM", TFMLabelConverter), ("Attn", AttnLabelConverter)):
+        conv = cls(vocab, "cpu")
+        end = conv.dict["[s]"]
+        V = len(conv.character)
+        ids = torch.randint(len(cls.list_token), min(V, 60), (12, 24), generator=g)
+        for r, pos in enumerate([0, 1, 5, 23, 12, 3, 3, None, None, 7, 22, 10]):   # first END position per row (None: no END)
+            if pos is not None:
+                ids[r, pos] = end
+                if r % 2:
+                    ids[r, min(23, pos + 2)] = end                                  # a second END later in the row
+        labels = [[vocab[int(i)] for i in torch.randint(0, 50, (int(n),), generator=g)] for n in (0, 1, 4, 9, 30)]
+        labels.append(["not-in-vocab", vocab[3], "??"])
+        enc, lens = conv.encode(labels, batch_max_length=12)
+        rec = {"ids": ids.tolist(), "labels": labels, "encode": enc.tolist(), "encode_len": lens.tolist(),
+               "special": {k: conv.dict[k] for k in cls.list_token}, "detokenize": conv.detokenize(ids)}
+        for level in ("word", "char"):
+            dec = conv.decode(ids, level)
+            rec[f"decode_{level}"] = dec
+            rec[f"cut_{level}"] = [s_[: s_.find("[s]")] for s_ in dec]
+        out["cases"][name] = rec
+    with open(os.path.join(GOLD, "converters.json"), "w") as f:
+        json.dump(out, f)
+    print("[converters] written")
+
+
+def validation_case():
+    """f2: the LIVE reference's validation_step (engine/inferencing.py:12-247) on two TFM weight sets and one Attnv2 set,
+    two batches of three images each.  python-Levenshtein is absent from this image, so the module is imported with the
+    repo's numpy edit distance registered under that name (the metric values depend on it; strings, losses and accuracy
+    do not)."""
+    import json
+    import types
+    from doc2tex_b200 import engine_inferencing as ei
+    lev = types.ModuleType("Levenshtein")
+    lev.distance = lambda a_, b_: ei.edit_distance(a_, b_)
+    sys.modules.setdefault("Levenshtein", lev)
+    from doc2tex.engine.inferencing import validation_step as ref_validation_step
+    from doc2tex.modules.converter.attn_converter import AttnLabelConverter
+    from doc2tex.modules.converter.tfm_converter import TFMLabelConverter
+    vocab = latex_vocab()
+    g = torch.Generator().manual_seed(11)
+    out = {"vocab": vocab, "cases": {}}
+    for name, head, eb in (("tfm_noend", "TFM", None), ("tfm_end15", "TFM", 1.5), ("attnv2_end30", "Attnv2", 3.0)):
+        cfg = synth.make_config(head)
+        sd = synth.make_state_dict(cfg, seed=1111, end_bias=eb)
+        m = ref_model(cfg, sd)
+        conv = (TFMLabelConverter if head == "TFM" else AttnLabelConverter)(vocab, "cpu")
+        labels_all, loader = [], []
+        for bidx in range(2):
+            img = synth.make_images(3, 64, 256, seed=5000 + 3 * bidx)
+            labels = [[vocab[int(i)] for i in torch.randint(0, 50, (int(n),), generator=g)] for n in torch.randint(1, 12, (3,), generator=g)]
+            names = [f"img_{bidx}_{k}.png" for k in range(3)]
+            loader.append((img, labels, names))
+            labels_all.append(labels)
+        config = dict(cfg, export_csv=False, use_amp=False, sanity_check=False, token_level="word", postprocess=True)
+        crit = torch.nn.CrossEntropyLoss(ignore_index=conv.ignore_idx, reduction="none")
+        with torch.no_grad():
+            res = ref_validation_step(m, None, crit, loader, conv, config, types.SimpleNamespace(log_path="golden.log"), "cpu")
+        all_loss, names, mean_loss, acc, bleu_s, ned, wed, preds, labs, _, n = res
+        print(f"[validation {name}] n={n} acc={acc} bleu={bleu_s} norm_ED={ned:.4f} word_ED={wed:.4f} mean loss {float(mean_loss):.5f}; "
+              f"pred[0]={preds[0][:60]!r}")
+        out["cases"][name] = {"head": head, "end_bias": eb, "labels_in": labels_all, "all_loss": [float(x) for x in all_loss],
+                              "names": names, "mean_loss": float(mean_loss), "accuracy": acc,
+                              "bleu": None if bleu_s is None else float(bleu_s), "norm_ED": float(ned), "word_ED": float(wed),
+                              "preds": preds, "labels": labs, "n": n}
+    with open(os.path.join(GOLD, "validation_step.json"), "w") as f:
+        json.dump(out, f)
+    print("[validation_step] written")
+
+
+from oracle.make_golden_helpers import synth_crop  # noqa: E402
+
+
+def preprocess_case():
+    """f3: the reference's own pad / minmax_size (utils/data_utils.py, imported unmodified; PIL and cv2 are present here), and
+    cv2.resize(INTER_AREA) as predict_utils.py:33-44 calls it, on seeded synthetic crops.  Asserts the numpy oracle equals
+    them bit for bit and stores the REFERENCE outputs.  The albumentations Normalize of the test transform cannot be imported
+    (package absent): its arithmetic is applied as published ((v - mean*255) * (1/(std*255)) in float32)."""
+    import cv2
+    from PIL import Image
+    from doc2tex.utils import data_utils as du
+    from oracle import preprocess_oracle as po
+    MAXD, MIND = [448, 960], [32, 32]
+    out = {"max_dimension": np.array(MAXD), "min_dimension": np.array(MIND)}
+    # (a) crop-to-ink + minmax: pad True, no down-sampling
+    specs = [(60, 200, True), (37, 150, True), (64, 256, False), (33, 33, True), (128, 400, False), (200, 611, True),
+             (600, 700, True), (96, 1000, True), (300, 1500, False), (470, 500, True)]
+    keep = []
+    for k, (h, w, dark) in enumerate(specs):
+        a = synth_crop(h, w, 1000 + k, dark)
+        data = np.array(Image.fromarray(a).convert("LA"))
+        data = (data - data.min()) / (data.max() - data.min()) * 255
+        gray = 255 * (data[..., 0] < 128).astype(np.uint8) if data[..., 0].mean() > 128 else 255 * (data[..., 0] > 128).astype(np.uint8)
+        box = cv2.boundingRect(cv2.findNonZero(gray))                 # data_utils.py:31-32
+        padded = du.pad(Image.fromarray(a))
+        o_pad, o_box = po.pad_to_ink(a)
+        assert tuple(box) == tuple(o_box), (box, o_box)
+        assert np.array_equal(np.array(padded), o_pad)
+        try:
+            ref = np.array(du.minmax_size(padded, MAXD, MIND))
+        except UnboundLocalError:
+            print(f"[preprocess] crop {k} {h}x{w}: the reference's minmax_size raises UnboundLocalError (get_divisible_size) — skipped")
+            continue
+        mine = po.minmax_size(o_pad, MAXD, MIND)
+        assert np.array_equal(ref, mine), (k, ref.shape, mine.shape)
+        out[f"a{len(keep)}_img"] = a
+        out[f"a{len(keep)}_box"] = np.array(box)
+        out[f"a{len(keep)}_u8"] = ref       # the normalised floats follow from these by Normalize's published arithmetic
+        print(f"[preprocess] crop {k} {h}x{w} dark_ink={dark}: box {box} -> padded {np.array(padded).shape} -> {ref.shape}")
+        keep.append(k)
+    out["a_count"] = np.array(len(keep))
+    # (b) cv2.INTER_AREA down-sampling by 2 + minmax, pad False (config/test.yaml: pad False, downsample 2)
+    nb = 0
+    for k, (h, w) in enumerate([(128, 512), (64, 256), (192, 896), (64, 128)]):
+        a = synth_crop(h, w, 2000 + k, True)
+        ref_small = cv2.resize(a, dsize=(int(w / 2), int(h / 2)), interpolation=cv2.INTER_AREA)
+        assert np.array_equal(ref_small, po.area_downsample(a, 2))
+        ref = np.array(du.minmax_size(Image.fromarray(ref_small).convert("L"), MAXD, MIND))
+        assert np.array_equal(ref, po.minmax_size(ref_small, MAXD, MIND))
+        out[f"b{nb}_img"], out[f"b{nb}_u8"] = a, ref
+        nb += 1
+    out["b_count"] = np.array(nb)
+    np.savez_compressed(os.path.join(GOLD, "preprocess.npz"), **out)
+    print(f"[preprocess] written: {len(keep)} crop-to-ink cases, {nb} down-sampling cases")
+
+
 if __name__ == "__main__":
     torch.manual_seed(0)
     os.makedirs(GOLD, exist_ok=True)
@@ -293,3 +439,6 @@ if __name__ == "__main__":
     attn_beam_cases()
     attn_base_cases()
     encoder_variant_cases()
+    converter_case()
+    validation_case()
+    preprocess_case()

@@ -486,66 +486,37 @@ def test_merged_decode_schedule_equals_sequential(built_lib, merge):
     e.set_option("encoder_sms", 148)
 
 
-@pytest.mark.parametrize("beam,split", [(5, 0), (5, 1), (3, 0), (10, 0)])
-def test_image_block_attention_equals_per_row_kernel(built_lib, beam, split):
-    """Option attn_image_block: one attention block owns all hypotheses of an image (shared records served by L1).  Per
-    (row, head) the arithmetic is the per-row kernel's with the same key split, so beams, lengths, traces AND scores are
-    bit-identical when the splits agree (per-row auto split = 2 at these row counts, image-block default = 2)."""
-    e = engine_for("TFM", 1.5, "bf16x3")
-    ctx, _, _ = e.encode(synth.make_images(6, 64, 256, seed=55).cuda())
-    e.set_option("attn_staged", 0)
-    e.set_option("attn_image_block", 0)
-    e.set_option("attn_split", split)
-    try:
-        b0 = e.decode_beam(ctx, beam, trace=True)
-        e.set_option("attn_image_block", 1)
-        b1 = e.decode_beam(ctx, beam, trace=True)
-    finally:
-        e.set_option("attn_image_block", 1)
-        e.set_option("attn_split", 0)
-        e.set_option("attn_staged", 1)
-    assert b0[3] == b1[3] and torch.equal(b0[0], b1[0]) and torch.equal(b0[1], b1[1])
-    assert torch.equal(b0[4][:, :b0[3]], b1[4][:, :b1[3]])
-    if beam <= 8:   # same split on both sides -> same summation order
-        assert torch.equal(b0[2], b1[2])
-    else:           # beam 10: image-block runs one warp per (row, head), the per-row kernel two
-        assert float((b0[2] - b1[2]).abs().max()) <= 1e-4 * float(b0[2].abs().max())
-
-
 @pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
-@pytest.mark.parametrize("cap", [0, 32, 40])
-def test_staged_attention_equals_walking_kernel(built_lib, precision, cap):
-    """Option attn_staged: every K / V record of a (image, head) block staged in shared memory by cp.async, softmax over the
-    whole round instead of the online walk.  Same math in a different fp32 order: per-step logits within the fp32-parity
-    tolerance of the walking kernel, greedy tokens and beams identical (bf16x3).  cap = 32 / 40 forces several staging
-    rounds (online merge across rounds; 40 is not a multiple of the beam width), also for the 67-token encoder memory."""
+def test_attention_keys_in_flight_do_not_change_results(built_lib, precision):
+    """Option attn_kpi: 2 / 4 / 8 keys in flight per quarter warp of the decode attention walk (fp32 and bf16 KV caches,
+    one and two warps per (row, head)).  Same online softmax over differently sized key batches: per-step logits within the
+    fp32-parity tolerance of each other, greedy tokens and beams identical (bf16x3)."""
     from doc2tex_b200.engine import Engine
     cfg, sd = state_dict_for("TFM", 1.5, 4.0)
     e = Engine(cfg, "cuda:0", precision=precision)
     e.load_state_dict(sd)
     ctx, _, _ = e.encode(synth.make_images(7, 64, 256, seed=123).cuda())
+    big = ctx.repeat(100, 1, 1)[:650].contiguous()    # > 4 x 148 rows: the one-warp-per-(row, head) kernel
     out = {}
-    for staged in (0, 2):   # 2 = greedy rows through the staged kernel too (1, the default, stages beam search only)
-        e.set_option("attn_staged", staged)
-        e.set_option("attn_cap", cap)
+    for kpi in (2, 4, 8):
+        e.set_option("attn_kpi", kpi)
         ids, lg, st = e.decode_greedy(ctx, max_steps=70, is_test=False)
-        beam = e.decode_beam(ctx, 5, max_steps=70, trace=True)
-        beam3 = e.decode_beam(ctx, 3, max_steps=70)
-        out[staged] = (ids.cpu(), lg.cpu(), [x.cpu() for x in beam[:3]], beam[4].cpu(), [x.cpu() for x in beam3[:3]])
+        beam = e.decode_beam(ctx, 5, max_steps=70)
+        ids_big, _, _ = e.decode_greedy(big, max_steps=30, is_test=False, return_logits=False)
+        out[kpi] = (ids.cpu(), lg.cpu(), [x.cpu() for x in beam[:3]], ids_big.cpu())
     e.close()
-    a, b = out[0], out[2]
-    same = (a[0] == b[0]).cumprod(dim=1).bool()
-    first = torch.ones_like(same)
-    first[:, 1:] = same[:, :-1]
-    err = ((a[1] - b[1]).abs().amax(dim=2) / a[1].abs().amax(dim=2).clamp_min(1e-6))[first]
-    assert float(err.max()) < (1e-4 if precision == "bf16x3" else 2e-2), float(err.max())
-    if precision == "bf16x3":
-        assert torch.equal(a[0], b[0])
-        assert torch.equal(a[2][0], b[2][0]) and torch.equal(a[2][1], b[2][1])
-        if cap == 0:   # several rounds merge their softmax states in another order: near-tied candidates may swap places
-            assert torch.equal(a[3], b[3])
-        assert float((a[2][2] - b[2][2]).abs().max()) <= 1e-4 * float(a[2][2].abs().max())
-        assert torch.equal(a[4][0], b[4][0]) and torch.equal(a[4][1], b[4][1])
+    a = out[2]
+    for kpi in (4, 8):
+        b = out[kpi]
+        same = (a[0] == b[0]).cumprod(dim=1).bool()
+        first = torch.ones_like(same)
+        first[:, 1:] = same[:, :-1]
+        err = ((a[1] - b[1]).abs().amax(dim=2) / a[1].abs().amax(dim=2).clamp_min(1e-6))[first]
+        assert float(err.max()) < (1e-4 if precision == "bf16x3" else 2e-2), (kpi, float(err.max()))
+        if precision == "bf16x3":
+            assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3])
+            assert torch.equal(a[2][0], b[2][0]) and torch.equal(a[2][1], b[2][1])
+            assert float((a[2][2] - b[2][2]).abs().max()) <= 1e-4 * float(a[2][2].abs().max())
 
 
 @pytest.mark.parametrize("spg", [1, 3, 16])
@@ -555,7 +526,6 @@ def test_steps_per_graph_do_not_change_results(built_lib, spg):
     e = engine_for("TFM", 1.5, "bf16x3")
     ctx, _, _ = e.encode(synth.make_images(4, 64, 256, seed=91).cuda())
     e.set_option("steps_per_graph", 8)
-    e.set_option("attn_fit", 0 if spg == 3 else 1)   # per-block graphs with fitted shared memory, and one graph for all steps
     ids0, lg0, st0 = e.decode_greedy(ctx, is_test=True)
     full0, _, _ = e.decode_greedy(ctx, is_test=False, return_logits=False)
     b0 = e.decode_beam(ctx, 5, trace=True)
@@ -566,7 +536,6 @@ def test_steps_per_graph_do_not_change_results(built_lib, spg):
         b1 = e.decode_beam(ctx, 5, trace=True)
     finally:
         e.set_option("steps_per_graph", 8)
-        e.set_option("attn_fit", 1)
     assert st0 == st1 and torch.equal(ids0[:, :st0], ids1[:, :st1]) and torch.equal(lg0[:, :st0], lg1[:, :st1])
     assert torch.equal(full0, full1)
     assert b0[3] == b1[3] and all(torch.equal(a, b) for a, b in zip(b0[:3], b1[:3]))

@@ -170,3 +170,44 @@ def test_infer_cli_keeps_the_reference_flags():
                  "--resizer", "--start_idx", "--strong_log"}
     assert reference <= ours
     assert ours - reference == {"--precision", "--synthetic"}
+
+
+def test_converters_match_live_reference_fixture():
+    """a12 / f2: encode / decode / detokenize and the vectorised decode_cut against outputs of the LIVE reference converters
+    (tests/golden/converters.json, minted by oracle/make_golden.py::converter_case), including the callers' cut quirks:
+    a blank kept before "[s]" with word-level joining, the last character lost when a row has no "[s]"."""
+    import json
+    from doc2tex_b200.engine_inferencing import decode_cut, first_end_cut
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "converters.json")))
+    for name, cls in (("TFM", TFMLabelConverter), ("Attn", AttnLabelConverter)):
+        rec = g["cases"][name]
+        conv = cls(g["vocab"], "cpu")
+        assert {k: conv.dict[k] for k in rec["special"]} == rec["special"]
+        ids = torch.tensor(rec["ids"])
+        enc, lens = conv.encode(rec["labels"], batch_max_length=12)
+        assert enc.tolist() == rec["encode"] and lens.tolist() == rec["encode_len"]
+        assert conv.detokenize(ids) == rec["detokenize"]
+        cut = first_end_cut(ids, conv.dict["[s]"])
+        for level in ("word", "char"):
+            assert conv.decode(ids, level) == rec[f"decode_{level}"]
+            strings, tokens = decode_cut(conv, ids, level, cut)
+            assert strings == rec[f"cut_{level}"], (name, level)
+            assert tokens == rec["detokenize"]
+        # a vocabulary token that contains "[s]" switches decode_cut to the reference's string search
+        odd = cls(["x[s]y"] + g["vocab"][1:], "cpu")
+        first_tok = len(cls.list_token)
+        row = torch.tensor([[first_tok, first_tok + 1, odd.dict["[s]"], first_tok + 2]])
+        full = odd.decode(row)[0]
+        assert decode_cut(odd, row)[0] == [full[: full.find("[s]")]]
+
+
+def test_string_metrics_small_cases():
+    from doc2tex_b200.engine_inferencing import corpus_bleu, edit_distance, single_ed, squeeze_latex_whitespace, word_ned
+    assert edit_distance("kitten", "sitting") == 3 and edit_distance("", "abc") == 3 and edit_distance("abc", "abc") == 0
+    assert edit_distance(["a", "b", "c"], ["a", "c"]) == 1
+    assert single_ed("", "x") == 0 and abs(single_ed("abcd", "abed") - 0.75) < 1e-12
+    assert abs(word_ned("a b c", "a x c") - (1 - 1 / 3)) < 1e-12 and word_ned("", "a") == 0.0
+    assert corpus_bleu([["a", "b", "c", "d", "e"]], [[["a", "b", "c", "d", "e"]]]) == pytest.approx(1.0)
+    assert corpus_bleu([["a", "b"]], [[["c", "d"]]]) == 0.0
+    assert squeeze_latex_whitespace("x ^ { 2 } + \\mathrm { d } y") == "x^{2}+\\mathrm{d}y"
+    assert squeeze_latex_whitespace("\\sin x") == "\\sin x"

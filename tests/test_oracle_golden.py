@@ -136,3 +136,30 @@ def test_oracle_edge_cases():
     assert int(torch.argmax(torch.tensor([1.0, 3.0, 3.0]))) == 1       # lowest index wins
     pe = synth.sincos_pos_embed(256, 6, 113)
     assert pe.shape == (1, 679, 256) and float(pe[0, 0].abs().max()) == 0.0
+
+
+def test_preprocess_oracle_matches_reference_outputs():
+    """f3: the numpy restatement of pad / minmax_size / INTER_AREA / Pillow LANCZOS against the REFERENCE's outputs stored in
+    tests/golden/preprocess.npz (ink boxes and 8-bit images bit for bit)."""
+    import numpy as np
+    from oracle import preprocess_oracle as po
+    from tests.util import load_golden
+    g = load_golden("preprocess")
+    maxd, mind = g["max_dimension"].tolist(), g["min_dimension"].tolist()
+    shrunk = 0
+    for i in range(int(g["a_count"])):
+        a = g[f"a{i}_img"]
+        padded, box = po.pad_to_ink(a)
+        assert list(box) == g[f"a{i}_box"].tolist()
+        out = po.minmax_size(padded, maxd, mind)
+        assert np.array_equal(out, g[f"a{i}_u8"]), i
+        shrunk += out.shape != padded.shape
+    assert shrunk >= 1      # at least one case goes through the LANCZOS shrink
+    for i in range(int(g["b_count"])):
+        small = po.area_downsample(g[f"b{i}_img"], 2)
+        assert np.array_equal(po.minmax_size(small, maxd, mind), g[f"b{i}_u8"]), i
+    x = po.normalize(np.array([[0, 127, 128, 255]], dtype=np.uint8))
+    assert np.allclose(x, [[-1.0, -1 / 255, 1 / 255, 1.0]], atol=1e-7)
+    # sizes on which the reference itself dies (get_divisible_size): the oracle implements the evident intent
+    assert po.minmax_plan(500, 1800, maxd, mind) == ((288, 960), None)      # 266.67 -> up to 288
+    assert po.minmax_plan(20, 90, maxd, mind) == (None, (32, 160))

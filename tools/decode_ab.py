@@ -25,17 +25,15 @@ eng.load_state_dict(sd)
 img = synth.make_images(256, 64, 256, seed=2024).cuda()
 ctx, _, _ = eng.encode(img)
 
-BASE = {"stack_mma": 0, "attn_image_block": 0, "steps_per_graph": 1, "attn_split": 0, "attn_staged": 0, "attn_cap": 0, "attn_fit": 0}
+BASE = {"stack_mma": 1, "steps_per_graph": 8, "attn_split": 0, "attn_kpi": 4, "split_k": 1, "pdl": 1}
 SETS = [
-    ("round-1 chain", {}),
-    ("+ stack_mma", {"stack_mma": 1}),
-    ("+ attn_image_block", {"attn_image_block": 1}),
-    ("+ attn_image_block, split 1", {"attn_image_block": 1, "attn_split": 1}),
-    ("+ 8 steps per graph", {"steps_per_graph": 8}),
-    ("+ attn_staged (beam only)", {"attn_staged": 1}),
-    ("+ attn_staged, greedy too", {"attn_staged": 2}),
-    ("+ attn_staged + fit + 8 steps", {"attn_staged": 1, "attn_fit": 1, "steps_per_graph": 8}),
-    ("default: staged+fit+stack+8 steps", {"stack_mma": 1, "attn_staged": 1, "attn_fit": 1, "steps_per_graph": 8}),
+    ("default", {}),
+    ("attn_kpi 2", {"attn_kpi": 2}),
+    ("attn_kpi 8", {"attn_kpi": 8}),
+    ("stack_mma 0", {"stack_mma": 0}),
+    ("1 step per graph", {"steps_per_graph": 1}),
+    ("split_k 0", {"split_k": 0}),
+    ("pdl 0", {"pdl": 0}),
 ]
 WORK = [("greedy", 32), ("greedy", 256), ("greedy", 1024), ("beam", 32), ("beam", 256), ("beam", 1024)]
 
@@ -64,15 +62,12 @@ for name, opts in SETS:
         eng.set_option(k, v)
     row = []
     for mode, n in WORK:
-        if mode == "greedy" and "attn_image_block" in opts and "attn_staged" not in opts:
-            row.append("      -")
-            continue
         ms = run(mode, n)
         row.append(f"{1e3 * ms / 151:7.1f}")
     print(f"{name:<34}" + " ".join(f"{m[0]}{n}r={r}" for (m, n), r in zip([(m, n * (5 if m == 'beam' else 1)) for m, n in WORK], row)), flush=True)
 
 if a.timeline:
-    for k, v in {"stack_mma": 1, "attn_staged": 1, "attn_cap": 0, "steps_per_graph": 1, "attn_fit": 1}.items():
+    for k, v in dict(BASE, steps_per_graph=1).items():
         eng.set_option(k, v)
     eng.set_option("dbg_timeline", 1)
     for mode, n in (("greedy", 256), ("greedy", 1024), ("beam", 256)):
