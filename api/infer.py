@@ -11,11 +11,12 @@ row layout (:230-236).  Differences, on purpose:
     itself, so its batch is always 1: api/infer.py:94);
   * the model is ``doc2tex_b200.modules.build_model.Model`` (no CPU fallback);
   * ``--synthetic N`` runs N seeded synthetic images when no dataset is at hand (GPU box smoke test);
-  * metrics: exact match and token edit distance are computed in-process (the reference needs nltk / Levenshtein,
-    which are not part of the hot path); BLEU is omitted.
-The image preprocessing of the reference (utils/predict_utils.py::resize — crop to ink, pad to /32, normalise)
-is a 'next' row; here an image is converted to grayscale, padded with white to the next multiple
-of 32 and normalised with the YAML's mean/std.
+  * metrics: exact match and the edit distances are computed in-process (doc2tex_b200/engine_inferencing.py; the
+    reference needs nltk / Levenshtein, which are not part of the hot path); BLEU is omitted;
+  * the image preprocessing of the reference (utils/predict_utils.py::resize, per image on the host with PIL / cv2 /
+    albumentations: optional down-sampling, crop to ink when `pad`, minmax_size, normalise) runs on the GPU for the whole
+    list at once (doc2tex_b200/preprocess.py) and hands back the same-(H, W) buckets directly; --resizer (the
+    learned width predictor, predict_utils.py:59-83) is not part of the accelerated path and is refused.
 """
 from __future__ import annotations
 
@@ -36,33 +37,16 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from doc2tex_b200 import synth  # noqa: E402
+from doc2tex_b200.engine_inferencing import edit_distance  # noqa: E402
 from doc2tex_b200.modules.build_model import Model  # noqa: E402
 from doc2tex_b200.modules.converter import builder  # noqa: E402
 
 DELIMITER = "\t"  # doc2tex/data/data_const.py:18
 
 
-def edit_distance(a, b) -> int:
-    prev = list(range(len(b) + 1))
-    for i, x in enumerate(a, 1):
-        cur = [i]
-        for j, y in enumerate(b, 1):
-            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (x != y)))
-        prev = cur
-    return prev[-1]
-
-
-def load_image(path: str, config: dict) -> torch.Tensor:
+def load_grey(path: str) -> np.ndarray:
     from PIL import Image
-    img = Image.open(path).convert("L")
-    w, h = img.size
-    min_h, min_w = config.get("min_dimension", [32, 32])
-    H = max(min_h, (h + 31) // 32 * 32)
-    W = max(min_w, (w + 31) // 32 * 32)
-    canvas = Image.new("L", (W, H), 255)
-    canvas.paste(img, (0, 0))
-    x = torch.from_numpy(np.asarray(canvas, dtype=np.float32) / 255.0)
-    return ((x - config.get("mean", 0.5)) / config.get("std", 0.5))[None]
+    return np.asarray(Image.open(path).convert("L"), dtype=np.uint8)     # predict_utils.py:16
 
 
 def read_rows(args, config):
@@ -86,13 +70,24 @@ def run_infer(model, rows, converter, config, args):
     device = config["device"]
     buckets = defaultdict(list)
     pre_t = 0.0
-    for name, label, tensor in rows:
-        if config.get("data_filtering", True) and label is not None and len(label) > max_len:
-            continue
-        t0 = time.time()
-        x = tensor if tensor is not None else load_image(os.path.join(config["eval_data"], name), config)
-        pre_t += time.time() - t0
-        buckets[tuple(x.shape[-2:])].append((name, label, x))
+    kept = [(name, label, tensor) for name, label, tensor in rows
+            if not (config.get("data_filtering", True) and label is not None and len(label) > max_len)]
+    todo = [(name, label) for name, label, tensor in kept if tensor is None]
+    for name, label, tensor in kept:
+        if tensor is not None:                       # --synthetic: already a normalised (1, H, W) tensor
+            buckets[tuple(tensor.shape[-2:])].append((name, label, tensor.to(device)))
+    if todo:
+        from doc2tex_b200.preprocess import Preprocessor
+        prep = Preprocessor(model.engine, config)
+        for lo in range(0, len(todo), 1024):          # the whole chunk is packed, uploaded and preprocessed in one go
+            part = todo[lo: lo + 1024]
+            t0 = time.time()
+            greys = [load_grey(os.path.join(config["eval_data"], name)) for name, _ in part]
+            for (H, W), (batch, idx) in prep(greys).items():
+                for slot, i in enumerate(idx):
+                    buckets[(H, W)].append((part[i][0], part[i][1], batch[slot]))
+            torch.cuda.synchronize()
+            pre_t += time.time() - t0
     n = n_correct = 0
     norm_ed = word_ed = 0.0
     infer_time = post_time = 0.0
@@ -104,7 +99,7 @@ def run_infer(model, rows, converter, config, args):
     for (H, W), items in buckets.items():
         for lo in range(0, len(items), config["batch_size"]):
             chunk = items[lo: lo + config["batch_size"]]
-            image = torch.stack([c[2] for c in chunk]).to(device)
+            image = torch.stack([c[2] for c in chunk])
             B = image.size(0)
             text = torch.zeros(B, max_len + 1, dtype=torch.long, device=device) if is_attn \
                 else torch.full((B, 1), 1, dtype=torch.long, device=device)
@@ -199,6 +194,8 @@ def main(argv=None):
     config["batch_size"] = args.batch_size
     config["workers"] = args.num_workers
     config["use_amp"] = bool(args.amp)
+    if args.resizer:
+        parser.error("--resizer (the learned width predictor of predict_utils.py:59-83) is not on the accelerated path")
     config["use_resizer"] = args.resizer
     config["eval_data"] = args.data_dir
     if args.precision or args.amp:

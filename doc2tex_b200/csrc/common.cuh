@@ -57,29 +57,16 @@ inline bool& pdl_enabled() {
   return on;
 }
 
-inline int& launch_cluster_x() {   // thread-block cluster width of the next launch_kernel call (1 = none)
-  static thread_local int c = 1;
-  return c;
-}
-
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
-  cudaLaunchAttribute attr[2];
+  cudaLaunchAttribute attr[1];
   int n = 0;
   if (pdl_enabled()) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;
-  }
-  if (launch_cluster_x() > 1) {
-    attr[n].id = cudaLaunchAttributeClusterDimension;
-    attr[n].val.clusterDim.x = launch_cluster_x();
-    attr[n].val.clusterDim.y = 1;
-    attr[n].val.clusterDim.z = 1;
-    ++n;
-    launch_cluster_x() = 1;
   }
   cfg.attrs = attr;
   cfg.numAttrs = n;

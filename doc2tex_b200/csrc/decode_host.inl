@@ -10,7 +10,7 @@ constexpr int TFM_PAD = 0, TFM_GO = 1, TFM_END = 2;  // TFMLabelConverter (tfm_c
 constexpr int POLL_EVERY = 8;
 
 struct TfmBuffers {
-  float *crosskv = nullptr, *selfkv = nullptr, *crosskv_tmp = nullptr;
+  float *crosskv = nullptr, *selfkv = nullptr;
   float* crosskv_f32 = nullptr;   // bf16 KV mode: fp32 staging of one layer's cross K/V projection
   float *x = nullptr, *x2 = nullptr, *q = nullptr, *att = nullptr, *ffn = nullptr, *logits = nullptr;
   int *tokens = nullptr, *anc = nullptr, *n_live = nullptr, *n_done = nullptr, *finished = nullptr;
@@ -85,6 +85,9 @@ int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long 
   // r02_ncu_beam_attention_variants.txt): one block per image so that L1 serves the records the hypotheses share (L1 hit
   // rate 8 -> 79 %, 42.7 vs 35.0 us: the walk is bound by dependent round trips x waves, not by L2 traffic), and a kernel
   // that stages every record of an (image, head) in shared memory with cp.async (2 460 instructions per warp: issue-bound).
+  // A third, beam-grouped kernel (one warp = all hypotheses of an (image, head): every shared record loaded ONCE into
+  // registers) cut the L2 -> SM traffic five-fold and ran exactly as long as this walk at 1 280 and 5 120 rows (step 415 vs
+  // 414 us, 1 204 vs 1 190 us): at these sizes the walk is bound by its own dot / shuffle / exp instruction stream.
   // What helps is more loads in flight per warp: attn_kpi keys per quarter warp and iteration (4: -7 .. -11 % per step).
   const int kpi = e->attn_kpi;
 #define D2T_ROW_ATTN(SP, HB, TKV, KPI_, GRID, BLOCK, PTR)                                                                         \
@@ -126,111 +129,9 @@ int linear_ln(d2t_engine* e, ConvGemm g, const TfmBuffers& b, const float* lw, c
   return layernorm(e, b.x2, lw, lb, b.x, R, D, 1e-5f, s, b.x_hi, b.x_lo, parts, (long long)R * D);
 }
 
-// Tensor maps and occupancy of the cluster-resident decode step (decode_cluster.cuh).  The kernel is specialised for the
-// HybridViT-TFM geometry (d_model 256 = 8 heads x 32, dim_feedforward 1024, vocabulary <= 512); other geometries keep
-// the launch-per-sublayer chain.
-bool cluster_step_active(const d2t_engine* e) { return e->use_cluster_step && e->cs_plan.ready; }
-
-bool cluster_step_geometry_ok(const d2t_config& c) {
-  return c.head == D2T_HEAD_TFM && c.hidden == CS_D && c.dec_heads == CS_CL && c.dec_ff == CS_F && c.vocab <= CS_CL * 64 &&
-         c.dec_layers <= CS_MAX_LAYERS && c.max_seq_len + 2 <= CS_ANC_MAX &&
-         (c.precision == D2T_PREC_BF16X3 || c.precision == D2T_PREC_BF16);
-}
-
 }  // namespace
 
-int prepare_cluster_step(d2t_engine* e) {
-  const d2t_config& c = e->cfg;
-  e->cs_plan.ready = false;
-  if (!cluster_step_geometry_ok(c)) return 0;
-  const int L = c.dec_layers, D = c.hidden;
-  std::vector<CUtensorMap> maps((size_t)L * 12 + 2);
-  auto put = [&](const float* w, int N, int K, int box_rows, CUtensorMap* out) -> int {
-    auto it = e->tcw.find(w);
-    if (it == e->tcw.end() || !it->second.ready) return e->fail(D2T_ERR_STATE, "cluster step: weight planes missing");
-    cudaError_t st = cs_make_weight_map(it->second.hi, N, K, box_rows, out);
-    if (st == cudaSuccess) st = cs_make_weight_map(it->second.lo ? it->second.lo : it->second.hi, N, K, box_rows, out + 1);
-    if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "cluster step tensor map: %s", cudaGetErrorString(st));
-    return 0;
-  };
-  int rc;
-  for (int l = 0; l < L; ++l) {
-    const std::string p = PRED + "model.layers." + std::to_string(l) + ".";
-    CUtensorMap* m = maps.data() + (size_t)l * 12;
-    if ((rc = put(e->dev[p + "self_attn.in_proj_weight"], 3 * D, D, 32, m + 0))) return rc;
-    if ((rc = put(e->dev[p + "self_attn.out_proj.weight"], D, D, 32, m + 2))) return rc;
-    if ((rc = put(e->dev[p + "multihead_attn.in_proj_weight"], D, D, 32, m + 4))) return rc;
-    if ((rc = put(e->dev[p + "multihead_attn.out_proj.weight"], D, D, 32, m + 6))) return rc;
-    if ((rc = put(e->dev[p + "linear1.weight"], c.dec_ff, D, 128, m + 8))) return rc;
-    if ((rc = put(e->dev[p + "linear2.weight"], D, c.dec_ff, 128, m + 10))) return rc;
-  }
-  if ((rc = put(e->dev[PRED + "proj.weight"], c.vocab, D, 64, maps.data() + (size_t)L * 12))) return rc;
-  CUDA_TRY(e, cudaMalloc(&e->cs_plan.maps_dev, maps.size() * sizeof(CUtensorMap)));
-  e->owned.push_back(e->cs_plan.maps_dev);
-  CUDA_TRY(e, cudaMemcpy(e->cs_plan.maps_dev, maps.data(), maps.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-  e->cs_plan.n_maps = (int)maps.size();
-  cudaError_t st;
-  if (c.precision == D2T_PREC_BF16X3) {
-    st = cs_prepare_kernel<3, 16>(&e->cs_plan.max_clusters[0]);
-    if (st == cudaSuccess) st = cs_prepare_kernel<3, 32>(&e->cs_plan.max_clusters[1]);
-  } else {
-    st = cs_prepare_kernel<1, 16>(&e->cs_plan.max_clusters[0]);
-    if (st == cudaSuccess) st = cs_prepare_kernel<1, 32>(&e->cs_plan.max_clusters[1]);
-  }
-  if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "cluster step kernel setup: %s", cudaGetErrorString(st));
-  e->cs_plan.ready = e->cs_plan.max_clusters[0] > 0 && e->cs_plan.max_clusters[1] > 0;
-  if (e->dbg_decode)
-    fprintf(stderr, "[cluster step] co-resident clusters: %d (16 rows), %d (32 rows)\n", e->cs_plan.max_clusters[0], e->cs_plan.max_clusters[1]);
-  return 0;
-}
-
 namespace {
-
-int enqueue_cluster_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok, int beam, int T, cudaStream_t s) {
-  const d2t_config& c = e->cfg;
-  const int D = c.hidden, L = T + 1;
-  ClusterStepParams p{};
-  p.maps = e->cs_plan.maps_dev;
-  p.n_layers = c.dec_layers;
-  for (int l = 0; l < c.dec_layers; ++l) {
-    const std::string q = PRED + "model.layers." + std::to_string(l) + ".";
-    ClusterLayer& cl = p.layer[l];
-    cl.b_qkv = e->dev[q + "self_attn.in_proj_bias"];
-    cl.b_o1 = e->dev[q + "self_attn.out_proj.bias"];
-    cl.b_q2 = e->dev[q + "multihead_attn.in_proj_bias"];
-    cl.b_o2 = e->dev[q + "multihead_attn.out_proj.bias"];
-    cl.b_f1 = e->dev[q + "linear1.bias"];
-    cl.b_f2 = e->dev[q + "linear2.bias"];
-    cl.ln1_w = e->dev[q + "norm1.weight"]; cl.ln1_b = e->dev[q + "norm1.bias"];
-    cl.ln2_w = e->dev[q + "norm2.weight"]; cl.ln2_b = e->dev[q + "norm2.bias"];
-    cl.ln3_w = e->dev[q + "norm3.weight"]; cl.ln3_b = e->dev[q + "norm3.bias"];
-  }
-  p.b_vocab = e->dev[PRED + "proj.bias"];
-  p.V = c.vocab;
-  p.v_slice = (c.vocab + CS_CL - 1) / CS_CL;
-  p.tokens = b.tokens; p.tok_ld = L; p.tok_parity = beam > 0 ? (long long)R * L : 0;
-  p.step = b.counters;
-  p.emb = e->dev[PRED + "word_embed.weight"]; p.pe = e->dev[PRED + "pos_enc.pe"]; p.emb_mult = sqrtf((float)D);
-  p.selfkv = b.selfkv; p.kv_layer_stride = (long long)R * T * 2 * D; p.kv_row_stride = (long long)T * 2 * D; p.kv_T = T;
-  p.crosskv = b.crosskv; p.ckv_layer_stride = (long long)B * ntok * 2 * D; p.ntok = ntok;
-  p.rows_per_img = beam > 0 ? beam : 1;
-  p.anc = beam > 0 ? b.anc : nullptr; p.anc_parity = beam > 0 ? (long long)R * L : 0; p.anc_ld = L;
-  p.logits = b.logits;
-  p.R = R;
-  p.dbg = b.dbg;
-  int nc = 0;
-  const int small_cap = e->cs_plan.max_clusters[0] * 16;
-  if (R <= small_cap) {
-    cs_plan_rows(R, e->cs_plan.max_clusters[0], &p.rows_per_cluster, &nc);
-    if (p.rows_per_cluster > 16) { p.rows_per_cluster = 16; nc = (R + 15) / 16; }
-  } else {
-    cs_plan_rows(R, e->cs_plan.max_clusters[1], &p.rows_per_cluster, &nc);
-  }
-  cudaError_t st = c.precision == D2T_PREC_BF16X3 ? cs_launch<3>(p, nc, s) : cs_launch<1>(p, nc, s);
-  if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "cluster decode step launch failed: %s", cudaGetErrorString(st));
-  e->launches += 1;
-  return 0;
-}
 
 // D2T_DBG_TIMELINE=1: a one-thread kernel between the launches of a step records globaltimer, so the last step's
 // per-launch durations (each inflated by one extra launch gap) can be printed.  Debug only.
@@ -270,10 +171,7 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
   auto from_ffn = [&](ConvGemm& g) { if (b.planes) { g.a_map_hi = &b.map_ffn_hi; g.a_map_lo = b.ffn_lo ? &b.map_ffn_lo : nullptr; } };
   Timeline tl; tl.buf = b.timeline; tl.s = s; tl.names = &g_tl_names;
   tl.mark("start");
-  const bool cluster = cluster_step_active(e) && b.crosskv_tmp != nullptr;
-  if (cluster) {
-    if ((rc = enqueue_cluster_step(e, b, R, B, ntok, beam, T, s))) return rc;
-  } else {
+  {
   // greedy chain: the pick kernel of step t already wrote x of step t + 1 and advanced the counter (tfm_decode embeds GO once)
   const bool fused_pick = beam == 0 && e->fuse_pick;
   if (!fused_pick) {
@@ -286,7 +184,7 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
   for (int l = 0; l < c.dec_layers; ++l) {
     const std::string p = PRED + "model.layers." + std::to_string(l) + ".";
     // element offset of layer l; a bf16 cache addresses 2-byte elements from the same base
-    const size_t kvdiv = kv_is_bf16(e) && !cluster ? 2 : 1;
+    const size_t kvdiv = kv_is_bf16(e) ? 2 : 1;
     float* selfkv = b.selfkv + (size_t)l * R * T * 2 * D / kvdiv;
     const float* crosskv = b.crosskv + (size_t)l * B * ntok * 2 * D / kvdiv;
     // self-attention: in_proj (q -> b.q, k|v -> cache slot t), attention over the prefix, out_proj + residual, norm1
@@ -365,7 +263,7 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
     // algorithmic bytes: the logits of every row, and the token + ancestry prefixes read from one buffer and written to the other
     DecTimer tm(e, true, 2, (double)R * V * 4 + 4.0 * R * (e->cur_step + 1) * 4, s);
     CUDA_TRY(e, launch_kernel(beam_step_kernel, dim3(B), dim3(256), (size_t)beam * V * sizeof(float), s, b.logits, st));
-  } else if (!cluster && e->fuse_pick) {
+  } else if (e->fuse_pick) {
     DecTimer tm(e, true, 3, (double)R * V * 4 * (want_logits ? 2 : 1) + (double)R * D * 4, s);
     CUDA_TRY(e, launch_kernel(greedy_pick_kernel, dim3(R), dim3(128), 0, s, b.logits, V, step, b.tokens, L, b.ids, T,
                               want_logits ? b.logits_out : nullptr, b.ended, b.counters + 1, b.counters + 2, R, TFM_END,
@@ -406,8 +304,7 @@ int alloc_group(d2t_engine* e, TfmGroup& grp, int ntok, int beam, int T, bool wa
   int rc;
   if ((rc = pool_get(e, &b.crosskv, (size_t)nl * B * ntok * 2 * D))) return rc;
   if ((rc = pool_get(e, &b.selfkv, (size_t)nl * R * T * 2 * D))) return rc;
-  if (cluster_step_active(e) && (rc = pool_get(e, &b.crosskv_tmp, (size_t)B * ntok * 2 * D))) return rc;
-  if (!cluster_step_active(e) && kv_is_bf16(e) && (rc = pool_get(e, &b.crosskv_f32, (size_t)B * ntok * 2 * D))) return rc;
+  if (kv_is_bf16(e) && (rc = pool_get(e, &b.crosskv_f32, (size_t)B * ntok * 2 * D))) return rc;
   if ((rc = pool_get(e, &b.x, (size_t)R * D))) return rc;
   b.x2_parts = 8;
   if ((rc = pool_get(e, &b.x2, (size_t)b.x2_parts * R * D))) return rc;
@@ -533,7 +430,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
       float* dst = grp.b.crosskv + (size_t)l * grp.Bg * ntok * 2 * D / (grp.b.crosskv_f32 ? 2 : 1);
       ConvGemm g = linear_params(ctx + (size_t)grp.B0 * ntok * D, e->dev[p + "in_proj_weight"] + (size_t)D * D,
                                  e->dev[p + "in_proj_bias"] + D,
-                                 grp.b.crosskv_tmp ? grp.b.crosskv_tmp : (grp.b.crosskv_f32 ? grp.b.crosskv_f32 : dst),
+                                 grp.b.crosskv_f32 ? grp.b.crosskv_f32 : dst,
                                  grp.Bg * ntok, 2 * D, D);
       if (int r = dec_linear(e, g, gs)) return r;
       if (grp.b.crosskv_f32) {   // bf16 KV cache
@@ -542,17 +439,11 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
         e->launches += 1;
         CUDA_TRY(e, cudaGetLastError());
       }
-      if (grp.b.crosskv_tmp) {   // cluster step: head-major [image][head][tok][K|V]
-        const long long total4 = (long long)grp.Bg * ntok * 128;
-        repack_cross_kv_kernel<<<grid_for(total4, 256, e->num_sms), 256, 0, gs>>>(grp.b.crosskv_tmp, dst, grp.Bg, ntok);
-        e->launches += 1;
-        CUDA_TRY(e, cudaGetLastError());
-      }
     }
     return 0;
   });
   if (rc) return rc;
-  if (beam == 0 && e->fuse_pick && !cluster_step_active(e)) {   // x of step 0 = embedding of GO; later steps: written by the pick kernel
+  if (beam == 0 && e->fuse_pick) {   // x of step 0 = embedding of GO; later steps: written by the pick kernel
     for (TfmGroup& grp : groups) {
       const TfmBuffers& b = grp.b;
       CUDA_TRY(e, launch_kernel(embed_tokens_kernel, dim3((grp.Rg * D / 4 + 255) / 256), dim3(256), 0, s, b.tokens, T + 1,
@@ -577,7 +468,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
       const void* ptrs[] = {b.crosskv, b.selfkv, b.x, b.x2, b.q, b.att, b.ffn, b.logits, b.counters, b.tokens, b.anc,
                             b.scores, b.n_live, b.n_done, b.finished, b.done_seq, b.done_len, b.done_score, b.trace,
                             b.trace_score, b.ended, b.ids, b.logits_out, b.dbg, b.x_hi, b.x_lo, b.att_hi, b.att_lo, b.ffn_hi, b.ffn_lo,
-                            b.crosskv_tmp, b.crosskv_f32, b.runner_up};
+                            b.crosskv_f32, b.runner_up};
       for (const void* q : ptrs) key.push_back((long long)(uintptr_t)q);
     }
     for (auto& g : e->graphs) if (g.key == key) { *exec_out = g.exec; *nodes_out = g.nodes; return 0; }
@@ -650,25 +541,7 @@ int tfm_decode(d2t_engine* e, const float* ctx, int B, int ntok, int beam, int m
   CUDA_TRY(e, cudaMemcpyAsync(e->h_counters, counters_all, (size_t)4 * G * sizeof(int), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(e, cudaStreamSynchronize(s));
   const int done_step = all_done_step();
-  if (groups[0].b.dbg && groups[0].b.crosskv_tmp) {
-    long long h[64];
-    cudaMemcpy(h, groups[0].b.dbg, sizeof h, cudaMemcpyDeviceToHost);
-    const int nl = c.dec_layers;
-    fprintf(stderr, "[cluster step dbg R=%d, last step] embed %lld ns; total %lld ns\n", groups[0].Rg, h[1] - h[0], h[2 + nl * 11] - h[0]);
-    static const char* names[11] = {"qkv", "self-attn+AG", "o1", "LN1+AG", "q2", "cross-attn+AG", "o2", "LN2+AG", "lin1", "lin2+RS", "LN3+AG"};
-    for (int l = 0; l < nl; ++l) {
-      fprintf(stderr, "  layer %d:", l);
-      long long prev = l == 0 ? h[1] : h[2 + (l - 1) * 11 + 10];
-      for (int k = 0; k < 11; ++k) { fprintf(stderr, " %s %lld", names[k], h[2 + l * 11 + k] - prev); prev = h[2 + l * 11 + k]; }
-      fprintf(stderr, "\n");
-    }
-    fprintf(stderr, "  vocab %lld\n", h[2 + nl * 11] - h[2 + (nl - 1) * 11 + 10]);
-    fprintf(stderr, "  layer 1 o2 MMA thread: operands seen +%lld, weights ready +%lld, all MMAs issued +%lld, accumulator complete +%lld (from operands_ready)\n",
-            h[57] - h[55], h[58] - h[55], h[59] - h[55], h[56] - h[55]);
-    fprintf(stderr, "  layer 1 detail: o2 wait_acc %lld, o2 epilogue %lld | LN2: cbar %lld, stats+stores %lld, handoff %lld, combine+cbar %lld, "
-                    "allgather+fence %lld, handoff %lld\n", h[56] - h[55], h[2 + 11 + 6] - h[56], h[49] - h[48], h[50] - h[49], h[51] - h[50],
-            h[52] - h[51], h[53] - h[52], h[54] - h[53]);
-  } else if (groups[0].b.dbg) {
+  if (groups[0].b.dbg) {
     long long h[12];
     cudaMemcpy(h, groups[0].b.dbg, sizeof h, cudaMemcpyDeviceToHost);
     fprintf(stderr, "[decode gemm dbg R=%d] prologue %lld ns, first full +%lld, last full +%lld, last commit +%lld, "

@@ -25,7 +25,6 @@
 #include "lstm_kernels.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc3.cuh"
-#include "decode_cluster.cuh"
 #include "preprocess_kernels.cuh"
 
 using namespace d2t;
@@ -136,12 +135,6 @@ struct d2t_engine {
   struct GraphEntry { std::vector<long long> key; cudaGraphExec_t exec = nullptr; int nodes = 0; };
   std::vector<GraphEntry> graphs;
   int* h_counters = nullptr;  // pinned [D2T_MAX_GROUPS][4]
-  // cluster-resident decode step (decode_cluster.cuh): one launch per step instead of the ~37-launch chain
-  ClusterStepPlan cs_plan;
-  // Off by default: measured 330 us per step against the chain's 292 us (B=256, step 99) — at N = 16/32 rows per cluster a
-  // tcgen05.mma retires every ~90 ns whatever its N, so the 48 MMAs of a K=256 bf16x3 projection cost as much as the
-  // chain's wide tiles, and the 40 cluster hand-offs per step add another ~60 us.
-  bool use_cluster_step = false;  // option "cluster_step"
   int decode_groups = 0;      // option "decode_groups": concurrent row groups of a decode call (0 = auto)
   cudaStream_t side[D2T_MAX_GROUPS] = {};   // side[g], g >= 1: stream of row group g (group 0 runs on `work`)
   cudaEvent_t ev_fork = nullptr, ev_join[D2T_MAX_GROUPS] = {};
@@ -164,7 +157,6 @@ static void drop_graphs(d2t_engine* e) {
 }
 
 int finalize_attn_extras(d2t_engine* e);
-int prepare_cluster_step(d2t_engine* e);
 
 #define CUDA_TRY(e, call)                                                                          \
   do {                                                                                             \
@@ -757,7 +749,6 @@ int d2t_finalize_weights(d2t_engine* e) {
         if ((rc = prep(e->dev[p + "linear2.weight"], D, c.dec_ff))) return rc;
       }
       if ((rc = prep(e->dev[PRED + "proj.weight"], c.vocab, D))) return rc;
-      if ((rc = prepare_cluster_step(e))) return rc;
     } else if (c.head == D2T_HEAD_ATTNV2 || c.head == D2T_HEAD_ATTN) {
       const int Hs = c.attn_hidden;
       const std::string a = PRED + "attention_cell.attn.";
@@ -819,8 +810,6 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
     e->steps_per_graph = value;
   } else if (k == "split_k") {
     e->split_k = value;
-  } else if (k == "cluster_step") {
-    e->use_cluster_step = value != 0;
   } else if (k == "pdl") {
     e->use_pdl = value != 0;
   } else if (k == "fuse_pick") {

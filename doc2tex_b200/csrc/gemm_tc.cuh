@@ -31,21 +31,6 @@ namespace d2t {
 // ------------------------------------------------------------------------------------------------
 namespace tc {
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// store two floats into the shared memory of CTA `rank` of this cluster (distributed shared memory)
-__device__ __forceinline__ void st_cluster_f32x2(uint32_t local_smem_addr, uint32_t rank, float a, float b) {
-  uint32_t remote;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local_smem_addr), "r"(rank));
-  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(remote), "f"(a), "f"(b) : "memory");
-}
 __device__ __noinline__ float4 gelu_erf4(float4 v) {
   return make_float4(gelu_erf(v.x), gelu_erf(v.y), gelu_erf(v.z), gelu_erf(v.w));
 }

@@ -165,7 +165,6 @@ int d2t_decode_attn_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, i
  *   "attn_split"       warps per (row, head) of the decode attention: 0 = auto, 1, 2
  *   "fuse_pick"        0/1 greedy pick also embeds the next token and advances the step counter (default 1)
  *   "kv_bf16"          0/1 bf16 KV caches in the single-pass bf16 mode (default 1; the fp32-parity modes always keep fp32)
- *   "cluster_step"     1 = experimental cluster-resident decode step kernel (decode_cluster.cuh; measured slower, default 0)
  *   "tc3"              0/1 stem convolutions fed from bf16 activation planes by cp.async (default 1)
  *   "lean_acts"        0/1 stem layers write only the representations their consumers read (default 1)
  *   "fuse_pool"        0/1 max-pools 1 and 2 fused into the producing convolution's epilogue (default 1)

@@ -670,3 +670,41 @@ def test_infer_cli_synthetic(built_lib, tmp_path):
         assert line in out.stdout
     text = log.read_text()
     assert "Trainable params num:" in text and "Total Infer Time:" in text
+
+
+def test_infer_cli_image_files(built_lib, tmp_path):
+    """api/infer.py on image FILES: grey crops of two sizes go through the GPU preprocessing (config: downsample 2, pad False),
+    are bucketed by their preprocessed (H, W) and decoded in batches; CSV rows and summary lines as in the reference."""
+    import os
+    import subprocess
+    import sys
+    from PIL import Image
+    from oracle import make_golden_helpers as mh
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    data = tmp_path / "images"
+    data.mkdir()
+    rows = ["id\tlabel"]
+    for k, (h, w) in enumerate([(128, 512), (128, 512), (192, 768), (128, 512), (192, 768)]):
+        Image.fromarray(mh.synth_crop(h, w, 6000 + k)).save(data / f"f{k}.png")
+        rows.append(f"f{k}.png\t\\tok1 \\tok2 \\tok3")
+    (tmp_path / "labels.tsv").write_text("\n".join(rows) + "\n")
+    import yaml
+    cfg = yaml.safe_load(open(os.path.join(root, "doc2tex_b200", "configs", "hybridvit_tfm.yaml")))
+    cfg["export_csv"] = True
+    vocab = tmp_path / "vocab.txt"
+    vocab.write_text("\n".join(synth.make_vocab()) + "\n")
+    cfg["vocab"] = str(vocab)
+    ckpt = tmp_path / "model.pth"
+    mcfg = synth.make_config("TFM")
+    torch.save({"model": synth.make_state_dict(mcfg, seed=1111, end_bias=1.5)}, ckpt)
+    cfg["saved_model"] = str(ckpt)
+    cfg_path = tmp_path / "cfg.yaml"
+    cfg_path.write_text(yaml.safe_dump(cfg))
+    log = tmp_path / "run.log"
+    out = subprocess.run([sys.executable, os.path.join(root, "api", "infer.py"), "--config", str(cfg_path), "--csv_dir",
+                          str(tmp_path / "labels.tsv"), "--data_dir", str(data), "--log_path", str(log), "--batch_size", "2"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "Acc:" in out.stdout and "Preprocess time:" in out.stdout
+    lines = (tmp_path / "run.csv").read_text().strip().splitlines()
+    assert len(lines) == 5 and {ln.split(",")[0] for ln in lines} == {f"f{k}.png" for k in range(5)}
