@@ -40,6 +40,10 @@ struct ConvGemm {
   int k_splits;            // 0 / 1 = no split
   int stack;               // bf16x3, TMA-fed-A path: 1 = two MMAs per k-step against the stacked [W_hi ; W_lo] operand (see gemm_tc.cuh)
   long long split_stride;  // elements between partial outputs
+  // fused 2x2 / stride-2 max-pool (conv_gemm_tc3_kernel only): row m of the GEMM addresses the pixels in WINDOW-major order
+  // (m = 4 * window + 2 * dy + dx), the epilogue reduces the four rows of a window after BN + ReLU and writes the pooled
+  // NHWC tensor [B, OH/2, OW/2, N] (planes and / or fp32).  OH and OW must be even.
+  int pool;
   // optional bf16 hi/lo NHWC planes of the INPUT activation (cp.async-fed A operand of conv_gemm_tc3_kernel)
   const __nv_bfloat16* x_hi;
   const __nv_bfloat16* x_lo;

@@ -353,8 +353,11 @@ bool routes_to_tc3(d2t_engine* e, const ConvGemm& p) {
   return w != e->tcw.end() && w->second.ready && w->second.N == p.N && w->second.K == p.K && m != e->tc3.end() && m->second.ready;
 }
 
+// pool = true: the 2x2 / stride-2 max-pool that follows this convolution is fused into its epilogue (tensor-core plane path
+// only; *pooled reports whether it was — the caller runs the stand-alone pool kernel otherwise).  y is then the POOLED map.
 int conv_layer(d2t_engine* e, const std::string& name, const Fmap& x, Fmap* y, int sh, int sw, int ph, int pw,
-               const Fmap* res, int act, cudaStream_t s, int oh_override = -1, int ow_override = -1, int need = NEED_BOTH) {
+               const Fmap* res, int act, cudaStream_t s, int oh_override = -1, int ow_override = -1, int need = NEED_BOTH,
+               bool pool = false, bool* pooled = nullptr) {
   auto it = e->conv.find(name);
   if (it == e->conv.end()) return e->fail(D2T_ERR_STATE, "conv '%s' not finalized", name.c_str());
   const ConvW& c = it->second;
@@ -369,6 +372,20 @@ int conv_layer(d2t_engine* e, const std::string& name, const Fmap& x, Fmap* y, i
   p.ldc = c.cout; p.ldc2 = 0; p.ldr = c.cout; p.n_split = c.cout;
   p.B = x.B; p.H = x.H; p.W = x.W; p.C = x.C; p.KH = c.kh; p.KW = c.kw; p.SH = sh; p.SW = sw; p.PH = ph; p.PW = pw;
   p.OH = OH; p.OW = OW; p.M = x.B * OH * OW; p.N = c.cout; p.K = c.kh * c.kw * c.cin; p.act = act;
+  if (pooled) *pooled = false;
+  if (pool && e->fuse_pool && !e->keep_taps && planes_mode && res == nullptr && OH % 2 == 0 && OW % 2 == 0) {
+    p.pool = 1;
+    if (routes_to_tc3(e, p)) {
+      // the pooled map feeds tensor-core convolutions only (block conv1 and the 1x1 downsample read the operand planes)
+      if (int rc = alloc_act(e, e->enc_pool, y, x.B, OH / 2, OW / 2, c.cout, true, false)) return rc;
+      p.out_hi = y->hi; p.out_lo = y->lo; p.out = y->p;
+      if (pooled) *pooled = true;
+      return run_contraction(e, p, nullptr, e->cfg.precision, s);
+    }
+    p.pool = 0;
+  }
+  if (p.x == nullptr && !routes_to_tc3(e, p))
+    return e->fail(D2T_ERR_STATE, "internal: conv '%s' reads an activation that exists as operand planes only", name.c_str());
   // the fp32 copy is dropped only when nobody reads it AND the kernel that will run tolerates its absence
   const bool want_f32 = (need & NEED_F32) || e->keep_taps || !want_planes || !e->lean_acts || !routes_to_tc3(e, p);
   if (int rc = alloc_act(e, e->enc_pool, y, x.B, OH, OW, c.cout, want_planes, want_f32)) return rc;
@@ -919,16 +936,28 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
     CUDA_TRY(e, cudaGetLastError());
     tap(e, "conv0_1", x);
   }
-  if ((rc = conv_layer(e, "conv0_2", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s, -1, -1, NEED_F32))) return rc;   // read by the max-pool
-  free_act(e, e->enc_pool, x); tap(e, "conv0_2", y);
-  if ((rc = pool_layer(e, y, &x, 2, 2, 0, 0, s))) return rc;
-  free_act(e, e->enc_pool, y);
+  bool pooled = false;
+  // conv0_2 + max-pool 1 (resnet.py:214-217): fused in the epilogue on the plane path, else the map is read by the pool kernel
+  if ((rc = conv_layer(e, "conv0_2", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s, -1, -1, NEED_F32, true, &pooled))) return rc;
+  free_act(e, e->enc_pool, x);
+  if (pooled) {
+    x = y; y = Fmap{};
+  } else {
+    tap(e, "conv0_2", y);
+    if ((rc = pool_layer(e, y, &x, 2, 2, 0, 0, s))) return rc;
+    free_act(e, e->enc_pool, y);
+  }
   if ((rc = basic_block(e, "layer1.0", x, s))) return rc;
   tap(e, "layer1", x);
-  if ((rc = conv_layer(e, "conv1", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s, -1, -1, NEED_F32))) return rc;
-  free_act(e, e->enc_pool, x); tap(e, "conv1", y);
-  if ((rc = pool_layer(e, y, &x, 2, 2, 0, 0, s))) return rc;
-  free_act(e, e->enc_pool, y);
+  if ((rc = conv_layer(e, "conv1", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s, -1, -1, NEED_F32, true, &pooled))) return rc;   // + max-pool 2
+  free_act(e, e->enc_pool, x);
+  if (pooled) {
+    x = y; y = Fmap{};
+  } else {
+    tap(e, "conv1", y);
+    if ((rc = pool_layer(e, y, &x, 2, 2, 0, 0, s))) return rc;
+    free_act(e, e->enc_pool, y);
+  }
   for (int b = 0; b < 2; ++b) if ((rc = basic_block(e, "layer2." + std::to_string(b), x, s))) return rc;
   tap(e, "layer2", x);
   if ((rc = conv_layer(e, "conv2", x, &y, 1, 1, 1, 1, nullptr, ACT_RELU, s, -1, -1, NEED_F32))) return rc;

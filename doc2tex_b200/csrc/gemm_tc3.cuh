@@ -134,6 +134,48 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
           *reinterpret_cast<uint4*>(stg + lane * TC_EPI_PITCH + q * 4) = make_uint4(r[q * 4], r[q * 4 + 1], r[q * 4 + 2], r[q * 4 + 3]);
         __syncwarp();
         const int n = tn * BN + j * 32 + c4;
+        if (p.pool) {
+          // rows 4 w .. 4 w + 3 of this 32-row chunk are the four pixels of pooling window w: BN scale / shift (the scale may
+          // be negative, so the affine comes first) + ReLU on each, then the maximum; lane (sub_r, c4) takes windows sub_r, sub_r + 4
+          if (n < N) {
+            float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + n));
+            if (shift) sh = __ldg(reinterpret_cast<const float4*>(shift + n));
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int w = sub_r + 4 * i;
+              const int m0 = tm * ROWS + h * TC_BM + quad * 32 + 4 * w;     // first GEMM row of the window
+              if (m0 < M) {
+                float4 best = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  float4 v = *reinterpret_cast<const float4*>(stg + (4 * w + u) * TC_EPI_PITCH + c4);
+                  v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+                  best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y); best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
+                }
+                if (act == ACT_RELU) {
+                  best.x = fmaxf(best.x, 0.f); best.y = fmaxf(best.y, 0.f); best.z = fmaxf(best.z, 0.f); best.w = fmaxf(best.w, 0.f);
+                }
+                const size_t o = (size_t)(m0 >> 2) * ldc + n;
+                if (out) *reinterpret_cast<float4*>(out + o) = best;
+                if (out_hi) {
+                  const float f[4] = {best.x, best.y, best.z, best.w};
+                  uint32_t hw[2], lw[2];
+#pragma unroll
+                  for (int u = 0; u < 2; ++u) {
+                    const __nv_bfloat16 h0 = __float2bfloat16_rn(f[2 * u]), h1 = __float2bfloat16_rn(f[2 * u + 1]);
+                    hw[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                    const __nv_bfloat16 l0 = __float2bfloat16_rn(f[2 * u] - __bfloat162float(h0));
+                    const __nv_bfloat16 l1 = __float2bfloat16_rn(f[2 * u + 1] - __bfloat162float(h1));
+                    lw[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+                  }
+                  *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(hw[0], hw[1]);
+                  if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(lw[0], lw[1]);
+                }
+              }
+            }
+          }
+        } else
         if (n < N) {
           float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), sh = make_float4(0.f, 0.f, 0.f, 0.f);
           if (scale) sc = __ldg(reinterpret_cast<const float4*>(scale + n));
@@ -202,10 +244,17 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
         const int m = tm * ROWS + r;
         ok[i] = m < p.M;
         const int mm = ok[i] ? m : 0;
-        const int ow = mm % p.OW;
-        const int t = mm / p.OW;
-        const int oh = t % p.OH;
-        const int b = t / p.OH;
+        int ow, oh, b;
+        if (p.pool) {   // window-major pixel order: m = 4 * (pooled pixel) + 2 * dy + dx
+          const int wdw = mm >> 2, qd = mm & 3, pw_ = p.OW >> 1, ph_ = p.OH >> 1;
+          const int px = wdw % pw_, t = wdw / pw_;
+          ow = 2 * px + (qd & 1); oh = 2 * (t % ph_) + (qd >> 1); b = t / ph_;
+        } else {
+          ow = mm % p.OW;
+          const int t = mm / p.OW;
+          oh = t % p.OH;
+          b = t / p.OH;
+        }
         ih0[i] = oh * p.SH - p.PH;
         iw0[i] = ow * p.SW - p.PW;
         base[i] = (long long)b * p.H * p.W * p.C;
@@ -329,6 +378,7 @@ inline cudaError_t tc3_prepare_maps(const TcWeight& w, Tc3Maps* out) {
 inline bool tc3_supported(const ConvGemm& p, int precision) {
   if (precision != 2 && precision != 3) return false;
   if (p.x_hi == nullptr || (precision == 2 && p.x_lo == nullptr)) return false;
+  if (p.pool && (p.res != nullptr || (p.OH & 1) || (p.OW & 1) || p.M % 4 != 0)) return false;
   return p.out2 == nullptr && p.a_map_hi == nullptr && p.C % 8 == 0 && p.K % 8 == 0 && p.ldc % 4 == 0 &&
          (p.res == nullptr || p.ldr % 4 == 0) && p.N % 4 == 0;
 }

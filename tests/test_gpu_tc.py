@@ -132,3 +132,26 @@ def test_bf16_mode_decode_tolerance(built_lib):
     err = ((l0 - l1).abs().amax(dim=2) / l0.abs().amax(dim=2).clamp_min(1e-6))[first]
     assert float(err.max()) < 5e-2, float(err.max())
     assert bool((bl == 40).all())
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("H,W", [(64, 256), (96, 384)])
+def test_fused_maxpool_is_bit_identical(built_lib, precision, H, W):
+    """Option fuse_pool: max-pools 1 and 2 (resnet.py:214-217, 222-225) run in the epilogue of conv0_2 / conv1 (window-major
+    pixel order, BN + ReLU on the four pixels, maximum, operand planes of the POOLED map only).  Same values, same order of
+    operations per element as conv -> fp32 map -> pool kernel: the encoder output must be bit-identical."""
+    from doc2tex_b200.engine import Engine
+    cfg, sd = state_dict_for("TFM", None)
+    e = Engine(cfg, "cuda:0", precision=precision)
+    e.load_state_dict(sd)
+    img = synth.make_images(3, H, W, seed=2024).cuda()
+    out = {}
+    for mode in (0, 1):
+        e.set_option("fuse_pool", mode)
+        l0 = e.launch_count()
+        ctx, _, _ = e.encode(img)
+        torch.cuda.synchronize()
+        out[mode] = (ctx.cpu(), e.launch_count() - l0)
+    e.close()
+    assert torch.equal(out[0][0], out[1][0])
+    assert out[0][1] - out[1][1] == 2      # two pool launches fewer
