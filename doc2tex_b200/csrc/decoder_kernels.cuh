@@ -71,60 +71,70 @@ __device__ __forceinline__ float4 kv_load4(const __nv_bfloat16* p) {
   return make_float4(fa.x, fa.y, fb.x, fb.y);
 }
 
+// 2^x in one MUFU.EX2 (the walk keeps its scores in log2 units: q is pre-scaled by log2(e) / sqrt(HD))
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // The key walk of one (row, head) by one warp: returns the warp-merged online-softmax state (every lane holds gm / sum,
 // lane c holds its 4 output channels summed over the four quarter warps).  A quarter warp takes KPI keys per iteration —
-// key j = g + 4 i + 4 KPI (sp + SPLIT it) — and issues all 2 KPI 16-byte loads before it touches any of them: the walk is
-// bound by memory latency x iterations, so the loads in flight per warp set its speed (KPI = 2: 13 dependent round trips
-// at step 100, KPI = 8: 4).  anc_r (beam search) may point to shared memory.
+// key j = g + 4 i + 4 KPI (sp + SPLIT it) — and issues all 2 KPI 16-byte loads before it touches any of them: with few
+// rows the walk is bound by memory latency x iterations, so the loads in flight per warp set its speed (KPI = 2: 13
+// dependent round trips at step 100, KPI = 4: 7).  With many rows (5 120 merged beam rows) it is bound by instruction
+// issue (ncu: 57 % of the issue slots busy, 1 687 instructions per warp), so the loop is kept lean: the trip count is
+// warp-uniform (full-mask shuffles: a partial-mask shuffle costs a WARPSYNC + collective bracket each), record offsets are
+// 32-bit relative to the image's first row, and the exponentials are single MUFU.EX2 on scores kept in log2 units.
+// anc_r (beam search): ancestry row of this hypothesis; src0 = first physical row of the image (or the row itself).
 template <int SPLIT, int KPI, typename KV>
 __device__ __forceinline__ void attention_walk(const float4 q4, const KV* __restrict__ kbase, long long row_stride,
-                                               int pos_stride, const int* anc_r, int src_base, int n_keys,
+                                               int pos_stride, const int* __restrict__ anc_r, int src_base, int n_keys,
                                                int g, int sp, int D, float& gm_out, float& sum_out, float4& acc_out) {
   float mx = -INFINITY, sum = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const unsigned gmask = 0xFFu << (g * 8);   // quarter warps run different trip counts: group-local shuffles
-  for (int j0 = g + 4 * KPI * sp; j0 < n_keys; j0 += 4 * KPI * SPLIT) {
-    const KV* p[KPI];
+  const KV* const kb = kbase + (size_t)src_base * row_stride;   // 64-bit once; per-key offsets fit 32 bits (<= 16 rows x T x 2D)
+  const int rs = (int)row_stride;
+  for (int jb = 4 * KPI * sp; jb < n_keys; jb += 4 * KPI * SPLIT) {   // warp-uniform
+    const int j0 = jb + g;
     float4 k[KPI], v[KPI];
     float d[KPI];
 #pragma unroll
     for (int i = 0; i < KPI; ++i) {
-      const int j = (j0 + 4 * i < n_keys) ? j0 + 4 * i : j0;
-      const int src = anc_r ? src_base + anc_r[j] : src_base;
-      p[i] = kbase + (size_t)src * row_stride + (size_t)j * pos_stride;
+      const int j = (j0 + 4 * i < n_keys) ? j0 + 4 * i : n_keys - 1;
+      const int off = (anc_r ? anc_r[j] * rs : 0) + j * pos_stride;
+      k[i] = kv_load4(kb + off);
+      v[i] = kv_load4(kb + off + D);
     }
-#pragma unroll
-    for (int i = 0; i < KPI; ++i) k[i] = kv_load4(p[i]);
-#pragma unroll
-    for (int i = 0; i < KPI; ++i) v[i] = kv_load4(p[i] + D);
 #pragma unroll
     for (int i = 0; i < KPI; ++i) d[i] = fmaf(q4.x, k[i].x, fmaf(q4.y, k[i].y, fmaf(q4.z, k[i].z, q4.w * k[i].w)));
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
 #pragma unroll
-      for (int i = 0; i < KPI; ++i) d[i] += __shfl_xor_sync(gmask, d[i], o);
+      for (int i = 0; i < KPI; ++i) d[i] += __shfl_xor_sync(0xffffffffu, d[i], o);
     }
-    float nm = mx;
+    if (j0 < n_keys) {     // a quarter warp without keys in this (last) iteration keeps its state
+      float nm = mx;
 #pragma unroll
-    for (int i = 0; i < KPI; ++i) {
-      if (j0 + 4 * i >= n_keys) d[i] = -INFINITY;
-      nm = fmaxf(nm, d[i]);
-    }
-    const float corr = expf(mx - nm);   // 0 on the first iteration (mx = -inf)
-    sum *= corr; acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
+      for (int i = 0; i < KPI; ++i) {
+        if (j0 + 4 * i >= n_keys) d[i] = -INFINITY;
+        nm = fmaxf(nm, d[i]);
+      }
+      const float corr = fast_exp2(mx - nm);   // 0 on the first iteration (mx = -inf)
+      sum *= corr; acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
 #pragma unroll
-    for (int i = 0; i < KPI; ++i) {
-      const float e = expf(d[i] - nm);
-      sum += e;
-      acc.x = fmaf(e, v[i].x, acc.x); acc.y = fmaf(e, v[i].y, acc.y); acc.z = fmaf(e, v[i].z, acc.z); acc.w = fmaf(e, v[i].w, acc.w);
+      for (int i = 0; i < KPI; ++i) {
+        const float e = fast_exp2(d[i] - nm);
+        sum += e;
+        acc.x = fmaf(e, v[i].x, acc.x); acc.y = fmaf(e, v[i].y, acc.y); acc.z = fmaf(e, v[i].z, acc.z); acc.w = fmaf(e, v[i].w, acc.w);
+      }
+      mx = nm;
     }
-    mx = nm;
   }
   // merge the four quarter-warp states
-  __syncwarp();
   float gm = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
   gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 16));
-  const float sc = (mx == -INFINITY) ? 0.f : expf(mx - gm);
+  const float sc = (mx == -INFINITY) ? 0.f : fast_exp2(mx - gm);
   sum *= sc; acc.x *= sc; acc.y *= sc; acc.z *= sc; acc.w *= sc;
 #pragma unroll
   for (int o = 8; o < 32; o <<= 1) {
@@ -143,12 +153,12 @@ __device__ __forceinline__ void attention_merge_splits(const float* __restrict__
   float M = gm;
 #pragma unroll
   for (int q = 0; q < SPLIT - 1; ++q) M = fmaxf(M, parts[q * 36]);
-  const float w0 = (gm == -INFINITY) ? 0.f : expf(gm - M);
+  const float w0 = (gm == -INFINITY) ? 0.f : fast_exp2(gm - M);   // the walk's maxima are in log2 units
   sum *= w0; acc.x *= w0; acc.y *= w0; acc.z *= w0; acc.w *= w0;
 #pragma unroll
   for (int q = 0; q < SPLIT - 1; ++q) {
     const float* pp = parts + q * 36;
-    const float wq = (pp[0] == -INFINITY) ? 0.f : expf(pp[0] - M);
+    const float wq = (pp[0] == -INFINITY) ? 0.f : fast_exp2(pp[0] - M);
     const float4 a = *reinterpret_cast<const float4*>(pp + 4 + c);
     sum = fmaf(wq, pp[1], sum);
     acc.x = fmaf(wq, a.x, acc.x); acc.y = fmaf(wq, a.y, acc.y); acc.z = fmaf(wq, a.z, acc.z); acc.w = fmaf(wq, a.w, acc.w);
@@ -194,7 +204,7 @@ decode_attention_kernel(const float* __restrict__ q, int ldq, const KV* __restri
   const int n_keys = n_fixed > 0 ? n_fixed : t + 1;
   const int* anc_r = anc ? anc + (anc_parity_stride ? (long long)(t & 1) * anc_parity_stride : 0) + (size_t)r * anc_ld : nullptr;
   const int src_base = (r / rows_per_src) * (anc ? rows_per_src : 1);
-  const float scale = rsqrtf((float)HD);
+  const float scale = rsqrtf((float)HD) * 1.4426950408889634f;   // scores in log2 units: softmax = 2^(s - max) / sum
   float4 q4 = *reinterpret_cast<const float4*>(q + (size_t)r * ldq + h * HD + c);
   q4.x *= scale; q4.y *= scale; q4.z *= scale; q4.w *= scale;
   float gm, sum;
