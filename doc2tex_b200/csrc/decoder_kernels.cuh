@@ -381,6 +381,7 @@ __global__ void set_go_tokens_kernel(int* tokens, int tok_ld, long long parity_s
 // The KV "reorder" is the rewrite of the ancestry table; tokens/anc are ping-ponged by step parity.
 // ---------------------------------------------------------------------------------------------
 constexpr int BEAM_MAX = 16;
+constexpr int BEAM_CPL = 16;   // beam_step fast path: candidates per lane held in registers (vocabulary <= 512)
 
 struct BeamState {
   int* tokens;          // [2][B*beam][L]
@@ -427,6 +428,89 @@ beam_step_kernel(const float* __restrict__ logits, BeamState st) {
   const int* anc_old = st.anc + (long long)(t & 1) * par + (size_t)img * beam * L;
   int* anc_new = st.anc + (long long)((t + 1) & 1) * par + (size_t)img * beam * L;
 
+  const int rounds = k + (st.runner_up != nullptr ? 1 : 0);   // one more when the near-tie audit wants the runner-up's score
+  if (V <= 32 * BEAM_CPL) {
+    // ---- fast path: a warp keeps the candidates of one live row in registers (BEAM_CPL per lane), takes the row's own
+    // top `rounds` with warp-level argmax rounds (no block barrier), and warp 0 merges the nlive x rounds survivors.
+    // Total order everywhere: value descending, flat index (row * V + word) ascending. ----
+    __shared__ float s_lv[BEAM_MAX * (BEAM_MAX + 1)];
+    __shared__ int s_li[BEAM_MAX * (BEAM_MAX + 1)];
+    for (int s = wid; s < nlive; s += nw) {
+      const float* x = logits + ((size_t)img * beam + s) * V;
+      float c[BEAM_CPL];
+      float mxr = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < BEAM_CPL; ++i) {
+        const int v = lane + 32 * i;
+        c[i] = v < V ? x[v] : -INFINITY;
+        mxr = fmaxf(mxr, c[i]);
+      }
+      mxr = warp_max(mxr);
+      float sm = 0.f;
+#pragma unroll
+      for (int i = 0; i < BEAM_CPL; ++i) sm += (lane + 32 * i < V) ? expf(c[i] - mxr) : 0.f;
+      sm = warp_sum(sm);
+      const float lse = logf(sm), base = st.scores[img * beam + s];
+#pragma unroll
+      for (int i = 0; i < BEAM_CPL; ++i) c[i] = (lane + 32 * i < V) ? base + ((c[i] - mxr) - lse) : -INFINITY;
+      for (int round = 0; round < rounds; ++round) {
+        float bv = -INFINITY; int bi = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < BEAM_CPL; ++i) {            // ascending word index: strict > keeps the lowest index on ties
+          if (c[i] > bv) { bv = c[i]; bi = lane + 32 * i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        if (lane == 0) { s_lv[s * (BEAM_MAX + 1) + round] = bv; s_li[s * (BEAM_MAX + 1) + round] = bi == 0x7fffffff ? bi : s * V + bi; }
+        if (bi != 0x7fffffff && (bi & 31) == lane) {     // the owner drops the winner
+#pragma unroll
+          for (int i = 0; i < BEAM_CPL; ++i) if (i == (bi >> 5)) c[i] = -INFINITY;
+        }
+      }
+    }
+    __syncthreads();
+    if (wid == 0) {
+      const int ncand = nlive * rounds;                   // <= 16 * 17 survivors
+      float c[(BEAM_MAX * (BEAM_MAX + 1) + 31) / 32];
+      int ci[(BEAM_MAX * (BEAM_MAX + 1) + 31) / 32];
+#pragma unroll
+      for (int i = 0; i < (BEAM_MAX * (BEAM_MAX + 1) + 31) / 32; ++i) {
+        const int e = lane + 32 * i;
+        const bool ok = e < ncand;
+        const int s = ok ? e / rounds : 0, r_ = ok ? e - s * rounds : 0;
+        c[i] = ok ? s_lv[s * (BEAM_MAX + 1) + r_] : -INFINITY;
+        ci[i] = ok ? s_li[s * (BEAM_MAX + 1) + r_] : 0x7fffffff;
+      }
+      for (int round = 0; round < rounds; ++round) {
+        float bv = -INFINITY; int bi = 0x7fffffff, bslot = -1;
+#pragma unroll
+        for (int i = 0; i < (BEAM_MAX * (BEAM_MAX + 1) + 31) / 32; ++i) {
+          if (c[i] > bv || (c[i] == bv && ci[i] < bi)) { bv = c[i]; bi = ci[i]; bslot = i; }
+        }
+        float wv = bv; int wi = bi;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, wv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, wi, o);
+          if (ov > wv || (ov == wv && oi < wi)) { wv = ov; wi = oi; }
+        }
+        if (lane == 0) {
+          if (round < k) { top_v[round] = wv; top_i[round] = wi; }
+          else st.runner_up[(size_t)img * st.max_steps + t] = wv;
+        }
+        if (bslot >= 0 && wi == bi && wv == bv && wi != 0x7fffffff) {   // flat indices are unique: exactly one lane owns it
+#pragma unroll
+          for (int i = 0; i < (BEAM_MAX * (BEAM_MAX + 1) + 31) / 32; ++i) if (i == bslot) { c[i] = -INFINITY; ci[i] = 0x7fffffff; }
+        }
+      }
+    }
+    __syncthreads();
+  } else {
+  // ---- generic path (large vocabularies): candidates in shared memory, block-wide argmax rounds ----
   // log-softmax per live row (warp per row): lp = (x - max) - log(sum exp(x - max))
   for (int s = wid; s < nlive; s += nw) {
     const float* x = logits + ((size_t)img * beam + s) * V;
@@ -446,8 +530,7 @@ beam_step_kernel(const float* __restrict__ logits, BeamState st) {
     s_cand[i] = st.scores[img * beam + s] + lp;
   }
   __syncthreads();
-  // k rounds of block-wide argmax (value desc, index asc); one more when the near-tie audit wants the runner-up's score
-  const int rounds = k + (st.runner_up != nullptr ? 1 : 0);
+  // `rounds` rounds of block-wide argmax (value desc, index asc)
   for (int round = 0; round < rounds; ++round) {
     float bv = -INFINITY; int bi = 0x7fffffff;
     for (int i = threadIdx.x; i < ncand; i += blockDim.x) {
@@ -470,6 +553,7 @@ beam_step_kernel(const float* __restrict__ logits, BeamState st) {
       if (bi != 0x7fffffff) s_cand[bi] = -INFINITY;  // exclude from later rounds
     }
     __syncthreads();
+  }
   }
   // process candidates in top-k order
   if (threadIdx.x == 0) {
