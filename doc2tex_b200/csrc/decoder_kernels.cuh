@@ -80,58 +80,58 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 // The key walk of one (row, head) by one warp: returns the warp-merged online-softmax state (every lane holds gm / sum,
 // lane c holds its 4 output channels summed over the four quarter warps).  A quarter warp takes KPI keys per iteration —
-// key j = g + 4 i + 4 KPI (sp + SPLIT it) — and issues all 2 KPI 16-byte loads before it touches any of them: with few
-// rows the walk is bound by memory latency x iterations, so the loads in flight per warp set its speed (KPI = 2: 13
-// dependent round trips at step 100, KPI = 4: 7).  With many rows (5 120 merged beam rows) it is bound by instruction
-// issue (ncu: 57 % of the issue slots busy, 1 687 instructions per warp), so the loop is kept lean: the trip count is
-// warp-uniform (full-mask shuffles: a partial-mask shuffle costs a WARPSYNC + collective bracket each), record offsets are
-// 32-bit relative to the image's first row, and the exponentials are single MUFU.EX2 on scores kept in log2 units.
-// anc_r (beam search): ancestry row of this hypothesis; src0 = first physical row of the image (or the row itself).
+// key j = g + 4 i + 4 KPI (sp + SPLIT it) — and issues all 2 KPI 16-byte loads before it touches any of them: the walk is
+// bound by memory latency x iterations, so the loads in flight per warp set its speed (KPI = 2: 13 dependent round trips
+// at step 100, KPI = 4: 7).  The pointer array / K loads / V loads are three separate unrolled loops ON PURPOSE: written
+// any other way tried (one loop; a warp-uniform trip count with a branch or with selects around the update) nvcc sinks the
+// value loads below the score shuffles, every iteration pays two dependent round trips and the kernel is 20 % slower
+// (ncu at 5 120 rows: 136.9 vs 115.8 us) although it executes 14 % fewer instructions.
 template <int SPLIT, int KPI, typename KV>
 __device__ __forceinline__ void attention_walk(const float4 q4, const KV* __restrict__ kbase, long long row_stride,
-                                               int pos_stride, const int* __restrict__ anc_r, int src_base, int n_keys,
+                                               int pos_stride, const int* anc_r, int src_base, int n_keys,
                                                int g, int sp, int D, float& gm_out, float& sum_out, float4& acc_out) {
   float mx = -INFINITY, sum = 0.f;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const KV* const kb = kbase + (size_t)src_base * row_stride;   // 64-bit once; per-key offsets fit 32 bits (<= 16 rows x T x 2D)
-  const int rs = (int)row_stride;
-  for (int jb = 4 * KPI * sp; jb < n_keys; jb += 4 * KPI * SPLIT) {   // warp-uniform
-    const int j0 = jb + g;
+  const unsigned gmask = 0xFFu << (g * 8);   // quarter warps run different trip counts: group-local shuffles
+  for (int j0 = g + 4 * KPI * sp; j0 < n_keys; j0 += 4 * KPI * SPLIT) {
+    const KV* p[KPI];
     float4 k[KPI], v[KPI];
     float d[KPI];
 #pragma unroll
     for (int i = 0; i < KPI; ++i) {
-      const int j = (j0 + 4 * i < n_keys) ? j0 + 4 * i : n_keys - 1;
-      const int off = (anc_r ? anc_r[j] * rs : 0) + j * pos_stride;
-      k[i] = kv_load4(kb + off);
-      v[i] = kv_load4(kb + off + D);
+      const int j = (j0 + 4 * i < n_keys) ? j0 + 4 * i : j0;
+      const int src = anc_r ? src_base + anc_r[j] : src_base;
+      p[i] = kbase + (size_t)src * row_stride + (size_t)j * pos_stride;
     }
+#pragma unroll
+    for (int i = 0; i < KPI; ++i) k[i] = kv_load4(p[i]);
+#pragma unroll
+    for (int i = 0; i < KPI; ++i) v[i] = kv_load4(p[i] + D);
 #pragma unroll
     for (int i = 0; i < KPI; ++i) d[i] = fmaf(q4.x, k[i].x, fmaf(q4.y, k[i].y, fmaf(q4.z, k[i].z, q4.w * k[i].w)));
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
 #pragma unroll
-      for (int i = 0; i < KPI; ++i) d[i] += __shfl_xor_sync(0xffffffffu, d[i], o);
+      for (int i = 0; i < KPI; ++i) d[i] += __shfl_xor_sync(gmask, d[i], o);
     }
-    if (j0 < n_keys) {     // a quarter warp without keys in this (last) iteration keeps its state
-      float nm = mx;
+    float nm = mx;
 #pragma unroll
-      for (int i = 0; i < KPI; ++i) {
-        if (j0 + 4 * i >= n_keys) d[i] = -INFINITY;
-        nm = fmaxf(nm, d[i]);
-      }
-      const float corr = fast_exp2(mx - nm);   // 0 on the first iteration (mx = -inf)
-      sum *= corr; acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
-#pragma unroll
-      for (int i = 0; i < KPI; ++i) {
-        const float e = fast_exp2(d[i] - nm);
-        sum += e;
-        acc.x = fmaf(e, v[i].x, acc.x); acc.y = fmaf(e, v[i].y, acc.y); acc.z = fmaf(e, v[i].z, acc.z); acc.w = fmaf(e, v[i].w, acc.w);
-      }
-      mx = nm;
+    for (int i = 0; i < KPI; ++i) {
+      if (j0 + 4 * i >= n_keys) d[i] = -INFINITY;
+      nm = fmaxf(nm, d[i]);
     }
+    const float corr = fast_exp2(mx - nm);   // 0 on the first iteration (mx = -inf)
+    sum *= corr; acc.x *= corr; acc.y *= corr; acc.z *= corr; acc.w *= corr;
+#pragma unroll
+    for (int i = 0; i < KPI; ++i) {
+      const float e = fast_exp2(d[i] - nm);
+      sum += e;
+      acc.x = fmaf(e, v[i].x, acc.x); acc.y = fmaf(e, v[i].y, acc.y); acc.z = fmaf(e, v[i].z, acc.z); acc.w = fmaf(e, v[i].w, acc.w);
+    }
+    mx = nm;
   }
   // merge the four quarter-warp states
+  __syncwarp();
   float gm = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 8));
   gm = fmaxf(gm, __shfl_xor_sync(0xffffffffu, gm, 16));
   const float sc = (mx == -INFINITY) ? 0.f : fast_exp2(mx - gm);
