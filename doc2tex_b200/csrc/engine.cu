@@ -104,6 +104,7 @@ struct d2t_engine {
   SlotPool enc_pool, dec_pool;
   bool keep_taps = false;
   bool use_pdl = true;   // option "pdl": programmatic dependent launch in the decode step
+  int pdl_max_rows = 2560;   // option "pdl_max_rows": decode calls with more rows launch without it
   bool use_tc3 = true;   // option "tc3": stem convolutions fed from bf16 activation planes by cp.async
   // ViTEncoder (fix_embed: False, interpolate_embed: True): pos_embed is resampled bicubically to the grid of each image
   // size (vit_encoder.py:58-95) — options "pos_interpolate", "pos_grid_h", "pos_grid_w"; tables cached per grid
@@ -827,6 +828,8 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
     e->steps_per_graph = value;
   } else if (k == "split_k") {
     e->split_k = value;
+  } else if (k == "pdl_max_rows") {
+    e->pdl_max_rows = value;
   } else if (k == "pdl") {
     e->use_pdl = value != 0;
   } else if (k == "fuse_pick") {

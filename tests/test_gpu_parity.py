@@ -708,3 +708,28 @@ def test_infer_cli_image_files(built_lib, tmp_path):
     assert "Acc:" in out.stdout and "Preprocess time:" in out.stdout
     lines = (tmp_path / "run.csv").read_text().strip().splitlines()
     assert len(lines) == 5 and {ln.split(",")[0] for ln in lines} == {f"f{k}.png" for k in range(5)}
+
+
+def test_large_vocabulary_beam_matches_oracle(built_lib):
+    """Vocabularies above 512 classes take beam_step_kernel's generic path (candidates in shared memory, block-wide argmax
+    rounds) instead of the register path: beam-5 and greedy against the CPU oracle with num_class 700."""
+    from doc2tex_b200.engine import Engine
+    from oracle import oracle_model as om
+    cfg = synth.make_config("TFM", num_class=700)
+    sd = synth.make_state_dict(cfg, seed=1111, end_bias=0.9)   # 151 steps, hypotheses complete at different steps (k shrinks 5 -> 1); margins >= 300 ulp
+    e = Engine(cfg, "cuda:0", precision="fp32")
+    e.load_state_dict(sd)
+    img = synth.make_images(3, 64, 256, seed=2024)
+    ctx, _, _ = e.encode(img.cuda())
+    ctx_or, _, _ = om.encoder_forward(sd, img)
+    head = om.TFMHead(sd, max_seq_len=150)
+    ids, logits, steps = e.decode_greedy(ctx, max_steps=10, is_test=False)
+    _, logits_or, gen_or = head.greedy(ctx_or, is_test=False, max_steps=10)
+    assert torch.equal(ids.cpu(), gen_or) and logits.shape[-1] == 700
+    bids, blen, bscore, _, _, _ = e.decode_beam(ctx, 5)
+    for i in range(3):
+        seq, sc = head.beam(ctx_or[i:i + 1], 5)
+        n = int(blen[i])
+        assert bids[i, :n].cpu().tolist() == seq, i
+        assert abs(float(bscore[i]) - sc) <= REL_TOL_FP32 * max(1.0, abs(sc))
+    e.close()

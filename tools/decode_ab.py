@@ -25,7 +25,7 @@ eng.load_state_dict(sd)
 img = synth.make_images(256, 64, 256, seed=2024).cuda()
 ctx, _, _ = eng.encode(img)
 
-BASE = {"stack_mma": 1, "steps_per_graph": 8, "attn_split": 0, "attn_kpi": 4, "split_k": 1, "pdl": 1}
+BASE = {"stack_mma": 1, "steps_per_graph": 8, "attn_split": 0, "attn_kpi": 4, "split_k": 1, "pdl": 1, "pdl_max_rows": 2560}
 SETS = [
     ("default", {}),
     ("attn_kpi 2", {"attn_kpi": 2}),
@@ -34,8 +34,9 @@ SETS = [
     ("1 step per graph", {"steps_per_graph": 1}),
     ("split_k 0", {"split_k": 0}),
     ("pdl 0", {"pdl": 0}),
+    ("pdl at any size", {"pdl_max_rows": 1 << 30}),
 ]
-WORK = [("greedy", 32), ("greedy", 256), ("greedy", 1024), ("beam", 32), ("beam", 256), ("beam", 1024)]
+WORK = [("greedy", 32), ("greedy", 256), ("greedy", 1024), ("greedy", 2048), ("beam", 32), ("beam", 256), ("beam", 512), ("beam", 1024)]
 
 
 def run(mode, n):
