@@ -20,6 +20,15 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint3
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+// TMA im2col load (NHWC tensor map built by cuTensorMapEncodeIm2col): `pixelsPerColumn` consecutive output pixels, starting
+// at the filter's base position (w, h) of image n and walking the bounding box row-major, x `channelsPerPixel` channels from
+// channel c, for the filter tap (kw, kh); out-of-image taps are zero-filled — the padding of the convolution.
+__device__ __forceinline__ void tma_load_im2col_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c, int w, int h, int n,
+                                                   uint16_t kw, uint16_t kh) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(kw), "h"(kh) : "memory");
+}
 // K-major operand tile with 64-byte rows and 64B swizzle: 8-row atoms of 512 B
 __device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
   uint64_t d = 0;
@@ -57,10 +66,15 @@ struct Tc3Cfg {
   static_assert(MT == 1 || MT == 2, "MT");
 };
 
-template <int PASSES, int BN, int MT>
+// A_TMA: the activation operand arrives by TMA im2col loads of the bf16 NHWC planes (one instruction per 128-pixel tile,
+// plane and k-block, issued by the TMA thread next to the weight tile; hardware zero-fill = the convolution's padding)
+// instead of the producer warps' cp.async gather — both operands are then "fed by TMA" and the eight producer warps idle.
+// Stride-1 convolutions with symmetric padding and C % 32 == 0 in row-major pixel order (not the fused-pool order).
+template <int PASSES, int BN, int MT, bool A_TMA = false>
 __global__ void __launch_bounds__(Tc3Cfg<PASSES, BN, MT>::THREADS, 1)
 conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_hi,
-                     const __grid_constant__ CUtensorMap map_lo, int tiles_m, int tiles_n) {
+                     const __grid_constant__ CUtensorMap map_lo, int tiles_m, int tiles_n,
+                     const __grid_constant__ CUtensorMap amap_hi, const __grid_constant__ CUtensorMap amap_lo) {
   using Cfg = Tc3Cfg<PASSES, BN, MT>;
   constexpr int ROWS = MT * TC_BM;                          // output rows per CTA tile
   constexpr int STAGES = Cfg::STAGES, PLANES = Cfg::PLANES;
@@ -83,7 +97,7 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      tc::mbar_init(full_bar(s), TC_PROD_THREADS + 1);   // 256 cp.async completion arrivals + the TMA thread's expect_tx
+      tc::mbar_init(full_bar(s), A_TMA ? 1 : TC_PROD_THREADS + 1);   // 256 cp.async completion arrivals + the TMA thread's expect_tx
       tc::mbar_init(empty_bar(s), 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -96,6 +110,10 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
   if (warp == TMA_WARP && lane == 0) {
     tc::tma_prefetch_desc(&map_hi);
     if (PLANES == 2) tc::tma_prefetch_desc(&map_lo);
+    if (A_TMA) {
+      tc::tma_prefetch_desc(&amap_hi);
+      if (PLANES == 2) tc::tma_prefetch_desc(&amap_lo);
+    }
   }
   tc::tcgen05_before_sync();
   __syncthreads();
@@ -225,6 +243,7 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
   } else if (warp < TMA_WARP) {
     // =========================== A producers: cp.async from the bf16 NHWC planes ===========================
     // ROWS rows x 4 chunks (16 B) per plane and k-block: 2 * MT rows per thread.
+    if constexpr (!A_TMA) {
     constexpr int RPT = 2 * MT;
     const int pt = threadIdx.x - EPI_WARPS * 32;   // 0..255
     const int chunk = pt & 3;                      // 16-byte chunk of the 64-byte operand row
@@ -281,16 +300,45 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    }  // !A_TMA
   } else if (warp == TMA_WARP) {
-    // =========================== W producer (TMA, 64-byte rows) ===========================
+    // =========================== W producer (TMA, 64-byte rows) [+ the A operand by TMA im2col] ===========================
     if (lane == 0) {
       int kit = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
+        int aw[MT], ah[MT], an[MT];
+        if constexpr (A_TMA) {
+#pragma unroll
+          for (int h = 0; h < MT; ++h) {   // base filter position of the first pixel of m-tile h
+            const int m0 = tm * ROWS + h * TC_BM;
+            const int ow = m0 % p.OW, t = m0 / p.OW;
+            aw[h] = ow * p.SW - p.PW; ah[h] = (t % p.OH) * p.SH - p.PH; an[h] = t / p.OH;
+          }
+        }
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
           const int s = kit % STAGES;
           tc::mbar_wait(empty_bar(s), ((kit / STAGES) & 1) ^ 1);
-          tc::mbar_arrive_expect_tx(full_bar(s), PLANES * Cfg::B_BYTES);
+          int a_tiles = 0;   // m-tiles of this CTA tile that hold pixels (the second half of a ragged MT = 2 tile may be empty)
+          if constexpr (A_TMA) {
+#pragma unroll
+            for (int h = 0; h < MT; ++h) a_tiles += an[h] < p.B ? 1 : 0;
+          }
+          tc::mbar_arrive_expect_tx(full_bar(s), PLANES * (Cfg::B_BYTES + a_tiles * Cfg::A_HALF_BYTES));
+          if constexpr (A_TMA) {
+            const int k = kb * Cfg::KB_ELEMS;
+            const int tap = k / p.C, ci = k - tap * p.C;
+            const int kh = tap / p.KW, kw = tap - kh * p.KW;
+            const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
+#pragma unroll
+            for (int h = 0; h < MT; ++h) {
+              if (an[h] < p.B) {
+                tc::tma_load_im2col_4d(a_hi + h * Cfg::A_HALF_BYTES, &amap_hi, full_bar(s), ci, aw[h], ah[h], an[h], (uint16_t)kw, (uint16_t)kh);
+                if (PLANES == 2)
+                  tc::tma_load_im2col_4d(a_hi + Cfg::A_BYTES + h * Cfg::A_HALF_BYTES, &amap_lo, full_bar(s), ci, aw[h], ah[h], an[h], (uint16_t)kw, (uint16_t)kh);
+              }
+            }
+          }
           const uint32_t b_hi = smem_base + s * Cfg::STAGE_BYTES + PLANES * Cfg::A_BYTES;
           tc::tma_load_2d(b_hi, &map_hi, full_bar(s), kb * Cfg::KB_ELEMS, tn * BN);
           if (PLANES == 2) tc::tma_load_2d(b_hi + Cfg::B_BYTES, &map_lo, full_bar(s), kb * Cfg::KB_ELEMS, tn * BN);
@@ -383,10 +431,66 @@ inline bool tc3_supported(const ConvGemm& p, int precision) {
          (p.res == nullptr || p.ldr % 4 == 0) && p.N % 4 == 0;
 }
 
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeIm2col tc3_encode_im2col_fn() {
+  static PFN_encodeIm2col fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &ptr, cudaEnableDefault, &q) == cudaSuccess && ptr) fn = (PFN_encodeIm2col)ptr;
+  }
+  return fn;
+}
+
+// The activation operand by TMA im2col: stride 1, symmetric padding, whole k-blocks inside one filter tap, row-major pixels.
+inline bool tc3_a_tma_supported(const ConvGemm& p) {
+  return !p.pool && p.SH == 1 && p.SW == 1 && p.PH == p.PW && p.KH == p.KW && p.C % 32 == 0 && p.PH < 128 &&
+         p.OH == p.H + 2 * p.PH - p.KH + 1 && p.OW == p.W + 2 * p.PW - p.KW + 1 && tc3_encode_im2col_fn() != nullptr;
+}
+
+// Tensor map over one bf16 NHWC plane [B, H, W, C]: bounding box of the filter's base position = [-pad, dim + pad - k],
+// 32 channels (one 64-byte operand row) x 128 pixels per load, 64B swizzle = the layout the UMMA descriptor reads.
+inline cudaError_t tc3_make_a_map(const __nv_bfloat16* plane, const ConvGemm& p, CUtensorMap* out) {
+  const cuuint64_t gdim[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
+  const cuuint64_t gstr[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.H * p.W * p.C * 2};
+  const int lower[2] = {-p.PW, -p.PH};
+  const int upper[2] = {p.PW - (p.KW - 1), p.PH - (p.KH - 1)};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = tc3_encode_im2col_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(plane), gdim, gstr, lower,
+                                      upper, 32, TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
+inline bool& tc3_use_a_tma() {
+  static bool on = true;
+  return on;
+}
+
 template <int PASSES, int BN, int MT = 1>
 inline cudaError_t tc3_launch_one(const ConvGemm& p, const Tc3Maps& m, cudaStream_t s, int num_sms) {
   using Cfg = Tc3Cfg<PASSES, BN, MT>;
-  static bool attr_set = false;
+  static bool attr_set = false, attr_set_t = false;
+  const int tiles_m_ = (p.M + MT * TC_BM - 1) / (MT * TC_BM), tiles_n_ = (p.N + BN - 1) / BN;
+  constexpr int mi_ = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
+  if (tc3_use_a_tma() && tc3_a_tma_supported(p)) {
+    auto kern_t = conv_gemm_tc3_kernel<PASSES, BN, MT, true>;
+    if (!attr_set_t) {
+      cudaError_t st = cudaFuncSetAttribute(kern_t, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+      if (st != cudaSuccess) return st;
+      attr_set_t = true;
+    }
+    CUtensorMap ah, al;
+    cudaError_t st = tc3_make_a_map(p.x_hi, p, &ah);
+    if (st != cudaSuccess) return st;
+    al = ah;
+    if (PASSES == 3 && (st = tc3_make_a_map(p.x_lo, p, &al)) != cudaSuccess) return st;
+    const int grid_t = tiles_m_ * tiles_n_ < num_sms ? tiles_m_ * tiles_n_ : num_sms;
+    return launch_kernel(kern_t, dim3(grid_t), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, p, m.hi[mi_], m.lo[mi_], tiles_m_, tiles_n_, ah, al);
+  }
   auto kern = conv_gemm_tc3_kernel<PASSES, BN, MT>;
   if (!attr_set) {
     cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
@@ -396,7 +500,7 @@ inline cudaError_t tc3_launch_one(const ConvGemm& p, const Tc3Maps& m, cudaStrea
   const int tiles_m = (p.M + MT * TC_BM - 1) / (MT * TC_BM), tiles_n = (p.N + BN - 1) / BN;
   const int grid = tiles_m * tiles_n < num_sms ? tiles_m * tiles_n : num_sms;
   constexpr int mi = BN == 64 ? 0 : (BN == 128 ? 1 : 2);
-  return launch_kernel(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, p, m.hi[mi], m.lo[mi], tiles_m, tiles_n);
+  return launch_kernel(kern, dim3(grid), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, s, p, m.hi[mi], m.lo[mi], tiles_m, tiles_n, m.hi[mi], m.lo[mi]);
 }
 
 inline cudaError_t launch_conv_gemm_tc3(const ConvGemm& p, const Tc3Maps& m, int precision, cudaStream_t s, int num_sms) {
