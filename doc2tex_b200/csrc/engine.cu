@@ -106,7 +106,7 @@ struct d2t_engine {
   bool keep_taps = false;
   bool use_pdl = true;   // option "pdl": programmatic dependent launch in the decode step
   int pdl_max_rows = 2560;   // option "pdl_max_rows": decode calls with more rows launch without it
-  int use_pair = 0;      // option "pair": CTA-pair (cta_group::2) kernel for the wide stem convolutions (see run_contraction)
+  int use_pair = 2;      // option "pair": CTA-pair (cta_group::2) kernel for the wide stem convolutions (see run_contraction)
   bool use_tc3 = true;   // option "tc3": stem convolutions fed from bf16 activation planes by cp.async
   // ViTEncoder (fix_embed: False, interpolate_embed: True): pos_embed is resampled bicubically to the grid of each image
   // size (vit_encoder.py:58-95) — options "pos_interpolate", "pos_grid_h", "pos_grid_w"; tables cached per grid
@@ -288,7 +288,7 @@ int run_contraction(d2t_engine* e, const ConvGemm& p, const TcWeight* tcw, int p
         // large 256-multiple-wide convolutions: CTA pair with both operands by TMA (option "pair": 0 never, 1 single-pass bf16
         // only — where shared-memory bandwidth bounds the single-CTA kernel —, 2 also the 3-pass parity mode)
         if (e->use_pair && (precision == D2T_PREC_BF16 || e->use_pair >= 2) && tc3_use_a_tma() && tc5_supported(p, precision, e->active_sms)) {
-          cudaError_t st5 = launch_conv_gemm_tc5(p, m3->second, precision, s, e->active_sms);
+          cudaError_t st5 = launch_conv_gemm_tc5(p, *tcw, precision, s, e->active_sms);
           if (st5 != cudaSuccess) return e->fail(D2T_ERR_CUDA, "CTA-pair contraction launch failed: %s", cudaGetErrorString(st5));
           e->launches += 1;
           return 0;

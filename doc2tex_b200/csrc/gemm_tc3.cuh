@@ -453,14 +453,15 @@ inline bool tc3_a_tma_supported(const ConvGemm& p) {
 
 // Tensor map over one bf16 NHWC plane [B, H, W, C]: bounding box of the filter's base position = [-pad, dim + pad - k],
 // 32 channels (one 64-byte operand row) x 128 pixels per load, 64B swizzle = the layout the UMMA descriptor reads.
-inline cudaError_t tc3_make_a_map(const __nv_bfloat16* plane, const ConvGemm& p, CUtensorMap* out) {
+inline cudaError_t tc3_make_a_map(const __nv_bfloat16* plane, const ConvGemm& p, CUtensorMap* out, int channels = 32) {
   const cuuint64_t gdim[4] = {(cuuint64_t)p.C, (cuuint64_t)p.W, (cuuint64_t)p.H, (cuuint64_t)p.B};
   const cuuint64_t gstr[3] = {(cuuint64_t)p.C * 2, (cuuint64_t)p.W * p.C * 2, (cuuint64_t)p.H * p.W * p.C * 2};
   const int lower[2] = {-p.PW, -p.PH};
   const int upper[2] = {p.PW - (p.KW - 1), p.PH - (p.KH - 1)};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = tc3_encode_im2col_fn()(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(plane), gdim, gstr, lower,
-                                      upper, 32, TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                                      upper, (cuuint32_t)channels, TC_BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      channels == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }

@@ -40,23 +40,15 @@ __device__ __forceinline__ uint32_t leader_addr(uint32_t local_addr) {
   return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ uint32_t mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n.reg .pred p;\n"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n}\n"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok;
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-  while (!mbar_try_wait_cluster(bar, parity)) {}
-}
+// Waits on barriers that the other CTA of the pair arrives on use the ordinary (CTA-scope) try_wait: a .cluster-scope acquire
+// costs an L1 invalidate (CCTL.IVALL) per poll and a .cluster-scope release on the arrive a memory barrier (ERRBAR) per
+// k-block — ncu showed the first build of this kernel spending its time in exactly those (profiles/r02b_ncu_conv_tc5_*);
+// what the barriers order here travels through the async proxy (TMA bytes, tcgen05 commits), not through generic loads.
 // TMA loads into THIS CTA's shared memory whose transaction bytes are counted on the LEADER CTA's mbarrier
 __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile(
@@ -97,9 +89,12 @@ template <int PASSES>
 struct Tc5Cfg {
   static constexpr int PLANES = PASSES == 1 ? 1 : 2;
   static constexpr int BN = 256;                       // columns per pair
-  static constexpr int KB_ELEMS = 32;
-  static constexpr int A_BYTES = TC_BM * 64;           // per plane: this CTA's 128 pixel rows
-  static constexpr int B_BYTES = 128 * 64;             // per plane: this CTA's 128 weight rows
+  // 128-byte operand rows (64 channels of one filter tap, 128B swizzle): the TMA unit moves one ROW per request, so the
+  // 64-byte rows of the single-CTA kernel cost twice the requests per byte (measured: encoder 21.5 ms with 32-element
+  // k-blocks here)
+  static constexpr int KB_ELEMS = 64;
+  static constexpr int A_BYTES = TC_BM * 128;          // per plane: this CTA's 128 pixel rows
+  static constexpr int B_BYTES = 128 * 128;            // per plane: this CTA's 128 weight rows
   static constexpr int STAGE_BYTES = PLANES * (A_BYTES + B_BYTES);
   static constexpr int EPI_WARPS = 4, THREADS = (EPI_WARPS + 2) * 32;
   static constexpr int EPI_STAGE_BYTES = EPI_WARPS * 32 * TC_EPI_PITCH * 4;
@@ -270,24 +265,29 @@ conv_gemm_tc5_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
       int kit = 0, it = 0;
       for (int tile = pair; tile < num_tiles; tile += num_pairs, ++it) {
         const int acc = it & 1;
-        tc::mbar_wait_cluster(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
+        tc::mbar_wait(tempty_bar(acc), ((it >> 1) & 1) ^ 1);
         tc::tcgen05_after_sync();
         const uint32_t d = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < nkb; ++kb, ++kit) {
           const int s = kit % STAGES;
-          tc::mbar_wait_cluster(full_bar(s), (kit / STAGES) & 1);
+          tc::mbar_wait(full_bar(s), (kit / STAGES) & 1);
           tc::tcgen05_after_sync();
           const uint32_t a_hi = smem_base + s * Cfg::STAGE_BYTES;
           const uint32_t b_hi = a_hi + PLANES * Cfg::A_BYTES;
-          const uint64_t da_hi = tc::make_smem_desc_sw64(a_hi), db_hi = tc::make_smem_desc_sw64(b_hi);
-          const uint64_t da_lo = tc::make_smem_desc_sw64(a_hi + Cfg::A_BYTES), db_lo = tc::make_smem_desc_sw64(b_hi + Cfg::B_BYTES);
+          const uint64_t da_hi = tc::make_smem_desc(a_hi), db_hi = tc::make_smem_desc(b_hi);
+          const uint64_t da_lo = tc::make_smem_desc(a_hi + Cfg::A_BYTES), db_lo = tc::make_smem_desc(b_hi + Cfg::B_BYTES);
+          // per 32-element half: hi.hi, lo.hi, hi.lo — the accumulation order of the single-CTA kernel's 32-element k-blocks,
+          // so the two kernels round identically (the A/B tool asserts equal outputs)
 #pragma unroll
-          for (int k = 0; k < 2; ++k) tc::umma_2sm(d, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb | k) != 0);
-          if constexpr (PASSES == 3) {
+          for (int h = 0; h < 2; ++h) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) tc::umma_2sm(d, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+            for (int k = 2 * h; k < 2 * h + 2; ++k) tc::umma_2sm(d, da_hi + 2 * k, db_hi + 2 * k, idesc, (kb | k) != 0);
+            if constexpr (PASSES == 3) {
 #pragma unroll
-            for (int k = 0; k < 2; ++k) tc::umma_2sm(d, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+              for (int k = 2 * h; k < 2 * h + 2; ++k) tc::umma_2sm(d, da_lo + 2 * k, db_hi + 2 * k, idesc, 1u);
+#pragma unroll
+              for (int k = 2 * h; k < 2 * h + 2; ++k) tc::umma_2sm(d, da_hi + 2 * k, db_lo + 2 * k, idesc, 1u);
+            }
           }
           tc::umma_commit_2sm(empty_bar(s));
         }
@@ -306,12 +306,12 @@ conv_gemm_tc5_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
 
 // host side ---------------------------------------------------------------------------------------------------------
 inline bool tc5_supported(const ConvGemm& p, int precision, int num_sms) {
-  if (!tc3_supported(p, precision) || !tc3_a_tma_supported(p) || p.N % 256 != 0 || p.K % 32 != 0) return false;
+  if (!tc3_supported(p, precision) || !tc3_a_tma_supported(p) || p.N % 256 != 0 || p.C % 64 != 0) return false;
   return (long long)((p.M + 255) / 256) * (p.N / 256) >= num_sms / 2;   // enough pair tiles to fill the machine
 }
 
 template <int PASSES>
-inline cudaError_t tc5_launch(const ConvGemm& p, const Tc3Maps& m, cudaStream_t s, int num_sms) {
+inline cudaError_t tc5_launch(const ConvGemm& p, const TcWeight& w, cudaStream_t s, int num_sms) {
   using Cfg = Tc5Cfg<PASSES>;
   static bool attr_set = false;
   auto kern = conv_gemm_tc5_kernel<PASSES>;
@@ -321,10 +321,10 @@ inline cudaError_t tc5_launch(const ConvGemm& p, const Tc3Maps& m, cudaStream_t 
     attr_set = true;
   }
   CUtensorMap ah, al;
-  cudaError_t st = tc3_make_a_map(p.x_hi, p, &ah);
+  cudaError_t st = tc3_make_a_map(p.x_hi, p, &ah, 64);
   if (st != cudaSuccess) return st;
   al = ah;
-  if (PASSES == 3 && (st = tc3_make_a_map(p.x_lo, p, &al)) != cudaSuccess) return st;
+  if (PASSES == 3 && (st = tc3_make_a_map(p.x_lo, p, &al, 64)) != cudaSuccess) return st;
   const int tiles_m2 = (p.M + 255) / 256, tiles_n = p.N / 256;
   int pairs = tiles_m2 * tiles_n;
   if (pairs > num_sms / 2) pairs = num_sms / 2;
@@ -341,12 +341,12 @@ inline cudaError_t tc5_launch(const ConvGemm& p, const Tc3Maps& m, cudaStream_t 
     ++na;
   }
   cfg.attrs = attr; cfg.numAttrs = na;
-  // weight maps with 128-row boxes (index 1): each CTA fetches its half of the 256-row tile
-  return cudaLaunchKernelEx(&cfg, kern, p, m.hi[1], m.lo[1], ah, al, tiles_m2, tiles_n);
+  // weight maps with 128-row x 128-byte boxes (index 1): each CTA fetches its half of the 256-row tile
+  return cudaLaunchKernelEx(&cfg, kern, p, w.map_hi[1], w.map_lo[1], ah, al, tiles_m2, tiles_n);
 }
 
-inline cudaError_t launch_conv_gemm_tc5(const ConvGemm& p, const Tc3Maps& m, int precision, cudaStream_t s, int num_sms) {
-  return precision == 2 ? tc5_launch<3>(p, m, s, num_sms) : tc5_launch<1>(p, m, s, num_sms);
+inline cudaError_t launch_conv_gemm_tc5(const ConvGemm& p, const TcWeight& w, int precision, cudaStream_t s, int num_sms) {
+  return precision == 2 ? tc5_launch<3>(p, w, s, num_sms) : tc5_launch<1>(p, w, s, num_sms);
 }
 
 }  // namespace d2t

@@ -169,7 +169,7 @@ int d2t_decode_attn_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, i
  *   "tma_a"            0/1 stem convolutions (stride 1, symmetric padding): the activation operand by TMA im2col loads of the bf16 planes
  *                      instead of the producer warps' cp.async gather (process-wide; default 1)
  *   "pair"             stem convolutions with 256-multiple output channels on a CTA pair (tcgen05 cta_group::2, both operands by
- *                      TMA): 0 = never, 1 = single-pass bf16 mode only, 2 = the 3-pass parity mode too (needs tma_a = 1)
+ *                      TMA): 0 = never, 1 = single-pass bf16 mode only, 2 = the 3-pass parity mode too (default; needs tma_a = 1)
  *   "tc3"              0/1 stem convolutions fed from bf16 activation planes by cp.async (default 1)
  *   "lean_acts"        0/1 stem layers write only the representations their consumers read (default 1)
  *   "fuse_pool"        0/1 max-pools 1 and 2 fused into the producing convolution's epilogue (default 1)

@@ -155,3 +155,29 @@ def test_fused_maxpool_is_bit_identical(built_lib, precision, H, W):
     e.close()
     assert torch.equal(out[0][0], out[1][0])
     assert out[0][1] - out[1][1] == 2      # two pool launches fewer
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("B,H,W", [(3, 64, 256), (5, 96, 384), (1, 32, 32), (2, 160, 928)])
+def test_pair_and_tma_kernels_are_bit_identical(built_lib, precision, B, H, W):
+    """The three ways the stem convolutions receive their operands — producer-warp cp.async gather (tma_a 0), TMA im2col
+    loads in the single-CTA kernel (tma_a 1, pair 0) and the CTA-pair kernel with 128-byte rows (pair 2) — accumulate the
+    same products in the same order: the encoder output must be bit-identical, including the ragged last tiles of small and
+    odd-sized batches (the pair's second CTA may own no pixel at all)."""
+    from doc2tex_b200.engine import Engine
+    cfg, sd = state_dict_for("TFM", None)
+    e = Engine(cfg, "cuda:0", precision=precision)
+    e.load_state_dict(sd)
+    img = synth.make_images(B, H, W, seed=99).cuda()
+    out = []
+    try:
+        for tma_a, pair in ((0, 0), (1, 0), (1, 2)):
+            e.set_option("tma_a", tma_a)
+            e.set_option("pair", pair)
+            ctx, _, _ = e.encode(img)
+            out.append(ctx.cpu())
+    finally:
+        e.set_option("tma_a", 1)     # process-wide switch: restore the default
+        e.close()
+    assert torch.equal(out[0], out[1])
+    assert torch.equal(out[0], out[2])

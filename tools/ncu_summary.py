@@ -17,6 +17,13 @@ for n, r in enumerate(rows[2:]):
             if x == k:
                 print(f"{k:70s} {r[i]} {units[i]}")
                 vals[k] = (r[i], units[i])
+    import re
+    extra = re.compile(r"^(lts__throughput|l1tex__throughput|lts__t_sectors\.sum$|lts__t_sectors_op_read\.sum$|l1tex__m_xbar2l1tex_read_bytes\.sum"
+                       r"|l1tex__m_l1tex2xbar_write_bytes\.sum|sm__cycles_elapsed\.max|smsp__inst_executed\.sum$|lts__t_sectors_srcunit_tex\.sum$"
+                       r"|l1tex__data_pipe_lsu_wavefronts_mem_shared\.sum$|sm__inst_executed_pipe_uniform|smsp__cycles_active\.avg$)")
+    for i, x in enumerate(h):
+        if extra.match(x) and x not in keys:
+            print(f"{x:70s} {r[i]} {units[i]}")
     try:
         t = float(vals['gpu__time_duration.sum'][0].replace(',', ''))
         tu = vals['gpu__time_duration.sum'][1]
