@@ -70,15 +70,25 @@ def parse():
                     help="encode decode_merge batches back to back on all SMs, then decode them in one call (no stage overlap)")
     ap.add_argument("--sequential", action="store_true", help="no encode/decode overlap across batches")
     ap.add_argument("--records", default="all",
-                    help="'all', 'none' or a comma list of beam5,bf16_greedy,bf16_beam5,strong_greedy,strong_beam5,attnv2_b512")
+                    help="'all', 'none' or a comma list of beam5,bf16_greedy,bf16_beam5,strong_greedy,strong_beam5,attnv2_b512,"
+                         "sweep_<H>x<W>_b<images per GPU> (beam-5, BASELINE configs[4])")
     ap.add_argument("--record-steps", type=int, default=0, help="timed steps of each sub-record (0 = min(steps, 4))")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (d2t_set_option), repeatable")
     a = ap.parse_args()
-    if a.decode_merge <= 0:
-        a.decode_merge = 4   # measured: profiles/r01_pipeline_sweep.txt (decode of 4 encoded batches costs ~1.6x one)
     if a.encoder_sms <= 0:
         a.encoder_sms = 132  # measured sweet spot with merged decode (112 / 88 without)
     return a
+
+
+def auto_merge(mode: str, steps: int) -> int:
+    """Encoded batches handed to one decode call.  The decode step is a chain of dependent launches whose duration grows far
+    slower than its rows (profiles/r02c_decode_vs_rows.txt: 256 rows 34.4 ms, 1 024 rows 16.5 ms, 2 048 rows 12.2 ms per 256
+    images), so greedy merges up to 10 batches (2 560 rows) and beam-5 up to 5 (6 400 rows); the count divides the number of
+    timed steps so that no decode call of the bracket runs on a partial group (profiles/r02c_schedule_sweep*.txt)."""
+    for m in ((10, 8, 5, 4) if mode == "greedy" else (4, 5)):
+        if steps % m == 0:
+            return m
+    return min(steps, 8 if mode == "greedy" else 4)
 
 
 def peaks():
@@ -280,8 +290,9 @@ class Bench:
         # rank r holds images [r*B, (r+1)*B) of the global batch (seeded per image)
         img_host = synth.make_images(B, H, W, seed=2024 + rank * B).pin_memory()
         img_dev = img_host.to(dev)
+        merge = a.decode_merge if a.decode_merge > 0 else auto_merge(mode, steps)
         pipe = PipelinedRecognizer(eng, mode, a.beam, T, encoder_sms=None if a.sequential else a.encoder_sms,
-                                   decode_merge=1 if a.sequential else a.decode_merge, overlap=not a.no_overlap)
+                                   decode_merge=1 if a.sequential else merge, overlap=not a.no_overlap)
         if a.no_overlap and not a.sequential:
             eng.set_option("encoder_sms", self.sms)
 
@@ -415,7 +426,8 @@ class Bench:
             gflop = ENC_GFLOP.get((H, W))
             roof = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
                     "traffic": traffic,
-                    "kernel": "conv_gemm_tc3_kernel (tcgen05 implicit GEMM, cp.async-fed bf16 planes) on layer3.1.conv1 "
+                    "kernel": "conv_gemm_tc5_kernel (tcgen05 cta_group::2 implicit GEMM, M=256 per CTA pair, activations by TMA "
+                              "im2col and weights by TMA from bf16 planes) on layer3.1.conv1 "
                               f"(M={int(conv_flops / (2 * 512 * 4608))}, N=512, K=4608)",
                     "flops_per_launch": conv_flops, "launch_ms": conv_ms / conv_n, "launches_timed": int(conv_n),
                     "mma_passes": passes, "executed_tflops": ach * max(passes, 1),
@@ -428,9 +440,9 @@ class Bench:
             "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16x3": "bf16x3", "bf16": "bf16"}[precision],
             "data": "synthetic", "config": dict(workload_config(head, mode, a.beam, precision, B, H, W, a.natural), schedule=(
                 "sequential" if a.sequential else
-                (f"grouped: {a.decode_merge} batches encoded back to back on all SMs, then decoded in one call; one batch "
+                (f"grouped: {merge} batches encoded back to back on all SMs, then decoded in one call; one batch "
                  f"alone takes {seq_ms:.1f} ms") if a.no_overlap else
-                f"pipelined: encode on {a.encoder_sms} SMs overlaps the decode of the previous batches, {a.decode_merge} encoded "
+                f"pipelined: encode on {a.encoder_sms} SMs overlaps the decode of the previous batches, {merge} encoded "
                 f"batch(es) per decode call; one batch alone takes {seq_ms:.1f} ms (encode {enc_ms:.1f} + decode {dec_ms:.1f})")),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "formulas/s", "h2d_bytes_per_step": img_host.numel() * 4,
@@ -452,31 +464,55 @@ def run_engine(args):
     line = b.measure(args.head, args.mode, args.precision, args.batch, args.steps, args.warmup, main=True)
     want = args.records
     names = [] if want == "none" else (
-        ["beam5", "bf16_greedy", "bf16_beam5", "strong_greedy", "strong_beam5", "attnv2_b512"] if want == "all" else want.split(","))
+        ["beam5", "bf16_greedy", "bf16_beam5", "strong_greedy", "strong_beam5", "attnv2_b512", "sweep_64x256_b32",
+         "sweep_64x256_b1024", "sweep_128x512_b128", "sweep_192x896_b64"] if want == "all" else want.split(","))
     rs = args.record_steps if args.record_steps > 0 else min(args.steps, 4)
+    # greedy sub-records: enough steps for one full merged decode group (auto_merge)
+    rs_g = args.record_steps if args.record_steps > 0 else (8 if args.steps >= 8 else args.steps)
     records = {}
-    for name in names:
-        if name.startswith("strong") and world == 1:
-            continue   # one rank: the strong-scaling shard IS the main / beam5 record
+
+    def one(name):
         if name == "beam5":
-            r = b.measure("TFM", "beam", "bf16x3", args.batch, rs, 3)
-        elif name == "bf16_greedy":
-            r = b.measure("TFM", "greedy", "bf16", args.batch, rs, 3)
-        elif name == "bf16_beam5":
-            r = b.measure("TFM", "beam", "bf16", args.batch, rs, 3)
-        elif name in ("strong_greedy", "strong_beam5"):
+            return b.measure("TFM", "beam", "bf16x3", args.batch, rs, 3)
+        if name == "bf16_greedy":
+            return b.measure("TFM", "greedy", "bf16", args.batch, rs_g, 3)
+        if name == "bf16_beam5":
+            return b.measure("TFM", "beam", "bf16", args.batch, rs, 3)
+        if name in ("strong_greedy", "strong_beam5"):
             # BASELINE configs[2]: ONE batch of 256 images, batch-sharded 256 / N per rank -> value = 256 * steps / time
-            r = b.measure("TFM", "greedy" if name == "strong_greedy" else "beam", "bf16x3", max(1, 256 // world), rs, 3)
+            r = b.measure("TFM", "greedy" if name == "strong_greedy" else "beam", "bf16x3", max(1, 256 // world),
+                          rs_g if name == "strong_greedy" else rs, 3)
             r["scaling"] = "strong"
             r["config"]["global_batch"] = max(1, 256 // world) * world
-        elif name == "attnv2_b512":
+            return r
+        if name == "attnv2_b512":
             # BASELINE configs[3]: config/train.yaml default stack (Attnv2), greedy, global batch 512 sharded over the ranks
             r = b.measure("Attnv2", "greedy", "bf16x3", max(1, 512 // world), rs, 3)
             r["scaling"] = "strong"
             r["config"]["global_batch"] = max(1, 512 // world) * world
-        else:
-            raise SystemExit(f"unknown record {name!r}")
-        records[name] = r
+            return r
+        if name.startswith("sweep_"):
+            # BASELINE configs[4]: beam-5 over image sizes / batches, e.g. sweep_192x896_b64 (images per GPU; weak scaling)
+            hw, bs = name[len("sweep_"):].split("_b")
+            h, w = (int(v) for v in hw.split("x"))
+            keep = (args.height, args.width)
+            args.height, args.width = h, w
+            try:
+                return b.measure("TFM", "beam", "bf16x3", int(bs), 2, 3)
+            finally:
+                args.height, args.width = keep
+        raise SystemExit(f"unknown record {name!r}")
+
+    for name in names:
+        if name.startswith("strong") and world == 1:
+            continue   # one rank: the strong-scaling shard IS the main / beam5 record
+        try:
+            records[name] = one(name)
+        except SystemExit:
+            raise
+        except Exception as ex:   # a failing sub-record must not take the main record's line with it (same on every rank)
+            records[name] = {"error": f"{type(ex).__name__}: {ex}"[:300]}
+            torch.cuda.empty_cache()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()

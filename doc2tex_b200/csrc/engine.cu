@@ -129,6 +129,8 @@ struct d2t_engine {
   bool stack_mma = true;    // option "stack_mma": bf16x3 decode projections issue 2 MMAs per k-step against [W_hi ; W_lo]
   int steps_per_graph = 8;  // option "steps_per_graph": decode steps captured per CUDA graph (= the early-exit poll interval)
   bool kv_bf16 = true;      // option "kv_bf16": bf16 KV caches in the single-pass bf16 mode (fp32-parity modes keep fp32)
+  int vit_planes = 1;       // option "vit_planes": the ViT blocks' Linears read bf16 operand planes by TMA (1: auto — CTA-pair kernel
+                            // in bf16x3, single-CTA kernel in bf16 —, 2: single-CTA kernel only, 3: CTA pair wherever it applies)
   bool fuse_pool = true;    // option "fuse_pool": 2x2 max-pools 1 and 2 fused into the producing convolution's epilogue
   bool time_decode = false; // option "time_decode": bracket the decode-attention / beam-step launches with events
   bool dbg_decode = false, dbg_timeline = false;   // options "dbg_decode" / "dbg_timeline": phase / per-launch timestamps
@@ -287,7 +289,10 @@ int run_contraction(d2t_engine* e, const ConvGemm& p, const TcWeight* tcw, int p
       if (m3 != e->tc3.end() && m3->second.ready) {
         // large 256-multiple-wide convolutions: CTA pair with both operands by TMA (option "pair": 0 never, 1 single-pass bf16
         // only — where shared-memory bandwidth bounds the single-CTA kernel —, 2 also the 3-pass parity mode)
-        if (e->use_pair && (precision == D2T_PREC_BF16 || e->use_pair >= 2) && tc3_use_a_tma() && tc5_supported(p, precision, e->active_sms)) {
+        // short-K 1x1 problems (ViT Linears, downsample branches) are epilogue-bound: measured (tools/encoder_ab.py vit_planes=0,1,2,
+        // profiles/r02d_encoder_ab_vit_planes.txt) the pair kernel wins in the 3-pass mode, the 128-wide single-CTA tile in bf16
+        const bool vit_single = (e->vit_planes == 2 || (e->vit_planes == 1 && precision == D2T_PREC_BF16)) && p.KH == 1 && p.KW == 1 && p.K <= 1024;
+        if (e->use_pair && !vit_single && (precision == D2T_PREC_BF16 || e->use_pair >= 2) && tc3_use_a_tma() && tc5_supported(p, precision, e->active_sms)) {
           cudaError_t st5 = launch_conv_gemm_tc5(p, *tcw, precision, s, e->active_sms);
           if (st5 != cudaSuccess) return e->fail(D2T_ERR_CUDA, "CTA-pair contraction launch failed: %s", cudaGetErrorString(st5));
           e->launches += 1;
@@ -469,8 +474,15 @@ int layernorm(d2t_engine* e, const float* x, const float* w, const float* b, flo
   return 0;
 }
 
+// Operand planes of a Linear on the tensor-core plane path (option "vit_planes"): input planes written by the producing
+// kernel, output planes for the next Linear; either side may be absent.
+struct LinPlanes {
+  const __nv_bfloat16 *x_hi = nullptr, *x_lo = nullptr;
+  __nv_bfloat16 *out_hi = nullptr, *out_lo = nullptr;
+};
+
 int linear(d2t_engine* e, const float* x, const std::string& wkey, const std::string& bkey, float* out, int M, int N,
-           int K, int act, const float* res, cudaStream_t s, int w_row_off = 0) {
+           int K, int act, const float* res, cudaStream_t s, int w_row_off = 0, const LinPlanes* pl = nullptr) {
   auto wi = e->dev.find(wkey);
   if (wi == e->dev.end()) return e->fail(D2T_ERR_STATE, "weight '%s' not finalized", wkey.c_str());
   const float* bias = nullptr;
@@ -481,6 +493,11 @@ int linear(d2t_engine* e, const float* x, const std::string& wkey, const std::st
   }
   ConvGemm p = linear_params(x, wi->second + (size_t)w_row_off * K, bias, out, M, N, K);
   p.act = act; p.res = res; p.ldr = N;
+  if (pl && pl->x_hi) {
+    // rows as the pixels of ONE image row (B = 1, H = 1, W = M): the TMA im2col load of a 1x1 "convolution" walks 128 rows
+    p.x_hi = pl->x_hi; p.x_lo = pl->x_lo; p.out_hi = pl->out_hi; p.out_lo = pl->out_lo;
+    p.B = 1; p.W = M; p.OW = M;
+  }
   return run_contraction(e, p, nullptr, e->cfg.precision, s);
 }
 
@@ -764,6 +781,15 @@ int d2t_finalize_weights(d2t_engine* e) {
       if ((rc = prep(e->dev[p + "attn.proj.weight"], D, D))) return rc;
       if ((rc = prep(e->dev[p + "mlp.fc1.weight"], 4 * D, D))) return rc;
       if ((rc = prep(e->dev[p + "mlp.fc2.weight"], D, 4 * D))) return rc;
+      if (c.precision == D2T_PREC_BF16X3 || c.precision == D2T_PREC_BF16) {   // option "vit_planes": same kernels as the stem
+        for (const char* n : {"attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight"}) {
+          const float* w = e->dev[p + n];
+          Tc3Maps m3;
+          cudaError_t st = tc3_prepare_maps(e->tcw[w], &m3);
+          if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tc3_prepare_maps(%s%s): %s", p.c_str(), n, cudaGetErrorString(st));
+          e->tc3[w] = m3;
+        }
+      }
     }
     if (c.head == D2T_HEAD_TFM) {
       for (int l = 0; l < c.dec_layers; ++l) {
@@ -848,6 +874,8 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
     e->kv_bf16 = value != 0;
   } else if (k == "lean_acts") {
     e->lean_acts = value != 0; decode_affecting = false;
+  } else if (k == "vit_planes") {
+    e->vit_planes = value; decode_affecting = false;
   } else if (k == "fuse_pool") {
     e->fuse_pool = value != 0; decode_affecting = false;
   } else if (k == "pair") {
@@ -1003,11 +1031,31 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
   }
   const int N = gh * gw, T = N + 1, rows = B * T;
   Fmap xs, hs, qkv, att, x2, ff;
+  // Plane path (option "vit_planes", tensor-core precisions): LayerNorm, the attention kernel and fc1's GELU epilogue write
+  // bf16 hi/lo operand planes and no fp32 copy (nobody reads one), and the four Linears of a block run on the kernels of the
+  // stem — both operands by TMA, CTA pair where the tile count fills the machine — instead of gathering fp32 through registers.
+  bool vp = stem_planes(e) && e->vit_planes && D % 64 == 0;
+  for (int i = 0; i < c.depth && vp; ++i)
+    for (const char* n : {"attn.qkv.weight", "attn.proj.weight", "mlp.fc1.weight", "mlp.fc2.weight"}) {
+      auto m3 = e->tc3.find(e->dev[SEQ + "blocks." + std::to_string(i) + "." + n]);
+      if (m3 == e->tc3.end() || !m3->second.ready) vp = false;
+    }
   if ((rc = alloc_act(e, e->enc_pool, &xs, B, 1, T, D))) return rc;
-  if ((rc = alloc_act(e, e->enc_pool, &hs, B, 1, T, D))) return rc;
+  if ((rc = alloc_act(e, e->enc_pool, &hs, B, 1, T, D, vp, !vp))) return rc;
   if ((rc = alloc_act(e, e->enc_pool, &qkv, B, 1, T, 3 * D))) return rc;
-  if ((rc = alloc_act(e, e->enc_pool, &att, B, 1, T, D))) return rc;
-  if ((rc = alloc_act(e, e->enc_pool, &ff, B, 1, T, 4 * D))) return rc;
+  if ((rc = alloc_act(e, e->enc_pool, &att, B, 1, T, D, vp, !vp))) return rc;
+  if ((rc = alloc_act(e, e->enc_pool, &ff, B, 1, T, 4 * D, vp, !vp))) return rc;
+  LinPlanes from_hs, from_att, to_ff, from_ff;
+  if (vp) {
+    from_hs.x_hi = hs.hi; from_hs.x_lo = hs.lo;
+    from_att.x_hi = att.hi; from_att.x_lo = att.lo;
+    to_ff = from_hs; to_ff.out_hi = ff.hi; to_ff.out_lo = ff.lo;
+    from_ff.x_hi = ff.hi; from_ff.x_lo = ff.lo;
+  }
+  const LinPlanes* const p_hs = vp ? &from_hs : nullptr;
+  const LinPlanes* const p_att = vp ? &from_att : nullptr;
+  const LinPlanes* const p_toff = vp ? &to_ff : nullptr;
+  const LinPlanes* const p_ff = vp ? &from_ff : nullptr;
   const float* pos = e->dev[SEQ + "pos_embed"];
   if (e->pos_interpolate && (gh != e->pos_grid_h || gw != e->pos_grid_w)) {
     if (e->pos_grid_h <= 0 || e->pos_grid_w <= 0 || 1 + e->pos_grid_h * e->pos_grid_w != c.max_tokens)
@@ -1036,20 +1084,20 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
   for (int i = 0; i < c.depth; ++i) {
     const std::string p = SEQ + "blocks." + std::to_string(i) + ".";
     if ((rc = alloc_act(e, e->enc_pool, &x2, B, 1, T, D))) return rc;
-    if ((rc = layernorm(e, xs.p, e->dev[p + "norm1.weight"], e->dev[p + "norm1.bias"], hs.p, rows, D, 1e-6f, s))) return rc;
-    if ((rc = linear(e, hs.p, p + "attn.qkv.weight", p + "attn.qkv.bias", qkv.p, rows, 3 * D, D, ACT_NONE, nullptr, s))) return rc;
+    if ((rc = layernorm(e, xs.p, e->dev[p + "norm1.weight"], e->dev[p + "norm1.bias"], hs.p, rows, D, 1e-6f, s, hs.hi, hs.lo))) return rc;
+    if ((rc = linear(e, hs.p, p + "attn.qkv.weight", p + "attn.qkv.bias", qkv.p, rows, 3 * D, D, ACT_NONE, nullptr, s, 0, p_hs))) return rc;
     {
-      dim3 grid((T + 127) / 128, B * c.heads);
-      encoder_attention_kernel<32, 64><<<grid, 128, 0, s>>>(qkv.p, att.p, T, D, scale);
+      dim3 grid((T + ENC_ATT_QT - 1) / ENC_ATT_QT, B * c.heads);
+      encoder_attention_kernel<32><<<grid, 4 * ENC_ATT_QT, 0, s>>>(qkv.p, att.p, T, D, scale, att.hi, att.lo);
       e->launches += 1;
       CUDA_TRY(e, cudaGetLastError());
     }
-    if ((rc = linear(e, att.p, p + "attn.proj.weight", p + "attn.proj.bias", x2.p, rows, D, D, ACT_NONE, xs.p, s))) return rc;
-    if ((rc = layernorm(e, x2.p, e->dev[p + "norm2.weight"], e->dev[p + "norm2.bias"], hs.p, rows, D, 1e-6f, s))) return rc;
-    if ((rc = linear(e, hs.p, p + "mlp.fc1.weight", p + "mlp.fc1.bias", ff.p, rows, 4 * D, D, ACT_GELU, nullptr, s))) return rc;
+    if ((rc = linear(e, att.p, p + "attn.proj.weight", p + "attn.proj.bias", x2.p, rows, D, D, ACT_NONE, xs.p, s, 0, p_att))) return rc;
+    if ((rc = layernorm(e, x2.p, e->dev[p + "norm2.weight"], e->dev[p + "norm2.bias"], hs.p, rows, D, 1e-6f, s, hs.hi, hs.lo))) return rc;
+    if ((rc = linear(e, hs.p, p + "mlp.fc1.weight", p + "mlp.fc1.bias", ff.p, rows, 4 * D, D, ACT_GELU, nullptr, s, 0, p_toff))) return rc;
     free_act(e, e->enc_pool, xs);
     if ((rc = alloc_act(e, e->enc_pool, &xs, B, 1, T, D))) return rc;
-    if ((rc = linear(e, ff.p, p + "mlp.fc2.weight", p + "mlp.fc2.bias", xs.p, rows, D, 4 * D, ACT_NONE, x2.p, s))) return rc;
+    if ((rc = linear(e, ff.p, p + "mlp.fc2.weight", p + "mlp.fc2.bias", xs.p, rows, D, 4 * D, ACT_NONE, x2.p, s, 0, p_ff))) return rc;
     free_act(e, e->enc_pool, x2);
     tap(e, "block" + std::to_string(i), xs, true);
   }

@@ -307,7 +307,11 @@ conv_gemm_tc5_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
 // host side ---------------------------------------------------------------------------------------------------------
 inline bool tc5_supported(const ConvGemm& p, int precision, int num_sms) {
   if (!tc3_supported(p, precision) || !tc3_a_tma_supported(p) || p.N % 256 != 0 || p.C % 64 != 0) return false;
-  return (long long)((p.M + 255) / 256) * (p.N / 256) >= num_sms / 2;   // enough pair tiles to fill the machine
+  // a GELU epilogue over a short K is bound by its erf evaluations (ncu: fc1 of the ViT blocks 96 us here with 4 epilogue warps
+  // per CTA against 60 us on the gather kernel): such problems go to the single-CTA kernel's 128-wide tile (8 epilogue warps)
+  if ((p.act & 15) == ACT_GELU && p.K <= 1024) return false;
+  // enough pair tiles to fill (7/8 of) the machine in one wave: the ViT projections of a 256-image batch have 65
+  return 8LL * ((p.M + 255) / 256) * (p.N / 256) >= 7LL * (num_sms / 2);
 }
 
 template <int PASSES>

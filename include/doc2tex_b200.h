@@ -173,6 +173,8 @@ int d2t_decode_attn_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, i
  *   "tc3"              0/1 stem convolutions fed from bf16 activation planes by cp.async (default 1)
  *   "lean_acts"        0/1 stem layers write only the representations their consumers read (default 1)
  *   "fuse_pool"        0/1 max-pools 1 and 2 fused into the producing convolution's epilogue (default 1)
+ *   "vit_planes"       the ViT blocks' Linears read bf16 operand planes by TMA on the stem's kernels: 0 off (fp32 gather), 1 auto
+ *                      (default: CTA pair in bf16x3, single-CTA 128-wide tile in bf16), 2 single-CTA only, 3 CTA pair where it applies
  *   "pos_interpolate", "pos_grid_h", "pos_grid_w"   ViTEncoder (fix_embed: False) bicubic pos-embed resampling
  *   "time_conv", "time_decode"   see d2t_debug_conv_time / d2t_debug_decode_time
  *   "dbg_decode", "dbg_timeline" phase / per-launch timestamps of the last decode step on stderr

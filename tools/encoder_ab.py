@@ -20,6 +20,7 @@ for prec in precs:
     eng.load_state_dict(sd)
     res = {v: [] for v in vals}
     ref = None
+    worst = 0.0
     for rnd in range(4):
         for v in vals:
             eng.set_option(key, v)
@@ -36,6 +37,9 @@ for prec in precs:
                 ref = ctx.clone()
             else:
                 d = float((ctx - ref).abs().max() / ref.abs().max())
-                assert d < 1e-6, f"{key}={v}: encoder output differs from {key}={vals[0]} by {d:.2e}"
-    print(f"{prec}: " + ", ".join(f"{key}={v}: {statistics.median(res[v]):.2f} ms" for v in vals), flush=True)
+                # options that only move data are bit-equal; options that change a summation order (vit_planes) stay far inside
+                # the fp32-parity tolerance of the mode (1e-3)
+                assert d < 2e-4, f"{key}={v}: encoder output differs from {key}={vals[0]} by {d:.2e}"
+                worst = max(worst, d)
+    print(f"{prec}: " + ", ".join(f"{key}={v}: {statistics.median(res[v]):.2f} ms" for v in vals) + f"  (max rel diff {worst:.1e})", flush=True)
     eng.close()

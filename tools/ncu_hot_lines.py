@@ -27,7 +27,7 @@ for n, sec in enumerate(sections):
     tot = sum(int(r[si]) for r in rows) or 1
     inst = sum(int(r[ii]) for r in rows if r[ii].isdigit())
     print(f"## launch {n} hot instructions ({tot} stall samples, {inst} warp instructions executed)")
-    for r in sorted(rows, key=lambda r: -int(r[si]))[:8]:
+    for r in sorted(rows, key=lambda r: -int(r[si]))[:int(sys.argv[2]) if len(sys.argv) > 2 else 8]:
         print(f"   {100 * int(r[si]) / tot:5.1f} %  x{r[ii]:>9}  {r[1].strip()[:110]}")
     if len(raw) > 2 + n:
         d = dict(zip(raw[0], raw[2 + n]))

@@ -4,8 +4,11 @@ import sys
 
 
 def show(name, r):
-    print(f"{name}: {r['value']:.0f} formulas/s (e2e {r['e2e']['value']:.0f}), {r['ms_per_step']:.1f} ms/step, launches {r['gpu_launches']}, "
-          f"n_gpus {r['n_gpus']}, scaling {r['scaling']}")
+    if "error" in r:
+        print(f"{name}: ERROR {r['error']}")
+        return
+    print(f"{name}: {r['value']:.0f} formulas/s (e2e {r['e2e']['value']:.0f}), {r['ms_per_step']:.1f} ms/step x {r['steps']}, launches {r['gpu_launches']}, "
+          f"n_gpus {r['n_gpus']}, scaling {r['scaling']}, batch/GPU {r['config']['batch_per_gpu']} {r['config']['image']}")
     rf = r.get("roofline")
     if rf:
         print(f"   dominant conv: {rf['achieved']:.0f} TFLOP/s = {rf['frac']:.3f} of {rf['peak']:.0f} ({rf['launch_ms']:.3f} ms/launch); "
