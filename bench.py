@@ -85,7 +85,7 @@ def auto_merge(mode: str, steps: int) -> int:
     slower than its rows (profiles/r02c_decode_vs_rows.txt: 256 rows 34.4 ms, 1 024 rows 16.5 ms, 2 048 rows 12.2 ms per 256
     images), so greedy merges up to 10 batches (2 560 rows) and beam-5 up to 5 (6 400 rows); the count divides the number of
     timed steps so that no decode call of the bracket runs on a partial group (profiles/r02c_schedule_sweep*.txt)."""
-    for m in ((10, 8, 5, 4) if mode == "greedy" else (4, 5)):
+    for m in (range(10, 3, -1) if mode == "greedy" else (4, 5, 3)):
         if steps % m == 0:
             return m
     return min(steps, 8 if mode == "greedy" else 4)

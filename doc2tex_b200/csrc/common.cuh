@@ -47,6 +47,7 @@ struct ConvGemm {
   // optional bf16 hi/lo NHWC planes of the INPUT activation (cp.async-fed A operand of conv_gemm_tc3_kernel)
   const __nv_bfloat16* x_hi;
   const __nv_bfloat16* x_lo;
+  int single_cta;          // 1 = never the CTA-pair kernel (short-K problems whose tile count quantises badly over 74 pairs)
 };
 
 // Programmatic dependent launch (PDL): a kernel launched with the programmatic-serialization attribute may start

@@ -172,6 +172,19 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
   auto from_x = [&](ConvGemm& g) { if (b.planes) { g.a_map_hi = &b.map_x_hi; g.a_map_lo = b.x_lo ? &b.map_x_lo : nullptr; } };
   auto from_att = [&](ConvGemm& g) { if (b.planes) { g.a_map_hi = &b.map_att_hi; g.a_map_lo = b.att_lo ? &b.map_att_lo : nullptr; } };
   auto from_ffn = [&](ConvGemm& g) { if (b.planes) { g.a_map_hi = &b.map_ffn_hi; g.a_map_lo = b.ffn_lo ? &b.map_ffn_lo : nullptr; } };
+  // Merged decode calls (thousands of rows): a projection with more 128 x 128 tiles than SMs no longer fits the one-tile-per-CTA
+  // kernel and used to fall back to the fp32 register-gather kernel (timeline at 5 120 rows: lin1 34 us, vocab 19 us for
+  // 8 / 4 GFLOP).  Such projections read the same operand planes through the stem's persistent kernels instead (TMA-fed A,
+  // CTA pair when the tile count fills the machine): rows as the pixels of one image row, like the ViT Linears.
+  auto from_x_wide = [&](ConvGemm& g) {
+    const bool wide = b.planes && e->wide_decode && e->tc3.count(g.w) &&
+                      (long long)((R + TC_BM - 1) / TC_BM) * ((g.N + 127) / 128) > e->active_sms;
+    if (!wide) return from_x(g);
+    g.x_hi = b.x_hi; g.x_lo = b.x_lo; g.B = 1; g.W = R; g.OW = R;
+    // 128-wide single-CTA tiles (two epilogue warps per TMEM quadrant): with K = 256 these problems are bound by their epilogue
+    // and the pair kernel's 256 x 256 tiles quantise badly (lin1 at 5 120 rows: 80 tiles on 74 pairs, 34 us — no gain)
+    g.single_cta = 1;
+  };
   Timeline tl; tl.buf = b.timeline; tl.s = s; tl.names = &g_tl_names;
   tl.mark("start");
   {
@@ -236,8 +249,10 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
     // feed-forward, norm3
     {
       ConvGemm g = linear_params(b.x, e->dev[p + "linear1.weight"], e->dev[p + "linear1.bias"], b.ffn, R, F, D);
-      g.act = ACT_RELU; from_x(g);
+      g.act = ACT_RELU; from_x_wide(g);
       g.out_hi = b.ffn_hi; g.out_lo = b.ffn_lo;
+      // wide path: nobody reads the fp32 copy as long as linear2 still fits its one-tile-per-CTA kernel, which reads the planes
+      if (g.x_hi && (long long)((R + TC_BM - 1) / TC_BM) * ((D + 127) / 128) <= e->active_sms) g.out = nullptr;
       if ((rc = dec_linear(e, g, s))) return rc;
     }
     if (l == 1) tl.mark("lin1");
@@ -251,7 +266,7 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
   }
   {
     ConvGemm g = linear_params(b.x, e->dev[PRED + "proj.weight"], e->dev[PRED + "proj.bias"], b.logits, R, V, D);
-    from_x(g);
+    from_x_wide(g);
     if ((rc = dec_linear(e, g, s))) return rc;
   }
   tl.mark("vocab");

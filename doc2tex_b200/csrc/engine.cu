@@ -129,6 +129,7 @@ struct d2t_engine {
   bool stack_mma = true;    // option "stack_mma": bf16x3 decode projections issue 2 MMAs per k-step against [W_hi ; W_lo]
   int steps_per_graph = 8;  // option "steps_per_graph": decode steps captured per CUDA graph (= the early-exit poll interval)
   bool kv_bf16 = true;      // option "kv_bf16": bf16 KV caches in the single-pass bf16 mode (fp32-parity modes keep fp32)
+  bool wide_decode = true;  // option "wide_decode": decode projections with more tiles than SMs run on the stem's persistent kernels
   int vit_planes = 1;       // option "vit_planes": the ViT blocks' Linears read bf16 operand planes by TMA (1: auto — CTA-pair kernel
                             // in bf16x3, single-CTA kernel in bf16 —, 2: single-CTA kernel only, 3: CTA pair wherever it applies)
   bool fuse_pool = true;    // option "fuse_pool": 2x2 max-pools 1 and 2 fused into the producing convolution's epilogue
@@ -292,7 +293,7 @@ int run_contraction(d2t_engine* e, const ConvGemm& p, const TcWeight* tcw, int p
         // short-K 1x1 problems (ViT Linears, downsample branches) are epilogue-bound: measured (tools/encoder_ab.py vit_planes=0,1,2,
         // profiles/r02d_encoder_ab_vit_planes.txt) the pair kernel wins in the 3-pass mode, the 128-wide single-CTA tile in bf16
         const bool vit_single = (e->vit_planes == 2 || (e->vit_planes == 1 && precision == D2T_PREC_BF16)) && p.KH == 1 && p.KW == 1 && p.K <= 1024;
-        if (e->use_pair && !vit_single && (precision == D2T_PREC_BF16 || e->use_pair >= 2) && tc3_use_a_tma() && tc5_supported(p, precision, e->active_sms)) {
+        if (e->use_pair && !vit_single && !p.single_cta && (precision == D2T_PREC_BF16 || e->use_pair >= 2) && tc3_use_a_tma() && tc5_supported(p, precision, e->active_sms)) {
           cudaError_t st5 = launch_conv_gemm_tc5(p, *tcw, precision, s, e->active_sms);
           if (st5 != cudaSuccess) return e->fail(D2T_ERR_CUDA, "CTA-pair contraction launch failed: %s", cudaGetErrorString(st5));
           e->launches += 1;
@@ -803,6 +804,16 @@ int d2t_finalize_weights(d2t_engine* e) {
         if ((rc = prep(e->dev[p + "linear2.weight"], D, c.dec_ff))) return rc;
       }
       if ((rc = prep(e->dev[PRED + "proj.weight"], c.vocab, D))) return rc;
+      if (c.precision == D2T_PREC_BF16X3 || c.precision == D2T_PREC_BF16) {   // option "wide_decode": lin1 and the vocabulary projection
+        std::vector<const float*> ws = {e->dev[PRED + "proj.weight"]};
+        for (int l = 0; l < c.dec_layers; ++l) ws.push_back(e->dev[PRED + "model.layers." + std::to_string(l) + ".linear1.weight"]);
+        for (const float* w : ws) {
+          Tc3Maps m3;
+          cudaError_t st = tc3_prepare_maps(e->tcw[w], &m3);
+          if (st != cudaSuccess) return e->fail(D2T_ERR_CUDA, "tc3_prepare_maps(decoder): %s", cudaGetErrorString(st));
+          e->tc3[w] = m3;
+        }
+      }
     } else if (c.head == D2T_HEAD_ATTNV2 || c.head == D2T_HEAD_ATTN) {
       const int Hs = c.attn_hidden;
       const std::string a = PRED + "attention_cell.attn.";
@@ -874,6 +885,8 @@ int d2t_set_option(d2t_engine* e, const char* key, int value) {
     e->kv_bf16 = value != 0;
   } else if (k == "lean_acts") {
     e->lean_acts = value != 0; decode_affecting = false;
+  } else if (k == "wide_decode") {
+    e->wide_decode = value != 0;
   } else if (k == "vit_planes") {
     e->vit_planes = value; decode_affecting = false;
   } else if (k == "fuse_pool") {

@@ -173,6 +173,8 @@ int d2t_decode_attn_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, i
  *   "tc3"              0/1 stem convolutions fed from bf16 activation planes by cp.async (default 1)
  *   "lean_acts"        0/1 stem layers write only the representations their consumers read (default 1)
  *   "fuse_pool"        0/1 max-pools 1 and 2 fused into the producing convolution's epilogue (default 1)
+ *   "wide_decode"      0/1 decode projections with more 128x128 tiles than SMs (merged calls of thousands of rows) run on the
+ *                      stem's persistent TMA-fed kernels instead of the fp32 register-gather kernel (default 1)
  *   "vit_planes"       the ViT blocks' Linears read bf16 operand planes by TMA on the stem's kernels: 0 off (fp32 gather), 1 auto
  *                      (default: CTA pair in bf16x3, single-CTA 128-wide tile in bf16), 2 single-CTA only, 3 CTA pair where it applies
  *   "pos_interpolate", "pos_grid_h", "pos_grid_w"   ViTEncoder (fix_embed: False) bicubic pos-embed resampling

@@ -211,3 +211,20 @@ def test_string_metrics_small_cases():
     assert corpus_bleu([["a", "b"]], [[["c", "d"]]]) == 0.0
     assert squeeze_latex_whitespace("x ^ { 2 } + \\mathrm { d } y") == "x^{2}+\\mathrm{d}y"
     assert squeeze_latex_whitespace("\\sin x") == "\\sin x"
+
+
+def test_bench_auto_merge_divides_the_timed_steps():
+    """bench.py hands `decode_merge` encoded batches to one decode call; the count must divide the timed steps (a partial
+    group would cost a whole decode chain inside the bracket)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.auto_merge("greedy", 20) == 10 and bench.auto_merge("greedy", 16) == 8 and bench.auto_merge("greedy", 5) == 5
+    assert bench.auto_merge("beam", 20) == 4 and bench.auto_merge("beam", 5) == 5 and bench.auto_merge("beam", 4) == 4
+    for mode in ("greedy", "beam"):
+        for k in range(1, 41):
+            m = bench.auto_merge(mode, k)
+            cands = range(4, 11) if mode == "greedy" else (3, 4, 5)
+            assert 1 <= m <= k and (k % m == 0 or not any(k % c == 0 for c in cands))
