@@ -80,15 +80,25 @@ def parse():
     return a
 
 
-def auto_merge(mode: str, steps: int) -> int:
+MERGE_TARGET_IMAGES = {"greedy": 2560, "beam": 1024}   # images per decode call: 2 560 greedy rows / 5 120 beam-5 rows
+
+
+def merge_target(mode: str, batch: int) -> int:
+    return max(1, MERGE_TARGET_IMAGES[mode] // max(1, batch))
+
+
+def auto_merge(mode: str, steps: int, batch: int = 256) -> int:
     """Encoded batches handed to one decode call.  The decode step is a chain of dependent launches whose duration grows far
-    slower than its rows (profiles/r02c_decode_vs_rows.txt: 256 rows 34.4 ms, 1 024 rows 16.5 ms, 2 048 rows 12.2 ms per 256
-    images), so greedy merges up to 10 batches (2 560 rows) and beam-5 up to 5 (6 400 rows); the count divides the number of
-    timed steps so that no decode call of the bracket runs on a partial group (profiles/r02c_schedule_sweep*.txt)."""
-    for m in (range(10, 3, -1) if mode == "greedy" else (4, 5, 3)):
-        if steps % m == 0:
-            return m
-    return min(steps, 8 if mode == "greedy" else 4)
+    slower than its rows until the attention walks are HBM-bound (profiles/r02c_decode_vs_rows.txt: 256 rows 34.4 ms, 1 024
+    rows 16.5 ms, 2 048 rows 12.2 ms per 256 images), so consecutive batches are merged up to about 2 560 greedy rows /
+    5 120 beam-5 rows per call (10 / 4 batches of 256 images; more batches when a rank holds a smaller shard).  The count
+    divides the number of timed steps whenever it can: a partial group costs a whole decode chain inside the bracket
+    (profiles/r02c_schedule_sweep*.txt)."""
+    tgt = merge_target(mode, batch)
+    if steps % tgt == 0:
+        return tgt
+    best = max(d for d in range(1, min(steps, tgt * 5 // 4) + 1) if steps % d == 0)
+    return best if 2 * best >= min(steps, tgt) else min(steps, tgt)
 
 
 def peaks():
@@ -218,8 +228,9 @@ def run_reference(args):
         "impl": "reference", "metric": "formulas/sec", "value": value, "unit": "formulas/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args.head, args.mode, args.beam, args.precision, args.batch, args.height, args.width, args.natural),
-                       schedule="reference CPU implementation on the host cores (bounded sample of the workload)"),
+        # the SAME config object as the engine arm's line; how each arm walks the workload is the top-level "schedule"
+        "config": workload_config(args.head, args.mode, args.beam, args.precision, args.batch, args.height, args.width, args.natural),
+        "schedule": "reference CPU implementation on the host cores (bounded sample of the workload)",
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "formulas/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -290,7 +301,7 @@ class Bench:
         # rank r holds images [r*B, (r+1)*B) of the global batch (seeded per image)
         img_host = synth.make_images(B, H, W, seed=2024 + rank * B).pin_memory()
         img_dev = img_host.to(dev)
-        merge = a.decode_merge if a.decode_merge > 0 else auto_merge(mode, steps)
+        merge = a.decode_merge if a.decode_merge > 0 else auto_merge(mode, steps, batch)
         pipe = PipelinedRecognizer(eng, mode, a.beam, T, encoder_sms=None if a.sequential else a.encoder_sms,
                                    decode_merge=1 if a.sequential else merge, overlap=not a.no_overlap)
         if a.no_overlap and not a.sequential:
@@ -438,12 +449,13 @@ class Bench:
             "metric": "formulas/sec", "value": value, "unit": "formulas/s", "n_gpus": world, "steps": steps,
             "warmup": max(warmup, 3), "ms_per_step": t_ms / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": {"fp32": "f32", "tf32x3": "tf32x3", "bf16x3": "bf16x3", "bf16": "bf16"}[precision],
-            "data": "synthetic", "config": dict(workload_config(head, mode, a.beam, precision, B, H, W, a.natural), schedule=(
+            "data": "synthetic", "config": workload_config(head, mode, a.beam, precision, B, H, W, a.natural),
+            "schedule": (
                 "sequential" if a.sequential else
                 (f"grouped: {merge} batches encoded back to back on all SMs, then decoded in one call; one batch "
                  f"alone takes {seq_ms:.1f} ms") if a.no_overlap else
                 f"pipelined: encode on {a.encoder_sms} SMs overlaps the decode of the previous batches, {merge} encoded "
-                f"batch(es) per decode call; one batch alone takes {seq_ms:.1f} ms (encode {enc_ms:.1f} + decode {dec_ms:.1f})")),
+                f"batch(es) per decode call; one batch alone takes {seq_ms:.1f} ms (encode {enc_ms:.1f} + decode {dec_ms:.1f})"),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "formulas/s", "h2d_bytes_per_step": img_host.numel() * 4,
                     "d2h_bytes_per_step": B * world * (T + 2) * 8 if world > 1 else B * T * 8},
@@ -480,8 +492,11 @@ def run_engine(args):
             return b.measure("TFM", "beam", "bf16", args.batch, rs, 3)
         if name in ("strong_greedy", "strong_beam5"):
             # BASELINE configs[2]: ONE batch of 256 images, batch-sharded 256 / N per rank -> value = 256 * steps / time
-            r = b.measure("TFM", "greedy" if name == "strong_greedy" else "beam", "bf16x3", max(1, 256 // world),
-                          rs_g if name == "strong_greedy" else rs, 3)
+            # a rank's shard is small, so consecutive global batches are merged per decode call like the main record's are:
+            # the timed steps are one full merge group (at least the usual record length)
+            mode_s = "greedy" if name == "strong_greedy" else "beam"
+            shard = max(1, 256 // world)
+            r = b.measure("TFM", mode_s, "bf16x3", shard, max(rs_g if mode_s == "greedy" else rs, merge_target(mode_s, shard)), 3)
             r["scaling"] = "strong"
             r["config"]["global_batch"] = max(1, 256 // world) * world
             return r

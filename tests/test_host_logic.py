@@ -223,8 +223,12 @@ def test_bench_auto_merge_divides_the_timed_steps():
     spec.loader.exec_module(bench)
     assert bench.auto_merge("greedy", 20) == 10 and bench.auto_merge("greedy", 16) == 8 and bench.auto_merge("greedy", 5) == 5
     assert bench.auto_merge("beam", 20) == 4 and bench.auto_merge("beam", 5) == 5 and bench.auto_merge("beam", 4) == 4
+    # a rank's strong-scaling shard (256 / N images): more batches per call, same rows
+    assert bench.auto_merge("greedy", 80, 32) == 80 and bench.auto_merge("beam", 32, 32) == 32 and bench.auto_merge("greedy", 20, 128) == 20
     for mode in ("greedy", "beam"):
-        for k in range(1, 41):
-            m = bench.auto_merge(mode, k)
-            cands = range(4, 11) if mode == "greedy" else (3, 4, 5)
-            assert 1 <= m <= k and (k % m == 0 or not any(k % c == 0 for c in cands))
+        for batch in (32, 256, 1024):
+            tgt = bench.merge_target(mode, batch)
+            for k in range(1, 41):
+                m = bench.auto_merge(mode, k, batch)
+                assert 1 <= m <= k and m <= max(1, tgt * 5 // 4)
+                assert k % m == 0 or m == min(k, tgt)
