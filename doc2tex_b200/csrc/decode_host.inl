@@ -208,7 +208,7 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
       ConvGemm g = linear_params(b.x, e->dev[p + "self_attn.in_proj_weight"], e->dev[p + "self_attn.in_proj_bias"], b.q, R, 3 * D, D);
       g.ldc = D; g.n_split = D; g.out2 = selfkv; g.ldc2 = T * 2 * D; g.dyn = step; g.dyn_mul2 = 2 * D;
       g.out2_bf16 = kv_is_bf16(e) ? 1 : 0;
-      from_x(g);
+      from_x_wide(g);
       if (l == 1) g.dbg = b.dbg;
       if ((rc = dec_linear(e, g, s))) return rc;
     }

@@ -70,6 +70,83 @@ __global__ void conv0_direct_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// Same layer, register-blocked: one thread = FOUR consecutive pixels of a row x EIGHT output channels.  The thread's 72 filter
+// weights and its BN scale / shift stay in registers over the grid-stride loop (the channel group of a thread never changes:
+// the stride is a multiple of Cout / 8), the 3 x 6 input window is loaded once for the four pixels, and every pixel's eight
+// channels leave as one 16-byte store per plane.  Each output keeps the (kh, kw) accumulation order of the kernel above, so the
+// results are bit-identical; the first version spent its time on index arithmetic and 8-byte stores (ncu: 0.42 ms for 537 MB
+// of planes = 1.28 TB/s).  Needs Cout % 8 == 0 and W % 4 == 0.
+__global__ void __launch_bounds__(256)
+conv0_direct4x8_kernel(const float* __restrict__ x, const float* __restrict__ w /*[Cout][9]*/,
+                       const float* __restrict__ scale, const float* __restrict__ shift,
+                       float* __restrict__ out, int B, int H, int W, int Cout,
+                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  const int cg = Cout / 8, wq = W / 4;
+  const long long total = (long long)B * H * wq * cg;
+  const long long stride = (long long)gridDim.x * blockDim.x;   // host: a multiple of cg
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c8 = (int)(idx % cg) * 8;
+  float wr[9][8], sc[8], sh[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) wr[t][c] = __ldg(w + (c8 + c) * 9 + t);
+    sc[c] = __ldg(scale + c8 + c);
+    sh[c] = __ldg(shift + c8 + c);
+  }
+  for (; idx < total; idx += stride) {
+    const long long pg = idx / cg;
+    const int ow0 = (int)(pg % wq) * 4;
+    const int oh = (int)((pg / wq) % H);
+    const int b = (int)(pg / ((long long)wq * H));
+    const float* xb = x + (size_t)b * H * W;
+    float v[3][6];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int ih = oh + kh - 1;
+      const bool rok = (unsigned)ih < (unsigned)H;
+#pragma unroll
+      for (int i = 0; i < 6; ++i) {
+        const int iw = ow0 + i - 1;
+        v[kh][i] = (rok && (unsigned)iw < (unsigned)W) ? __ldg(xb + (size_t)ih * W + iw) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int px = 0; px < 4; ++px) {
+      float a[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) a[c] = 0.f;
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+          for (int c = 0; c < 8; ++c) a[c] = fmaf(v[kh][px + kw], wr[kh * 3 + kw][c], a[c]);
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] = fmaxf(a[c] * sc[c] + sh[c], 0.f);
+      const size_t off = ((size_t)((size_t)b * H + oh) * W + ow0 + px) * Cout + c8;
+      if (out) {
+        *reinterpret_cast<float4*>(out + off) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(out + off + 4) = make_float4(o[4], o[5], o[6], o[7]);
+      }
+      if (out_hi) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(o[2 * u]), h1 = __float2bfloat16_rn(o[2 * u + 1]);
+          hw[u] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          const __nv_bfloat16 l0 = __float2bfloat16_rn(o[2 * u] - __bfloat162float(h0));
+          const __nv_bfloat16 l1 = __float2bfloat16_rn(o[2 * u + 1] - __bfloat162float(h1));
+          lw[u] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        }
+        *reinterpret_cast<uint4*>(out_hi + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (out_lo) *reinterpret_cast<uint4*>(out_lo + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      }
+    }
+  }
+}
+
 // MaxPool2d(kernel 2x2, stride (SH,SW), padding (PH,PW)) on NHWC; padding behaves as -inf
 // (resnet.py:97,107,120: maxpool3 is k2 s(2,1) p(0,1)).
 __global__ void maxpool2x2_nhwc_kernel(const float* __restrict__ x, float* __restrict__ out, int B, int H, int W,

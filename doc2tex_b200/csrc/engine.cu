@@ -804,9 +804,12 @@ int d2t_finalize_weights(d2t_engine* e) {
         if ((rc = prep(e->dev[p + "linear2.weight"], D, c.dec_ff))) return rc;
       }
       if ((rc = prep(e->dev[PRED + "proj.weight"], c.vocab, D))) return rc;
-      if (c.precision == D2T_PREC_BF16X3 || c.precision == D2T_PREC_BF16) {   // option "wide_decode": lin1 and the vocabulary projection
+      if (c.precision == D2T_PREC_BF16X3 || c.precision == D2T_PREC_BF16) {   // option "wide_decode": qkv, lin1 and the vocabulary projection
         std::vector<const float*> ws = {e->dev[PRED + "proj.weight"]};
-        for (int l = 0; l < c.dec_layers; ++l) ws.push_back(e->dev[PRED + "model.layers." + std::to_string(l) + ".linear1.weight"]);
+        for (int l = 0; l < c.dec_layers; ++l) {
+          ws.push_back(e->dev[PRED + "model.layers." + std::to_string(l) + ".linear1.weight"]);
+          ws.push_back(e->dev[PRED + "model.layers." + std::to_string(l) + ".self_attn.in_proj_weight"]);
+        }
         for (const float* w : ws) {
           Tc3Maps m3;
           cudaError_t st = tc3_prepare_maps(e->tcw[w], &m3);
@@ -989,6 +992,11 @@ int d2t_encode(d2t_engine* e, const float* img, int B, int H, int W, float* ctx,
     if ((rc = alloc_act(e, e->enc_pool, &x, B, H, W, c0.cout, stem_planes(e), !(stem_planes(e) && e->lean_acts) || e->keep_taps))) return rc;
     const long long total = (long long)B * H * W * (c0.cout / 4);
     const size_t smem = (size_t)11 * c0.cout * sizeof(float);
+    if (c0.cout % 8 == 0 && W % 4 == 0 && 256 % (c0.cout / 8) == 0) {
+      // four pixels x eight channels per thread; the grid stride (a multiple of 256) keeps a thread on its channel group
+      const long long groups = (long long)B * H * (W / 4) * (c0.cout / 8);
+      conv0_direct4x8_kernel<<<grid_for(groups, 256, e->active_sms), 256, 0, s>>>(img, c0.w, c0.scale, c0.shift, x.p, B, H, W, c0.cout, x.hi, x.lo);
+    } else
     conv0_direct_kernel<<<grid_for(total, 256, e->active_sms), 256, smem, s>>>(img, c0.w, c0.scale, c0.shift, x.p, B, H, W, c0.cout, x.hi, x.lo);
     e->launches += 1;
     CUDA_TRY(e, cudaGetLastError());

@@ -134,6 +134,10 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
     float* const out = p.out;
     __nv_bfloat16* const out_hi = p.out_hi;
     __nv_bfloat16* const out_lo = p.out_lo;
+    // columns >= n_split go to a second tensor (the KV-cache slot of the current decode step; whole 32-column chunks)
+    const int n_split = p.n_split, ldc2 = p.ldc2;
+    float* out2 = nullptr;
+    if (p.out2) out2 = p.out2 + (p.dyn ? (long long)(*p.dyn) * p.dyn_mul2 : 0) - n_split;
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int tm = tile / tiles_n, tn = tile - tm * tiles_n;
@@ -215,6 +219,19 @@ conv_gemm_tc3_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
                 v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
               } else if (act == ACT_GELU) {
                 v = tc::gelu_erf4(v);
+              }
+              if (out2 != nullptr && n >= n_split) {
+                float* dst = out2 + (size_t)m * ldc2 + n;
+                if (p.out2_bf16) {   // bf16 KV cache: same element offsets, 2-byte elements
+                  const __nv_bfloat162 lo2 = __floats2bfloat162_rn(v.x, v.y), hi2 = __floats2bfloat162_rn(v.z, v.w);
+                  uint2 pk;
+                  pk.x = *reinterpret_cast<const uint32_t*>(&lo2);
+                  pk.y = *reinterpret_cast<const uint32_t*>(&hi2);
+                  *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out2) + (dst - p.out2)) = pk;
+                } else {
+                  *reinterpret_cast<float4*>(dst) = v;
+                }
+                continue;
               }
               const size_t o = (size_t)m * ldc + n;
               if (out) *reinterpret_cast<float4*>(out + o) = v;   // fp32 copy only when a consumer reads it
@@ -427,7 +444,8 @@ inline bool tc3_supported(const ConvGemm& p, int precision) {
   if (precision != 2 && precision != 3) return false;
   if (p.x_hi == nullptr || (precision == 2 && p.x_lo == nullptr)) return false;
   if (p.pool && (p.res != nullptr || (p.OH & 1) || (p.OW & 1) || p.M % 4 != 0)) return false;
-  return p.out2 == nullptr && p.a_map_hi == nullptr && p.C % 8 == 0 && p.K % 8 == 0 && p.ldc % 4 == 0 &&
+  if (p.out2 != nullptr && (p.pool || p.n_split % 32 != 0 || p.ldc2 % 4 != 0 || p.dyn_mul2 % 4 != 0)) return false;
+  return p.a_map_hi == nullptr && p.C % 8 == 0 && p.K % 8 == 0 && p.ldc % 4 == 0 &&
          (p.res == nullptr || p.ldr % 4 == 0) && p.N % 4 == 0;
 }
 

@@ -306,7 +306,7 @@ conv_gemm_tc5_kernel(const ConvGemm p, const __grid_constant__ CUtensorMap map_h
 
 // host side ---------------------------------------------------------------------------------------------------------
 inline bool tc5_supported(const ConvGemm& p, int precision, int num_sms) {
-  if (!tc3_supported(p, precision) || !tc3_a_tma_supported(p) || p.N % 256 != 0 || p.C % 64 != 0) return false;
+  if (!tc3_supported(p, precision) || !tc3_a_tma_supported(p) || p.N % 256 != 0 || p.C % 64 != 0 || p.out2 != nullptr) return false;
   // a GELU epilogue over a short K is bound by its erf evaluations (ncu: fc1 of the ViT blocks 96 us here with 4 epilogue warps
   // per CTA against 60 us on the gather kernel): such problems go to the single-CTA kernel's 128-wide tile (8 epilogue warps)
   if ((p.act & 15) == ACT_GELU && p.K <= 1024) return false;

@@ -8,6 +8,18 @@ inline bool is_lstm_head(int head) { return head == D2T_HEAD_ATTNV2 || head == D
 // first encoder token the decoder attends to: AttentionV2 (seqmodel 'TFM') drops the cls token, Attention keeps it
 inline int attn_tok0(const d2t_config& c) { return c.head == D2T_HEAD_ATTN ? 0 : 1; }
 
+// the step kernel stages [taps][256] location weights + the coverage / score rows in dynamic shared memory: beyond the 48 KB
+// default (very long location kernels or token sequences) the opt-in limit is raised once
+int lstm_attention_prepare(d2t_engine* e, int S, int taps) {
+  const size_t need = lstm_attention_smem_bytes(S, taps, 256);
+  static size_t granted = 48 * 1024;
+  if (need <= granted) return 0;
+  if (need > 200 * 1024) return e->fail(D2T_ERR_UNSUPPORTED, "attention step needs %zu bytes of shared memory (taps %d, tokens %d)", need, taps, S);
+  CUDA_TRY(e, cudaFuncSetAttribute(lstm_attention_step_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  granted = 200 * 1024;
+  return 0;
+}
+
 struct AttnBuffers {
   float *keyproj = nullptr, *qp = nullptr, *xcat = nullptr, *gates = nullptr, *h = nullptr, *c = nullptr;
   float *alpha_cum = nullptr, *logits = nullptr, *logits_out = nullptr;
@@ -30,7 +42,8 @@ int enqueue_attn_step(d2t_engine* e, const AttnBuffers& b, const float* ctx, int
     ConvGemm g = linear_params(b.h, e->dev[a + "query_proj.weight"], e->dev[a + "query_proj.bias"], b.qp, B, Hs, Hs);
     if ((rc = dec_linear(e, g, s))) return rc;
   }
-  lstm_attention_step_kernel<256><<<B, 256, (size_t)2 * S * sizeof(float), s>>>(
+  if ((rc = lstm_attention_prepare(e, S, taps))) return rc;
+  lstm_attention_step_kernel<256><<<B, 256, lstm_attention_smem_bytes(S, taps, 256), s>>>(
       b.keyproj, ctx, ntok, b.qp, e->dev["attn.locM"], e->dev["attn.locc"], taps, e->dev[a + "score.weight"],
       e->dev[a + "score.bias"], b.alpha_cum, b.xcat, Kc, 1, attn_tok0(c));
   e->launches += 1;
@@ -264,7 +277,8 @@ int enqueue_attn_beam_step(d2t_engine* e, const AttnBeamBuffers& b, const float*
     ConvGemm g = linear_params(b.h, e->dev[a + "query_proj.weight"], e->dev[a + "query_proj.bias"], b.qp, R, Hs, Hs);
     if ((rc = dec_linear(e, g, s))) return rc;
   }
-  lstm_attention_step_kernel<256><<<R, 256, (size_t)2 * S * sizeof(float), s>>>(
+  if ((rc = lstm_attention_prepare(e, S, taps))) return rc;
+  lstm_attention_step_kernel<256><<<R, 256, lstm_attention_smem_bytes(S, taps, 256), s>>>(
       b.keyproj, ctx, ntok, b.qp, e->dev["attn.locM"], e->dev["attn.locc"], taps, e->dev[a + "score.weight"],
       e->dev[a + "score.bias"], b.alpha_cum, b.xcat, Kc, beam, attn_tok0(c));
   e->launches += 1;

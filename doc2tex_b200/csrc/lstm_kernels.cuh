@@ -23,6 +23,15 @@ __global__ void lstm_embed_kernel(const int* __restrict__ tokens, int tok_ld, co
 //   alpha  = softmax_s(e);  context = alpha^T H;  alpha_cum += alpha
 // key_proj(H) is hoisted out of the loop (the reference recomputes it every step).  HBM traffic per step
 // = keyproj + H rows of the image, read once each as coalesced 1 KB rows.
+// The kernel is one block per decoder row and was bound by dependent load latency (ncu: 61 us at 256 rows, 21 % of the issue
+// slots, long-scoreboard stalls): a warp now scores FOUR tokens at a time with their 32 key_proj loads in flight before the
+// first use, the folded location matrix is staged once in shared memory ([tap][channel], conflict-free), the coverage copy is
+// zero-padded (no bounds tests), and the context pass issues 16 loads per thread before its FMAs.  Every sum keeps the
+// association order of the first version, so results are bit-identical to it.
+inline size_t lstm_attention_smem_bytes(int S, int taps, int HS) {
+  return (size_t)(2 * S + 2 * (taps / 2) + taps * HS) * sizeof(float);
+}
+
 template <int HS>  // hidden size (256)
 __global__ void __launch_bounds__(256)
 lstm_attention_step_kernel(const float* __restrict__ keyproj, const float* __restrict__ ctx, int ntok,
@@ -31,18 +40,25 @@ lstm_attention_step_kernel(const float* __restrict__ keyproj, const float* __res
                            const float* __restrict__ score_b, float* __restrict__ alpha_cum /*[B][S]*/,
                            float* __restrict__ xcat, int ld, int rows_per_img = 1,
                            int tok0 = 1 /* first attended token: 1 skips the cls token (Attnv2), 0 keeps it (Attn) */) {
-  extern __shared__ float sm[];  // [S] alpha_cum copy, [S] scores
+  extern __shared__ float sm[];  // [S + 2 pad] zero-padded alpha_cum copy, [S] scores, [taps][HS] folded location matrix
   const int S = ntok - tok0;
-  float* s_ac = sm;
-  float* s_e = sm + S;
+  const int pad = taps / 2;
+  float* s_ac = sm;                  // s_ac[pad + i] = alpha_cum[i]
+  float* s_e = sm + S + 2 * pad;
+  float* s_M = s_e + S;
   __shared__ float red[8];
   __shared__ float s_bc[2];
   const int b = blockIdx.x;               // decoder row (hypothesis slot)
   const int img = b / rows_per_img;       // the beams of an image share its encoder memory
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   constexpr int PER = HS / 32;
-  for (int i = threadIdx.x; i < S; i += blockDim.x) s_ac[i] = alpha_cum[(size_t)b * S + i];
-  float q[PER], sw[PER], cc[PER];
+  for (int i = threadIdx.x; i < S + 2 * pad; i += blockDim.x)
+    s_ac[i] = (i >= pad && i < pad + S) ? alpha_cum[(size_t)b * S + i - pad] : 0.f;
+  for (int i = threadIdx.x; i < taps * HS; i += blockDim.x) {
+    const int j = i / HS, h = i - j * HS;
+    s_M[i] = locM[h * taps + j];
+  }
+  float q[PER], sw[PER];
 #pragma unroll
   for (int k = 0; k < PER; ++k) {
     const int h = lane + 32 * k;
@@ -50,25 +66,39 @@ lstm_attention_step_kernel(const float* __restrict__ keyproj, const float* __res
     sw[k] = score_w[h];
   }
   __syncthreads();
-  const int pad = taps / 2;
   const float sb = score_b[0];
-  for (int s = wid; s < S; s += nw) {
-    const float* kr = keyproj + ((size_t)img * ntok + tok0 + s) * HS;
-    float acc = 0.f;
+  const float* const kbase = keyproj + ((size_t)img * ntok + tok0) * HS + lane;
+  for (int s0 = wid; s0 < S; s0 += 4 * nw) {   // tokens s0, s0 + nw, s0 + 2 nw, s0 + 3 nw of this warp
+    float kr[4][PER], loc[4][PER];
 #pragma unroll
-    for (int k = 0; k < PER; ++k) {
-      const int h = lane + 32 * k;
-      float loc = 0.f;
-      for (int j = 0; j < taps; ++j) {
-        const int ss = s + j - pad;
-        const float a = (ss >= 0 && ss < S) ? s_ac[ss] : 0.f;
-        loc = fmaf(locM[h * taps + j], a, loc);
+    for (int u = 0; u < 4; ++u) {
+      const int s = min(s0 + u * nw, S - 1);   // a clamped duplicate is computed and dropped
+#pragma unroll
+      for (int k = 0; k < PER; ++k) {
+        kr[u][k] = kbase[(size_t)s * HS + 32 * k];
+        loc[u][k] = 0.f;
       }
-      cc[k] = loc;
-      acc = fmaf(sw[k], tanhf(kr[h] + q[k] + cc[k]), acc);
     }
-    acc = warp_sum(acc);
-    if (lane == 0) s_e[s] = acc + sb;
+    for (int j = 0; j < taps; ++j) {
+      float m[PER], a[4];
+#pragma unroll
+      for (int k = 0; k < PER; ++k) m[k] = s_M[j * HS + lane + 32 * k];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) a[u] = s_ac[min(s0 + u * nw, S - 1) + j];   // = alpha_cum[s + j - pad], 0 outside
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int k = 0; k < PER; ++k) loc[u][k] = fmaf(m[k], a[u], loc[u][k]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < PER; ++k) acc = fmaf(sw[k], tanhf(kr[u][k] + q[k] + loc[u][k]), acc);
+      acc = warp_sum(acc);
+      const int s = s0 + u * nw;
+      if (lane == 0 && s < S) s_e[s] = acc + sb;
+    }
   }
   __syncthreads();
   // softmax over s
@@ -92,14 +122,24 @@ lstm_attention_step_kernel(const float* __restrict__ keyproj, const float* __res
   for (int i = threadIdx.x; i < S; i += blockDim.x) {
     const float a = s_e[i] * inv;
     s_e[i] = a;
-    alpha_cum[(size_t)b * S + i] = s_ac[i] + a;  // coverage update AFTER the step (seq2seq_v2.py:264-266)
+    alpha_cum[(size_t)b * S + i] = s_ac[pad + i] + a;  // coverage update AFTER the step (seq2seq_v2.py:264-266)
   }
   __syncthreads();
-  // context = alpha^T H, one thread per channel (HS == input channels == 256 here)
+  // context = alpha^T H, one thread per channel (HS == input channels == 256 here): even tokens into a0, odd into a1
   for (int d = threadIdx.x; d < HS; d += blockDim.x) {
     const float* hp = ctx + ((size_t)img * ntok + tok0) * HS + d;
     float a0 = 0.f, a1 = 0.f;
     int s = 0;
+    for (; s + 16 <= S; s += 16) {
+      float v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) v[u] = hp[(size_t)(s + u) * HS];
+#pragma unroll
+      for (int u = 0; u < 16; u += 2) {
+        a0 = fmaf(s_e[s + u], v[u], a0);
+        a1 = fmaf(s_e[s + u + 1], v[u + 1], a1);
+      }
+    }
     for (; s + 2 <= S; s += 2) {
       a0 = fmaf(s_e[s], hp[(size_t)s * HS], a0);
       a1 = fmaf(s_e[s + 1], hp[(size_t)(s + 1) * HS], a1);

@@ -181,3 +181,29 @@ def test_pair_and_tma_kernels_are_bit_identical(built_lib, precision, B, H, W):
         e.close()
     assert torch.equal(out[0], out[1])
     assert torch.equal(out[0], out[2])
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+@pytest.mark.parametrize("B,H,W", [(40, 64, 256), (33, 128, 512), (3, 96, 384)])
+def test_vit_linears_on_operand_planes_match_gather_path(built_lib, precision, B, H, W):
+    """Option vit_planes: the ViT blocks' Linears read bf16 operand planes by TMA on the stem's kernels (1 = auto, 2 = single-CTA
+    kernel, 3 = CTA pair wherever its tile count allows) instead of gathering fp32 rows through registers (0).  Same products,
+    another summation order: the encoder output agrees far inside the fp32-parity tolerance (bf16x3) / the mode's own noise
+    (bf16), including row counts that are no multiple of the 128- / 256-row tiles (33 x 261 = 8 613 rows)."""
+    from doc2tex_b200.engine import Engine
+    cfg, sd = state_dict_for("TFM", None)
+    e = Engine(cfg, "cuda:0", precision=precision)
+    e.load_state_dict(sd)
+    img = synth.make_images(B, H, W, seed=5).cuda()
+    out = {}
+    try:
+        for mode in (0, 1, 2, 3):
+            e.set_option("vit_planes", mode)
+            ctx, _, _ = e.encode(img)
+            out[mode] = ctx.cpu()
+    finally:
+        e.close()
+    tol = 2e-5 if precision == "bf16x3" else 2e-2
+    for mode in (1, 2, 3):
+        assert torch.isfinite(out[mode]).all()
+        assert rel_err(out[mode], out[0]) < tol, (mode, rel_err(out[mode], out[0]))
