@@ -90,6 +90,9 @@ int enqueue_attention(d2t_engine* e, const float* q, const float* kv, long long 
   // 414 us, 1 204 vs 1 190 us): at these sizes the walk is bound by its own dot / shuffle / exp instruction stream.
   // What helps is more loads in flight per warp: attn_kpi keys per quarter warp and iteration (4: -7 .. -11 % per step).
   const int kpi = e->attn_kpi;
+  // A fourth measured alternative for beam search, also removed: four lanes per key with 256-bit loads and eight channels per
+  // lane (a third fewer instructions per key, 41 instead of 57 % issue utilisation) ran 3-6 % SLOWER (profiles/
+  // r02g_attn_lpk_ab.txt): the walk is bound by load latency x resident warps, which is what five blocks per SM address.
 #define D2T_ROW_ATTN(SP, HB, TKV, KPI_, GRID, BLOCK, PTR)                                                                         \
   launch_kernel(decode_attention_kernel<32, SP, HB, TKV, KPI_>, GRID, BLOCK, 0, s, q, D, PTR, row_stride, 2 * D, anc, anc_parity,   \
                 anc_ld, rows_per_src, step, n_fixed, out, D, out_hi, out_lo)

@@ -184,8 +184,11 @@ __device__ __forceinline__ void attention_store(const float4 acc, float sum, siz
 
 // HB > 1: the heads of a row are spread over HB blocks (grid = rows x HB, 8 / HB heads each): 512 quarter-size blocks
 // balance over 148 SMs better than 256 full ones.
+// Five resident blocks per SM (48 registers, no spills): the walk waits on its loads (ncu at 5 120 beam rows: 41-57 % issue,
+// 30 % L2, long-scoreboard stalls, 47 % of the warp slots with 4 blocks of 60 registers), so warps in flight are what it
+// needs — beam-5 1 048 -> 964 us per step at 5 120 rows, greedy 797 -> 775 at 2 560; six blocks (40 registers) spill and lose.
 template <int HD, int SPLIT = 1, int HB = 1, typename KV = float, int KPI = 2>
-__global__ void __launch_bounds__(256 * SPLIT / HB)
+__global__ void __launch_bounds__(256 * SPLIT / HB, 5)
 decode_attention_kernel(const float* __restrict__ q, int ldq, const KV* __restrict__ kv,
                         long long row_stride, int pos_stride, const int* __restrict__ anc,
                         long long anc_parity_stride, int anc_ld, int rows_per_src,
