@@ -80,7 +80,7 @@ def parse():
     return a
 
 
-MERGE_TARGET_IMAGES = {"greedy": 2560, "beam": 1024}   # images per decode call: 2 560 greedy rows / 5 120 beam-5 rows
+MERGE_TARGET_IMAGES = {"greedy": 2560, "beam": 1280}   # images per decode call: 2 560 greedy rows / 6 400 beam-5 rows
 
 
 def merge_target(mode: str, batch: int) -> int:
@@ -91,7 +91,7 @@ def auto_merge(mode: str, steps: int, batch: int = 256) -> int:
     """Encoded batches handed to one decode call.  The decode step is a chain of dependent launches whose duration grows far
     slower than its rows until the attention walks are HBM-bound (profiles/r02c_decode_vs_rows.txt: 256 rows 34.4 ms, 1 024
     rows 16.5 ms, 2 048 rows 12.2 ms per 256 images), so consecutive batches are merged up to about 2 560 greedy rows /
-    5 120 beam-5 rows per call (10 / 4 batches of 256 images; more batches when a rank holds a smaller shard).  The count
+    6 400 beam-5 rows per call (10 / 5 batches of 256 images; more batches when a rank holds a smaller shard).  The count
     divides the number of timed steps whenever it can: a partial group costs a whole decode chain inside the bracket
     (profiles/r02c_schedule_sweep*.txt)."""
     tgt = merge_target(mode, batch)
@@ -478,9 +478,10 @@ def run_engine(args):
     names = [] if want == "none" else (
         ["beam5", "bf16_greedy", "bf16_beam5", "strong_greedy", "strong_beam5", "attnv2_b512", "sweep_64x256_b32",
          "sweep_64x256_b1024", "sweep_128x512_b128", "sweep_192x896_b64"] if want == "all" else want.split(","))
-    rs = args.record_steps if args.record_steps > 0 else min(args.steps, 4)
-    # greedy sub-records: enough steps for one full merged decode group (auto_merge)
-    rs_g = args.record_steps if args.record_steps > 0 else (8 if args.steps >= 8 else args.steps)
+    # sub-records: two full merged decode groups when the main record has that many steps (the second group's encodes overlap
+    # the first group's decode, as in the main record), else what the main record runs
+    rs = args.record_steps if args.record_steps > 0 else min(args.steps, 10)
+    rs_g = args.record_steps if args.record_steps > 0 else min(args.steps, 20)
     records = {}
 
     def one(name):
@@ -502,7 +503,7 @@ def run_engine(args):
             return r
         if name == "attnv2_b512":
             # BASELINE configs[3]: config/train.yaml default stack (Attnv2), greedy, global batch 512 sharded over the ranks
-            r = b.measure("Attnv2", "greedy", "bf16x3", max(1, 512 // world), rs, 3)
+            r = b.measure("Attnv2", "greedy", "bf16x3", max(1, 512 // world), min(rs, 4), 3)
             r["scaling"] = "strong"
             r["config"]["global_batch"] = max(1, 512 // world) * world
             return r

@@ -105,7 +105,7 @@ struct d2t_engine {
   SlotPool enc_pool, dec_pool;
   bool keep_taps = false;
   bool use_pdl = true;   // option "pdl": programmatic dependent launch in the decode step
-  int pdl_max_rows = 2560;   // option "pdl_max_rows": decode calls with more rows launch without it
+  int pdl_max_rows = 2048;   // option "pdl_max_rows": decode calls with more rows launch without it (2 560-row calls: 6 084 vs 5 990 formulas/s)
   int use_pair = 2;      // option "pair": CTA-pair (cta_group::2) kernel for the wide stem convolutions (see run_contraction)
   bool use_tc3 = true;   // option "tc3": stem convolutions fed from bf16 activation planes by cp.async
   // ViTEncoder (fix_embed: False, interpolate_embed: True): pos_embed is resampled bicubically to the grid of each image

@@ -157,7 +157,7 @@ int d2t_decode_attn_beam(d2t_engine* e, const float* ctx_dev, int B, int ntok, i
  *   "encoder_sms"      SMs the encoder's persistent tensor-core kernels may occupy (default: all) — leaving a few SMs free
  *                      lets the latency-bound decode of batch i overlap the encode of batch i+1 (doc2tex_b200/pipeline.py)
  *   "pdl"              0/1 programmatic dependent launch inside the decode step (default 1)
- *   "pdl_max_rows"     decode calls with more rows than this launch without it (default 2560: it only pays for small launches)
+ *   "pdl_max_rows"     decode calls with more rows than this launch without it (default 2048: it only pays for small launches)
  *   "steps_per_graph"  decode steps captured per CUDA graph, 1..16 (default 8 = the early-exit poll interval)
  *   "decode_groups"    concurrent row groups of one decode call (parallel graph branches; 0/1 = one chain, default)
  *   "split_k"          0 = never, 1 = auto split-K of the LayerNorm-fed decode projections (default 1)

@@ -222,9 +222,9 @@ def test_bench_auto_merge_divides_the_timed_steps():
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
     assert bench.auto_merge("greedy", 20) == 10 and bench.auto_merge("greedy", 16) == 8 and bench.auto_merge("greedy", 5) == 5
-    assert bench.auto_merge("beam", 20) == 4 and bench.auto_merge("beam", 5) == 5 and bench.auto_merge("beam", 4) == 4
+    assert bench.auto_merge("beam", 20) == 5 and bench.auto_merge("beam", 5) == 5 and bench.auto_merge("beam", 4) == 4
     # a rank's strong-scaling shard (256 / N images): more batches per call, same rows
-    assert bench.auto_merge("greedy", 80, 32) == 80 and bench.auto_merge("beam", 32, 32) == 32 and bench.auto_merge("greedy", 20, 128) == 20
+    assert bench.auto_merge("greedy", 80, 32) == 80 and bench.auto_merge("beam", 40, 32) == 40 and bench.auto_merge("greedy", 20, 128) == 20
     for mode in ("greedy", "beam"):
         for batch in (32, 256, 1024):
             tgt = bench.merge_target(mode, batch)

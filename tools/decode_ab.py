@@ -25,7 +25,7 @@ eng.load_state_dict(sd)
 img = synth.make_images(256, 64, 256, seed=2024).cuda()
 ctx, _, _ = eng.encode(img)
 
-BASE = {"stack_mma": 1, "steps_per_graph": 8, "attn_split": 0, "attn_kpi": 4, "split_k": 1, "pdl": 1, "pdl_max_rows": 2560}
+BASE = {"stack_mma": 1, "steps_per_graph": 8, "attn_split": 0, "attn_kpi": 4, "split_k": 1, "pdl": 1, "pdl_max_rows": 2048}
 SETS = [
     ("default", {}),
     ("attn_kpi 2", {"attn_kpi": 2}),
