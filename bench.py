@@ -15,6 +15,10 @@ its own value / ms_per_step / e2e / roofline measured the same way (fewer steps)
     bf16_greedy, bf16_beam5    the single-pass bf16 mode (configs[2]: "bf16")
     strong_greedy, strong_beam5   (N > 1) ONE global batch of 256 sharded 256/N per rank (configs[2] "batch-sharded")
     attnv2_b512    configs[3]: the config/train.yaml default stack, greedy, global batch 512 sharded over the ranks
+    sweep_<H>x<W>_b<B>   configs[4]: points of the beam-5 image-size x batch sweep (B images per GPU)
+The schedule (top-level "schedule" of every record) is the pipelined recognizer: encode(i+1) overlaps decode(i), and
+`decode_merge` encoded batches go to ONE decode call (auto_merge: about 2 560 greedy / 6 400 beam-5 rows per call).  A
+sub-record that fails carries {"error": ...} instead of taking the line with it.
 `--records none` prints the main record only; `--mode/--precision/...` change what the MAIN record measures.
 """
 from __future__ import annotations
