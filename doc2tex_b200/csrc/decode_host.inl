@@ -183,7 +183,9 @@ int enqueue_tfm_step(d2t_engine* e, const TfmBuffers& b, int R, int B, int ntok,
     const bool wide = b.planes && e->wide_decode && e->tc3.count(g.w) &&
                       (long long)((R + TC_BM - 1) / TC_BM) * ((g.N + 127) / 128) > e->active_sms;
     if (!wide) return from_x(g);
+    ConvGemm keep = g;
     g.x_hi = b.x_hi; g.x_lo = b.x_lo; g.B = 1; g.W = R; g.OW = R;
+    if (!routes_to_tc3(e, g)) { g = keep; return from_x(g); }   // e.g. option "tc3" off: stay on the former path
     // 128-wide single-CTA tiles (two epilogue warps per TMEM quadrant): with K = 256 these problems are bound by their epilogue
     // and the pair kernel's 256 x 256 tiles quantise badly (lin1 at 5 120 rows: 80 tiles on 74 pairs, 34 us — no gain)
     g.single_cta = 1;

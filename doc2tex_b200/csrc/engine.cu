@@ -498,6 +498,9 @@ int linear(d2t_engine* e, const float* x, const std::string& wkey, const std::st
     // rows as the pixels of ONE image row (B = 1, H = 1, W = M): the TMA im2col load of a 1x1 "convolution" walks 128 rows
     p.x_hi = pl->x_hi; p.x_lo = pl->x_lo; p.out_hi = pl->out_hi; p.out_lo = pl->out_lo;
     p.B = 1; p.W = M; p.OW = M;
+    // only the plane kernels tolerate a missing fp32 input / output: refuse instead of dereferencing a null pointer
+    if ((x == nullptr || out == nullptr) && !routes_to_tc3(e, p))
+      return e->fail(D2T_ERR_STATE, "internal: Linear '%s' on operand planes cannot run on the plane kernels", wkey.c_str());
   }
   return run_contraction(e, p, nullptr, e->cfg.precision, s);
 }

@@ -207,3 +207,25 @@ def test_vit_linears_on_operand_planes_match_gather_path(built_lib, precision, B
     for mode in (1, 2, 3):
         assert torch.isfinite(out[mode]).all()
         assert rel_err(out[mode], out[0]) < tol, (mode, rel_err(out[mode], out[0]))
+
+
+def test_plane_paths_fall_back_when_the_plane_kernels_are_off(built_lib):
+    """Option tc3 = 0 switches the cp.async / TMA-fed plane kernels off: the ViT Linears (vit_planes) and the wide decode
+    projections (wide_decode) must fall back to the register-gather / one-tile kernels instead of handing them a missing fp32
+    tensor; results stay within the fp32-parity tolerance of the default path."""
+    from doc2tex_b200.engine import Engine
+    cfg, sd = state_dict_for("TFM", 1.5)
+    img = synth.make_images(4, 64, 256, seed=3).cuda()
+    out = {}
+    for tc3 in (1, 0):
+        e = Engine(cfg, "cuda:0", precision="bf16x3")
+        e.load_state_dict(sd)
+        e.set_option("tc3", tc3)
+        ctx, _, _ = e.encode(img)
+        wide = ctx[:1].repeat(2560, 1, 1).contiguous()      # lin1: 20 x 8 = 160 tiles > 148 SMs
+        ids, logits, _ = e.decode_greedy(wide, max_steps=3, is_test=False)
+        out[tc3] = (ctx.cpu(), ids.cpu(), logits[:8].cpu())
+        e.close()
+    assert rel_err(out[0][0], out[1][0]) < 1e-4
+    assert torch.equal(out[0][1], out[1][1])
+    assert rel_err(out[0][2], out[1][2]) < 1e-4
