@@ -15,6 +15,7 @@ its own value / ms_per_step / e2e / roofline measured the same way (fewer steps)
     bf16_greedy, bf16_beam5    the single-pass bf16 mode (configs[2]: "bf16")
     strong_greedy, strong_beam5   (N > 1) ONE global batch of 256 sharded 256/N per rank (configs[2] "batch-sharded")
     attnv2_b512    configs[3]: the config/train.yaml default stack, greedy, global batch 512 sharded over the ranks
+    natural_greedy, natural_beam5   the "natural" decode-length regime (unmodified END logit, the reference's early exit)
     sweep_<H>x<W>_b<B>   configs[4]: points of the beam-5 image-size x batch sweep (B images per GPU)
 The schedule (top-level "schedule" of every record) is the pipelined recognizer: encode(i+1) overlaps decode(i), and
 `decode_merge` encoded batches go to ONE decode call (auto_merge: about 2 560 greedy / 6 400 beam-5 rows per call).  A
@@ -74,7 +75,7 @@ def parse():
                     help="encode decode_merge batches back to back on all SMs, then decode them in one call (no stage overlap)")
     ap.add_argument("--sequential", action="store_true", help="no encode/decode overlap across batches")
     ap.add_argument("--records", default="all",
-                    help="'all', 'none' or a comma list of beam5,bf16_greedy,bf16_beam5,strong_greedy,strong_beam5,attnv2_b512,"
+                    help="'all', 'none' or a comma list of beam5,bf16_greedy,bf16_beam5,strong_greedy,strong_beam5,attnv2_b512,natural_greedy,natural_beam5,"
                          "sweep_<H>x<W>_b<images per GPU> (beam-5, BASELINE configs[4])")
     ap.add_argument("--record-steps", type=int, default=0, help="timed steps of each sub-record (0 = min(steps, 4))")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (d2t_set_option), repeatable")
@@ -480,8 +481,9 @@ def run_engine(args):
     line = b.measure(args.head, args.mode, args.precision, args.batch, args.steps, args.warmup, main=True)
     want = args.records
     names = [] if want == "none" else (
-        ["beam5", "bf16_greedy", "bf16_beam5", "strong_greedy", "strong_beam5", "attnv2_b512", "sweep_64x256_b32",
-         "sweep_64x256_b1024", "sweep_128x512_b128", "sweep_192x896_b64"] if want == "all" else want.split(","))
+        ["beam5", "bf16_greedy", "bf16_beam5", "strong_greedy", "strong_beam5", "attnv2_b512", "natural_greedy", "natural_beam5",
+         "sweep_64x256_b32", "sweep_64x256_b1024", "sweep_96x384_b256", "sweep_128x512_b128", "sweep_160x704_b64",
+         "sweep_192x896_b64"] if want == "all" else want.split(","))
     # sub-records: two full merged decode groups when the main record has that many steps (the second group's encodes overlap
     # the first group's decode, as in the main record), else what the main record runs
     rs = args.record_steps if args.record_steps > 0 else min(args.steps, 10)
@@ -511,6 +513,15 @@ def run_engine(args):
             r["scaling"] = "strong"
             r["config"]["global_batch"] = max(1, 512 // world) * world
             return r
+        if name in ("natural_greedy", "natural_beam5"):
+            # SURVEY 8d's second decode-length regime: unmodified END logit, early exit as in the reference (tfm.py:138-140, 174)
+            keep = args.natural
+            args.natural = True
+            try:
+                return b.measure("TFM", "greedy" if name == "natural_greedy" else "beam", "bf16x3", args.batch,
+                                 rs_g if name == "natural_greedy" else rs, 3)
+            finally:
+                args.natural = keep
         if name.startswith("sweep_"):
             # BASELINE configs[4]: beam-5 over image sizes / batches, e.g. sweep_192x896_b64 (images per GPU; weak scaling)
             hw, bs = name[len("sweep_"):].split("_b")
