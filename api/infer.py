@@ -96,24 +96,36 @@ def run_infer(model, rows, converter, config, args):
         os.makedirs(os.path.dirname(args.export_path) or ".", exist_ok=True)
         fo = open(args.export_path, "wt" if args.start_idx == 0 else "at", newline="")
         writer = csv.writer(fo)
+    # The batches of a bucket go through the pipelined recognizer (doc2tex_b200/pipeline.py): encode(i+1) overlaps decode(i),
+    # consecutive batches are decoded in one call (about 2 560 greedy rows / 1 280 beam images per call), and
+    # the (B, l, V) logits tensor that model(image, text) also returns — and this loop never read — is not materialised.
+    # Per-batch results are identical to model(image, text, is_train=False, is_test=True) (tests: merged == sequential).
+    from doc2tex_b200.pipeline import PipelinedRecognizer
+    eng = model.engine
+    beam_size = int(config.get("beam_size", 1) or 1)
+    mode = "beam" if beam_size > 1 else "greedy"
+    bs = int(config["batch_size"])
+    steps = (max_len + 1) if is_attn else None          # Model.forward_decoder: the LSTM heads decode batch_max_length + 1 steps
+    merge = max(1, (1280 if mode == "beam" else 2560) // max(1, bs))
     for (H, W), items in buckets.items():
-        for lo in range(0, len(items), config["batch_size"]):
-            chunk = items[lo: lo + config["batch_size"]]
-            image = torch.stack([c[2] for c in chunk])
-            B = image.size(0)
-            text = torch.zeros(B, max_len + 1, dtype=torch.long, device=device) if is_attn \
-                else torch.full((B, 1), 1, dtype=torch.long, device=device)
-            torch.cuda.synchronize()
+        chunks = [items[lo: lo + bs] for lo in range(0, len(items), bs)]
+        pipe = PipelinedRecognizer(eng, mode, beam_size, steps, is_test=True, return_logits=False, decode_merge=merge)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        results = list(pipe.run(torch.stack([c[2] for c in chunk]) for chunk in chunks))
+        torch.cuda.synchronize()
+        dt_img = (time.time() - t0) / max(1, len(items))
+        infer_time += dt_img * len(items)
+        for chunk, res in zip(chunks, results):
+            B = len(chunk)
+            dt = dt_img * B
             t0 = time.time()
-            preds_index, _, _ = model(image, text, is_train=False, is_test=True)
-            torch.cuda.synchronize()
-            dt = time.time() - t0
-            infer_time += dt
-            t0 = time.time()
-            if isinstance(preds_index, torch.Tensor) and preds_index.dim() == 2:
-                pred_tokens = converter.detokenize(preds_index.cpu())
+            ids = res["ids"].cpu()
+            if mode == "beam":                           # padded to the longest hypothesis: cut every row at its own length
+                lens = res["lens"].cpu().tolist()
+                pred_tokens = converter.detokenize([row[:n_] for row, n_ in zip(ids.tolist(), lens)])
             else:
-                pred_tokens = converter.detokenize(torch.as_tensor(preds_index).reshape(B, -1))
+                pred_tokens = converter.detokenize(ids)
             post_time += time.time() - t0
             for (name, label, _), pred in zip(chunk, pred_tokens):
                 n += 1
