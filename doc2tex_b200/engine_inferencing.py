@@ -189,12 +189,13 @@ class _Mean:
 
 
 def validation_step(model, augment, criterion, evaluation_loader: Iterable, converter, config: dict, args, device,
-                    decode_merge: int = 4, encoder_sms: int | None = 132):
+                    decode_merge: int | None = None, encoder_sms: int | None = 132):
     """validation or evaluation (doc2tex/engine/inferencing.py:12-247) on the engine.
 
     ``model`` is ``doc2tex_b200.modules.build_model.Model``; ``evaluation_loader`` yields ``(image_tensors, labels,
     img_names)`` like the reference's loader (images already on ``device``, one (H, W) per batch).  Batches are pipelined:
-    results come back in order, ``decode_merge`` batches per decode call.
+    results come back in order, ``decode_merge`` batches per decode call (default: as many batches of the loader's batch size
+    as make about 2 560 rows, at most 16 — the row count at which the decode's attention walks are HBM-bound).
     """
     eng = model.engine
     is_attn = "Attn" in config["Prediction"]["name"]
@@ -233,10 +234,15 @@ def validation_step(model, augment, criterion, evaluation_loader: Iterable, conv
 
     # greedy, every one of the T steps (the reference calls model(image, text[, is_train=False]) with is_test=False:
     # no early exit, inferencing.py:73-76 / 151-153), logits kept for the caller's criterion
+    stream = batches()
+    first = next(stream, None)
+    if decode_merge is None:
+        decode_merge = 1 if first is None else max(1, min(16, 2560 // max(1, int(first.shape[0]))))
     pipe = PipelinedRecognizer(eng, "greedy", 1, T, encoder_sms=encoder_sms, is_test=False, return_logits=True,
                                decode_merge=decode_merge)
     start_time = time.time()
-    for k, res in enumerate(pipe.run(batches())):
+    import itertools
+    for k, res in enumerate(pipe.run(itertools.chain([] if first is None else [first], stream))):
         labels, img_names = meta[k]
         preds_index, preds = res["ids"], res["logits"]
         batch_size = preds_index.shape[0]
