@@ -282,7 +282,7 @@ class Bench:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def measure(self, head, mode, precision, batch, steps, warmup, main=False):
+    def measure(self, head, mode, precision, batch, steps, warmup, main=False, encode_merge=1):
         """batch = images per rank.  Returns the record dict (same keys on every rank; timings are max over ranks)."""
         from doc2tex_b200 import dist as d2dist
         from doc2tex_b200.engine import Engine
@@ -308,7 +308,8 @@ class Bench:
         img_dev = img_host.to(dev)
         merge = a.decode_merge if a.decode_merge > 0 else auto_merge(mode, steps, batch)
         pipe = PipelinedRecognizer(eng, mode, a.beam, T, encoder_sms=None if a.sequential else a.encoder_sms,
-                                   decode_merge=1 if a.sequential else merge, overlap=not a.no_overlap)
+                                   decode_merge=1 if a.sequential else merge, overlap=not a.no_overlap,
+                                   encode_merge=1 if a.sequential else encode_merge)
         if a.no_overlap and not a.sequential:
             eng.set_option("encoder_sms", self.sms)
 
@@ -460,7 +461,8 @@ class Bench:
                 (f"grouped: {merge} batches encoded back to back on all SMs, then decoded in one call; one batch "
                  f"alone takes {seq_ms:.1f} ms") if a.no_overlap else
                 f"pipelined: encode on {a.encoder_sms} SMs overlaps the decode of the previous batches, {merge} encoded "
-                f"batch(es) per decode call; one batch alone takes {seq_ms:.1f} ms (encode {enc_ms:.1f} + decode {dec_ms:.1f})"),
+                f"batch(es) per decode call" + (f", {encode_merge} per encode call" if encode_merge > 1 else "") +
+                f"; one batch alone takes {seq_ms:.1f} ms (encode {enc_ms:.1f} + decode {dec_ms:.1f})"),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "formulas/s", "h2d_bytes_per_step": img_host.numel() * 4,
                     "d2h_bytes_per_step": B * world * (T + 2) * 8 if world > 1 else B * T * 8},
@@ -503,7 +505,9 @@ def run_engine(args):
             # the timed steps are one full merge group (at least the usual record length)
             mode_s = "greedy" if name == "strong_greedy" else "beam"
             shard = max(1, 256 // world)
-            r = b.measure("TFM", mode_s, "bf16x3", shard, max(rs_g if mode_s == "greedy" else rs, merge_target(mode_s, shard)), 3)
+            # ... and consecutive shards are ENCODED together up to 256 images (the stem's tiles quantise over the SMs at 32)
+            r = b.measure("TFM", mode_s, "bf16x3", shard, max(rs_g if mode_s == "greedy" else rs, merge_target(mode_s, shard)), 3,
+                          encode_merge=max(1, 256 // shard))
             r["scaling"] = "strong"
             r["config"]["global_batch"] = max(1, 256 // world) * world
             return r

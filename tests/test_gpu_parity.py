@@ -475,14 +475,15 @@ def test_merged_decode_schedule_equals_sequential(built_lib, merge):
         b = e.decode_beam(ctx, 5)
         seq.append((ids[:, :steps].clone(), steps, b[0].clone(), b[1].clone(), b[2].clone()))
     for mode in ("greedy", "beam"):
-        pipe = PipelinedRecognizer(e, mode, 5, None, encoder_sms=120, decode_merge=merge)
-        outs = list(pipe.run(batches))
-        assert len(outs) == 5
-        for (g_ids, g_steps, b_ids, b_len, b_sc), res in zip(seq, outs):
-            if mode == "greedy":
-                assert res["steps"] == g_steps and torch.equal(res["ids"], g_ids)
-            else:
-                assert torch.equal(res["ids"], b_ids) and torch.equal(res["lens"], b_len) and torch.equal(res["scores"], b_sc)
+        for enc_merge in (1, 2):   # encode_merge: consecutive input batches also share one ENCODE call (rows are independent)
+            pipe = PipelinedRecognizer(e, mode, 5, None, encoder_sms=120, decode_merge=merge, encode_merge=enc_merge)
+            outs = list(pipe.run(batches))
+            assert len(outs) == 5
+            for (g_ids, g_steps, b_ids, b_len, b_sc), res in zip(seq, outs):
+                if mode == "greedy":
+                    assert res["steps"] == g_steps and torch.equal(res["ids"], g_ids)
+                else:
+                    assert torch.equal(res["ids"], b_ids) and torch.equal(res["lens"], b_len) and torch.equal(res["scores"], b_sc)
     e.set_option("encoder_sms", 148)
 
 
