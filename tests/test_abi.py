@@ -63,3 +63,23 @@ def test_sass_has_blackwell_tensor_and_tma_instructions(built_lib):
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnemonic in sass, mnemonic
     assert "sm_100a" in sass or "SM100" in sass.upper()
+
+
+def test_every_engine_option_is_documented_in_the_header():
+    """d2t_set_option is the only switchboard of the engine (nothing is read from the environment): every key it accepts must
+    be described in include/doc2tex_b200.h, and the sources must not read environment variables."""
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "doc2tex_b200", "csrc", "engine.cu")).read()
+    hdr = open(os.path.join(root, "include", "doc2tex_b200.h")).read()
+    seg = src[src.index("int d2t_set_option("):]
+    seg = seg[: seg.index("\nint d2t_", 10)]
+    keys = re.findall(r'k == "([a-z_0-9]+)"', seg)
+    assert len(keys) >= 20
+    missing = [k for k in keys if f'"{k}"' not in hdr]
+    assert not missing, f"options missing from the header: {missing}"
+    csrc = os.path.join(root, "doc2tex_b200", "csrc")
+    for f in os.listdir(csrc):
+        text = open(os.path.join(csrc, f)).read()
+        assert text.count("getenv") <= (1 if f == "engine.cu" else 0), f   # D2T_DBG_ACT inside the debug GEMM bench hook only
